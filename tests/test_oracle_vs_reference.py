@@ -1,0 +1,117 @@
+"""Pins the oracle restatement bit-for-bit against the imported reference (build container only).
+
+On machines without /root/reference (the GPU box) these tests skip; tests/test_golden.py then
+pins the oracle against fixtures minted here from the same reference.
+"""
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from oracle import ref_import as R
+from smpl_nerf_b200 import scene
+
+KINDS = ['nerf', 'append', 'smpl']
+
+
+def _run_oracle(kind, nets, args, data, **kw):
+    c, f, w, pe, de, he = nets
+    if kind == 'nerf':
+        return O.nerf_forward(c, f, pe, de, args, data, **kw)
+    if kind == 'append':
+        return O.append_to_nerf_forward(c, f, pe, de, he, args, data, **kw)
+    return O.smpl_nerf_forward(c, f, w, pe, de, he, args, data, **kw)
+
+
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('variant', ['default', 'dense', 'sharp'])
+def test_pipeline_bit_exact(reference, kind, variant):
+    rays = scene.make_rays(12, 12, 64, seed=3)
+    mine = O.build_nets(kind, 7, variant)
+    theirs = O.build_nets(kind, 7, variant, net_cls=reference.RenderRayNet,
+                          warp_cls=reference.WarpFieldNet, enc_cls=reference.PositionalEncoder)
+    assert O.weight_checksum(list(mine[:3])) == O.weight_checksum(list(theirs[:3]))
+    for run_fine in (1, 0):
+        args = O.make_args(run_fine=run_fine)
+        data = scene.data_list(rays, kind, slice(0, 48))
+        with torch.no_grad():
+            want = R.build_pipeline(kind, *theirs, args)(data)
+            got = O.as_tuple(_run_oracle(kind, mine, args, data))
+        assert len(want) == len(got)
+        for a, b in zip(want, got):
+            assert a.shape == b.shape and torch.equal(a, b)
+
+
+@pytest.mark.parametrize('kind', ['append', 'smpl'])
+def test_raw_pose_variant_bit_exact(reference, kind):
+    """human_pose_encoding=0 (raw 2-dim pose); for smpl only run_fine=0 is well-formed in the reference."""
+    rays = scene.make_rays(8, 8, 64, seed=5)
+    kw = dict(pose_encoded=False)
+    mine = O.build_nets(kind, 11, 'dense', **kw)
+    theirs = O.build_nets(kind, 11, 'dense', net_cls=reference.RenderRayNet,
+                          warp_cls=reference.WarpFieldNet, enc_cls=reference.PositionalEncoder, **kw)
+    args = O.make_args(human_pose_encoding=0, run_fine=0 if kind == 'smpl' else 1)
+    data = scene.data_list(rays, kind)
+    with torch.no_grad():
+        want = R.build_pipeline(kind, *theirs, args)(data)
+        got = O.as_tuple(_run_oracle(kind, mine, args, data))
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+
+
+def test_cfg1_shape_bit_exact(reference):
+    """BASELINE config 1: depth 4, no skips, 32 coarse samples, run_fine=0."""
+    rays = scene.make_rays(8, 8, 32, seed=1)
+    kw = dict(n_layers=4, skips=())
+    mine = O.build_nets('nerf', 2, 'dense', **kw)
+    theirs = O.build_nets('nerf', 2, 'dense', net_cls=reference.RenderRayNet,
+                          warp_cls=reference.WarpFieldNet, enc_cls=reference.PositionalEncoder, **kw)
+    args = O.make_args(run_fine=0)
+    data = scene.data_list(rays, 'nerf')
+    with torch.no_grad():
+        want = R.build_pipeline('nerf', *theirs, args)(data)
+        got = O.as_tuple(_run_oracle('nerf', mine, args, data))
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+
+
+def test_stage_functions_bit_exact(reference):
+    torch.manual_seed(0)
+    args = O.make_args()
+    raw = torch.randn(40, 64, 4)
+    z = torch.sort(torch.rand(40, 64) * 3 + 1, -1)[0]
+    dirs = torch.randn(40, 64, 3)
+    for white in (0, 1):
+        args.white_background = white
+        want = reference.raw2outputs(raw, z, dirs, args)
+        got = O.composite(raw, z, dirs, white_background=white)
+        for a, b in zip(want, got):
+            assert torch.equal(a, b)
+    w = torch.rand(40, 62) ** 4
+    w[3] = 0
+    w[4, 10:] = 0
+    bins = .5 * (z[:, 1:] + z[:, :-1])
+    assert torch.equal(reference.sample_pdf(bins, w, args), O.inverse_cdf(bins, w, 128))
+    for L, ident in ((10, False), (4, False), (3, True), (0, True)):
+        x = torch.randn(5, 7, 3) * 3
+        assert torch.equal(reference.PositionalEncoder(L, ident).encode(x), O.Encoder(L, ident).encode(x))
+
+
+def test_sigma_noise_same_draw(reference):
+    """With sigma_noise_std>0 the reference draws N(0,std) inside raw2outputs; feeding the oracle the
+    same draw reproduces it bit-for-bit (the engine takes the draw as an input tensor too)."""
+    rays = scene.make_rays(6, 6, 64, seed=2)
+    mine = O.build_nets('nerf', 3, 'dense')
+    theirs = O.build_nets('nerf', 3, 'dense', net_cls=reference.RenderRayNet,
+                          warp_cls=reference.WarpFieldNet, enc_cls=reference.PositionalEncoder)
+    args = O.make_args(sigma_noise_std=1.0)
+    data = scene.data_list(rays, 'nerf')
+    B = data[0].shape[0]
+    with torch.no_grad():
+        torch.manual_seed(123)
+        want = R.build_pipeline('nerf', *theirs, args)(data)
+        torch.manual_seed(123)
+        n_c = torch.normal(0, args.sigma_noise_std, (B, 64))
+        n_f = torch.normal(0, args.sigma_noise_std, (B, 192))
+        got = O.as_tuple(O.nerf_forward(mine[0], mine[1], mine[3], mine[4], args, data, noise_coarse=n_c, noise_fine=n_f))
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
