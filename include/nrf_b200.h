@@ -1,0 +1,165 @@
+/* nrf_b200.h -- C ABI of the B200-native NeRF volume-rendering engine (libnrf_b200.so).
+ *
+ * Drop-in boundary for the hot path of HannesStark/SMPL-NeRF (citations are paths in that repo):
+ *
+ *   models/nerf_pipeline.py:14-67, models/smpl_nerf_pipeline.py:16-100,
+ *   models/append_to_nerf_pipeline.py:14-90          -> nrf_render()           (one fused kernel)
+ *   models/render_ray_net.py:6-61 (weights, [out,in])  -> nrf_pack_raynet()      (fp32 -> packed fp16 hi/lo)
+ *   models/warp_field_net.py:6-21                      -> nrf_pack_warpnet()
+ *   utils.py:114-131  PositionalEncoder.encode         -> nrf_positional_encoding()
+ *   utils.py:134-191  raw2outputs                      -> nrf_raw2outputs()
+ *   utils.py:194-228  sample_pdf                       -> nrf_sample_pdf()
+ *   torchsearchsorted/src/cuda/searchsorted_cuda_wrapper.cpp:18-20
+ *       searchsorted_cuda_wrapper(a, v, res, side_left) -> nrf_searchsorted()
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name says host
+ *   - all tensors are contiguous row-major fp32 (int64 for searchsorted results), as the reference's
+ *     collate + .to(device) produces them
+ *   - nothing here allocates device memory or synchronises: work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*); outputs and the workspace are caller-owned
+ *   - return value 0 = ok, negative = error (NRF_E_*); nrf_last_error() gives the per-thread message
+ *   - re-entrant per device; no global mutable state besides the per-thread error string
+ */
+#ifndef NRF_B200_H_
+#define NRF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRF_ABI_VERSION 1
+
+enum {
+  NRF_OK = 0,
+  NRF_E_INVALID = -1,     /* bad argument / unsupported shape (message says which) */
+  NRF_E_CUDA = -2,        /* a CUDA runtime call failed (message carries cudaGetErrorString) */
+  NRF_E_UNSUPPORTED = -3, /* device is not sm_100 */
+};
+
+enum { NRF_KIND_NERF = 0, NRF_KIND_SMPL = 1, NRF_KIND_APPEND = 2 };
+
+#define NRF_MAX_SKIPS 4
+
+/* RenderRayNet hyper-parameters (models/render_ray_net.py:8-17) + the encoders that feed it
+ * (utils.py:115-125).  positions_dim must equal 3*(pos_identity + 2*pos_freqs), directions_dim
+ * 3*(dir_identity + 2*dir_freqs): the engine computes the encodings itself. */
+typedef struct NrfRayNetDesc {
+  int32_t n_layers;              /* netdepth (>= 2)                                   */
+  int32_t width;                 /* netwidth; this build supports 256                 */
+  int32_t positions_dim;         /* 60                                                */
+  int32_t directions_dim;        /* 24                                                */
+  int32_t additional_input_dim;  /* A: pose features prepended to the xyz encoding     */
+  int32_t use_directional_input; /* 0/1                                               */
+  int32_t n_skips;
+  int32_t skips[NRF_MAX_SKIPS];  /* indices into positional_net                       */
+  int32_t pos_freqs, pos_identity;
+  int32_t dir_freqs, dir_identity;
+  int32_t per_sample_dirs;       /* 1: directions differ per sample (SmplNerfPipeline) */
+} NrfRayNetDesc;
+
+/* WarpFieldNet (models/warp_field_net.py:8-15): Linear(positions_dim + pose_dim -> width), ReLU,
+ * Linear(width -> 3).  in_freqs/in_identity describe how xyz is encoded for it (10/0 when
+ * human_pose_encoding=1, 0/1 = raw xyz otherwise). */
+typedef struct NrfWarpNetDesc {
+  int32_t width;         /* 256 */
+  int32_t positions_dim; /* 3*(in_identity + 2*in_freqs) */
+  int32_t pose_dim;      /* per-ray pose features appended after the xyz features */
+  int32_t in_freqs, in_identity;
+} NrfWarpNetDesc;
+
+typedef struct NrfPipelineDesc {
+  int32_t kind;             /* NRF_KIND_*                                              */
+  int32_t n_coarse;         /* samples per ray in ray_samples / z_vals                 */
+  int32_t n_fine;           /* args.number_fine_samples (ignored when run_fine == 0)   */
+  int32_t run_fine;         /* args.run_fine                                           */
+  int32_t white_background; /* args.white_background                                   */
+  int32_t pose_freqs, pose_identity; /* human_pose_encoder                             */
+  int32_t pose_encoded;     /* args.human_pose_encoding                                */
+  int32_t pose_stride;      /* floats per row of goal_pose (69)                        */
+  int32_t pose_col0, pose_col1; /* the two columns the pipelines read (38, 41)         */
+  int32_t precision;        /* 0 = parity (fp16 hi/lo split, 3 MMA passes); 1 = fast (1 pass) */
+} NrfPipelineDesc;
+
+/* Inputs/outputs of one render call.  NULL is allowed where marked optional. */
+typedef struct NrfRenderIO {
+  /* inputs */
+  const float* ray_samples;  /* [B, n_coarse, 3]                                             */
+  const float* ray_origin;   /* [B, 3]  ("ray_translation")                                 */
+  const float* ray_dir;      /* [B, 3]                                                       */
+  const float* z_vals;       /* [B, n_coarse]                                                */
+  const float* goal_pose;    /* [B, pose_stride]  (smpl / append kinds)                      */
+  const float* u_fine;       /* [n_fine] = torch.linspace(0,1,n_fine) (utils.py:206)         */
+  const float* noise_coarse; /* optional [B, n_coarse]: N(0,sigma_noise_std) draw (utils.py:174) */
+  const float* noise_fine;   /* optional [B, n_coarse+n_fine]                                */
+  const float* z_all_in;     /* optional [B, n_coarse+n_fine]: use these fine depths instead of
+                                sampling (stage-wise parity tests, "teacher forcing")        */
+  /* outputs (fp32) */
+  float* rgb;         /* [B,3] coarse colour                                                 */
+  float* rgb_fine;    /* [B,3] (run_fine=0: may be NULL; the pipelines return rgb twice)     */
+  float* samples_out; /* [B,n,3] fine sample points (run_fine=1; n = n_coarse+n_fine)        */
+  float* alpha_out;   /* [B,n]   "densities" = alpha of the last pass                        */
+  float* warp_out;    /* [B,n,3] smpl kind: warp of the last pass                            */
+  float* warped_out;  /* [B,n,3] smpl kind: warped samples of the last pass                  */
+  /* optional debug taps */
+  float* raw_coarse;     /* [B,n_coarse,4] (rgb_raw, sigma_raw) of the coarse net            */
+  float* raw_fine;       /* [B,n,4]                                                          */
+  float* weights_coarse; /* [B,n_coarse]                                                     */
+  float* z_new;          /* [B,n_fine] inverse-CDF samples before the merge                  */
+  float* z_all;          /* [B,n] merged depths                                              */
+  int32_t* status;       /* optional [1]: bit0 set if an activation left the fp16 range      */
+} NrfRenderIO;
+
+const char* nrf_last_error(void);
+int nrf_abi_version(void);
+/* 0 if device `dev` can run the engine (compute capability 10.x), NRF_E_UNSUPPORTED otherwise. */
+int nrf_device_supported(int dev);
+
+/* Size in bytes of the packed form of a net (device buffer the caller allocates, 1024-aligned). */
+size_t nrf_raynet_packed_bytes(const NrfRayNetDesc* d);
+size_t nrf_warpnet_packed_bytes(const NrfWarpNetDesc* d);
+
+/* Pack fp32 nn.Linear parameters ([out,in] row-major weights, biases) into the engine's layout.
+ * `params` is a HOST array of DEVICE pointers in state_dict order:
+ *   positions_pose_input.{weight,bias}, positional_net.{0..n_layers-2}.{weight,bias},
+ *   additional_linear_layer.{weight,bias}, sigma_out_layer.{weight,bias},
+ *   directional_input.{weight,bias}, directional_net.0.{weight,bias}, rgb_out_layer.{weight,bias}
+ * Must be re-run whenever the parameters change (optimizer step, load_state_dict). */
+int nrf_pack_raynet(const NrfRayNetDesc* d, const float* const* params, int n_params, void* packed, void* stream);
+/* params: linear1.{weight,bias}, linear2.{weight,bias} */
+int nrf_pack_warpnet(const NrfWarpNetDesc* d, const float* const* params, int n_params, void* packed, void* stream);
+
+/* The fused forward of the three pipelines for B rays.  packed_warp/warp may be NULL unless
+ * kind == NRF_KIND_SMPL.  n_sms <= 0 means "all SMs of the current device". */
+int nrf_render(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, const void* packed_coarse,
+               const NrfRayNetDesc* fine, const void* packed_fine, const NrfWarpNetDesc* warp,
+               const void* packed_warp, const NrfRenderIO* io, int64_t n_rays, int n_sms, void* stream);
+
+/* Number of kernels nrf_render launches per call (for bench.py's gpu_launches accounting). */
+int nrf_render_launches(void);
+
+/* ---- stand-alone ops (same arithmetic as the fused kernel's stages) ---- */
+/* utils.py:127-131: x[n, c] -> out[n, c*(identity + 2*freqs)] */
+int nrf_positional_encoding(const float* x, int64_t n, int32_t c, int32_t freqs, int32_t identity, float* out,
+                            void* stream);
+/* utils.py:134-191: raw[B,n,4], z[B,n], dirs[B,n,3], optional noise[B,n] -> rgb[B,3], weights[B,n], alpha[B,n] */
+int nrf_raw2outputs(const float* raw, const float* z, const float* dirs, const float* noise, int64_t B, int32_t n,
+                    int32_t white_background, float* rgb, float* weights, float* alpha, void* stream);
+/* utils.py:194-228: bins[B,m], weights[B,m-1], u[n_fine] -> samples[B,n_fine] */
+int nrf_sample_pdf(const float* bins, const float* weights, const float* u, int64_t B, int32_t m, int32_t n_fine,
+                   float* samples, void* stream);
+/* torchsearchsorted: a[rows_a, na], v[rows_v, nv] (rows broadcast when one side has 1 row) -> res int64 */
+int nrf_searchsorted(const float* a, int64_t rows_a, int64_t na, const float* v, int64_t rows_v, int64_t nv,
+                     int64_t* res, int32_t side_left, void* stream);
+
+/* tcgen05 self-test: D[128,128] = A[128,64] * B[128,64]^T with fp16 operands staged through the same
+ * swizzled shared-memory layout / descriptors the renderer uses.  a, b: fp32 (rounded to fp16 inside). */
+int nrf_selftest_umma(const float* a, const float* b, float* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRF_B200_H_ */

@@ -1,0 +1,679 @@
+// The fused SMPL-NeRF forward: ONE persistent kernel per ray batch.
+//
+// Replaces (file:line in HannesStark/SMPL-NeRF)
+//   models/nerf_pipeline.py:26-67, models/smpl_nerf_pipeline.py:27-100,
+//   models/append_to_nerf_pipeline.py:25-90      (orchestration)
+//   utils.py:114-131 (positional encoding), models/render_ray_net.py:42-61 and
+//   models/warp_field_net.py:17-21 (MLPs), utils.py:134-191 (compositing),
+//   utils.py:194-264 + torchsearchsorted (inverse-CDF sampling, sort-merge).
+//
+// Work item = a group of G rays (G * n_coarse <= 128) owned by one CTA from the coarse pass to the
+// final colour, so no [rays x samples x features] tensor ever exists in HBM.
+//
+// CTA = 10 warps, warp-specialised:
+//   warp 0      weight producer: streams pre-swizzled fp16 hi/lo weight stages L2 -> SMEM ring with
+//               1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx)
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, fp16 x fp16 -> fp32 in TMEM);
+//               fp32-level accuracy comes from the split  x*w ~= xh*wh + xl*wh + xh*wl  (3 passes)
+//   warps 2..9  "epilogue" warps (thread = one sample row x half of the columns): positional
+//               encoding -> SMEM operand tiles, TMEM -> bias/ReLU/hi-lo split -> next layer's A
+//               operand (in place), sigma / rgb / warp heads as fp32 dot products, then per ray:
+//               alpha compositing, inverse-CDF sampling, sorted merge.
+// Two 256-column TMEM accumulators ping-pong between consecutive layers, and activations are handed
+// to the MMA issuer per 64-feature K-chunk, so layer l+1's MMAs start while layer l's epilogue is
+// still draining.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "nrf_plan.h"
+#include "nrf_ptx.cuh"
+#include "nrf_stages.cuh"
+
+namespace nrf {
+
+constexpr int kNumStages = 3;
+constexpr uint32_t kStageBytes = 16384;            // 128 rows x 128 B
+constexpr uint32_t kChunkBytes = 16384;            // one [128 x 64] fp16 operand tile
+constexpr uint32_t kOffA = 0;                      // 4 chunks x (hi, lo)
+constexpr uint32_t kOffAux = 4 * 2 * kChunkBytes;  // 131072
+constexpr uint32_t kOffRing = kOffAux + 2 * kChunkBytes;
+constexpr uint32_t kOffMisc = kOffRing + kNumStages * kStageBytes;  // 212992
+constexpr uint32_t kSmemLimit = 232448;            // 227 KB opt-in maximum per CTA
+constexpr int kEpiThreads = 256;
+constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kRayVec = 8 + kMaxRayFeat + 32;      // unit direction[3], raw pose pair[2]
+constexpr int kRayFloats = kRayVec + 8;            // o[3] d[3] |d| valid | pose feats[64] | dir feats[32] | unit d, pose
+
+// barrier slots inside the misc area (8 bytes each)
+enum { BAR_FULL = 0, BAR_EMPTY = kNumStages, BAR_ACC = 2 * kNumStages, BAR_AREADY = 2 * kNumStages + 2,
+       BAR_COUNT = 2 * kNumStages + 2 + 5 };
+
+struct RenderParams {
+  NetPlan net[2];
+  NetPlan warp;
+  const uint8_t* blob[3];
+  NrfRenderIO io;
+  int64_t n_rays;
+  int32_t kind, n_coarse, n_fine, n_all, run_fine, white_bkgd, fast;
+  int32_t pose_freqs, pose_identity, pose_encoded, pose_stride, pose_col0, pose_col1, pose_dim;
+  int32_t G, tiles_f, n_groups;
+  // float offsets inside the misc area (after the barriers)
+  uint32_t o_ray, o_rb, o_rbw, o_raw, o_zc, o_zf, o_dnorm, o_scratch;
+};
+
+struct Smem {
+  uint8_t* base;
+  float* misc;
+  __device__ uint32_t bar(int i) const { return smem_u32(base + kOffMisc) + 8u * i; }
+};
+
+// ---------------------------------------------------------------------------------- small helpers
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Write 8 consecutive features (one 16-byte swizzle chunk `cc` of row `row`) as hi/lo fp16 into an
+// operand tile pair (hi tile at `tile`, lo tile at `tile + kChunkBytes`).
+__device__ __forceinline__ void store_feat8(uint32_t tile, int row, int cc, const float (&x)[8], bool fast) {
+  __half h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_f16(x[i], h[i], l[i]);
+  const uint32_t ofs = static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>((cc ^ row) & 7) << 4);
+  st_shared_v4(tile + ofs, pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+  if (!fast)
+    st_shared_v4(tile + kChunkBytes + ofs, pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7]));
+}
+
+// Encoder features [32*HSEL, 32*HSEL+32) of vector v in ENGINE order (see enc_ref_col) -> aux tile.
+template <int HSEL>
+__device__ __forceinline__ void write_encoding_half(uint32_t aux_tile, int row, float vx, float vy, float vz, int freqs,
+                                                    int identity, bool fast) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = 16 * HSEL + 4 * q + i;   // (freq, comp) pair index; compile-time after unrolling
+      const int k = p / 3, comp = p % 3;
+      const float v = comp == 0 ? vx : (comp == 1 ? vy : vz);
+      if (p < 3 * freqs) {
+        float s, c;
+        sincosf(v * static_cast<float>(1u << k), &s, &c);
+        f[2 * i] = s; f[2 * i + 1] = c;
+      } else {
+        const int c0 = 2 * p - 6 * freqs;   // identity components follow the sin/cos block
+        const float id0 = (identity && c0 >= 0 && c0 < 3) ? (c0 == 0 ? vx : (c0 == 1 ? vy : vz)) : 0.f;
+        const int c1 = c0 + 1;
+        const float id1 = (identity && c1 >= 0 && c1 < 3) ? (c1 == 0 ? vx : (c1 == 1 ? vy : vz)) : 0.f;
+        f[2 * i] = id0; f[2 * i + 1] = id1;
+      }
+    }
+    store_feat8(aux_tile, row, 4 * HSEL + q, f, fast);
+  }
+}
+__device__ __forceinline__ void write_encoding(uint32_t aux_tile, int row, int hsel, float vx, float vy, float vz, int freqs,
+                                               int identity, bool fast) {
+  if (hsel == 0) write_encoding_half<0>(aux_tile, row, vx, vy, vz, freqs, identity, fast);
+  else write_encoding_half<1>(aux_tile, row, vx, vy, vz, freqs, identity, fast);
+}
+
+// ---------------------------------------------------------------------------------- roles
+struct RingState { uint32_t stage = 0, phase = 0; __device__ void advance() { if (++stage == kNumStages) { stage = 0; phase ^= 1; } } };
+
+__device__ __forceinline__ void producer_layer(const Smem& sm, const uint8_t* blob, const Layer& L, RingState& rs, bool fast) {
+  const uint32_t stage_bytes = (L.n_out / 2u) * 128u;
+  const uint8_t* src = blob + L.stream_ofs;
+  for (int kc = 0; kc < L.nk; ++kc) {
+    for (int part = 0; part < 4; ++part, src += stage_bytes) {
+      if (fast && part >= 2) continue;
+      mbar_wait(sm.bar(BAR_EMPTY + rs.stage), rs.phase ^ 1);
+      mbar_arrive_expect_tx(sm.bar(BAR_FULL + rs.stage), stage_bytes);
+      bulk_g2s(smem_u32(sm.base + kOffRing) + rs.stage * kStageBytes, src, stage_bytes, sm.bar(BAR_FULL + rs.stage));
+      rs.advance();
+    }
+  }
+}
+
+struct MmaState { RingState rs; uint32_t a_phase = 0; uint32_t layer_ctr = 0; };
+
+__device__ __forceinline__ void mma_layer(const Smem& sm, uint32_t tmem_base, const Layer& L, MmaState& st, bool fast) {
+  const uint32_t acc = tmem_base + (st.layer_ctr & 1u) * 256u;
+  const uint32_t n_half = L.n_out / 2u;
+  const uint32_t idesc = umma_idesc_f16(128, n_half);
+  const uint32_t a_base = smem_u32(sm.base);
+  for (int kc = 0; kc < L.nk; ++kc) {
+    const int src = L.ksrc[kc];
+    if (src != kSrcAux || (L.flags & LF_AUX_WAIT)) {
+      mbar_wait(sm.bar(BAR_AREADY + src), (st.a_phase >> src) & 1u);
+      st.a_phase ^= 1u << src;
+      tc_fence_after_sync();
+    }
+    const uint32_t a_hi = a_base + (src == kSrcAux ? kOffAux : kOffA + static_cast<uint32_t>(src) * 2u * kChunkBytes);
+    const uint32_t a_lo = a_hi + kChunkBytes;
+    for (int part = 0; part < 4; ++part) {
+      if (fast && part >= 2) continue;
+      const uint32_t half = part & 1, is_lo = part >> 1;
+      mbar_wait(sm.bar(BAR_FULL + st.rs.stage), st.rs.phase);
+      tc_fence_after_sync();
+      const uint32_t b_addr = a_base + kOffRing + st.rs.stage * kStageBytes;
+      const uint32_t d_tmem = acc + half * n_half;
+      const int n_apass = (is_lo || fast) ? 1 : 2;
+      for (int ap = 0; ap < n_apass; ++ap) {
+        const uint64_t adesc = umma_desc_sw128(ap == 0 ? a_hi : a_lo);
+        const uint64_t bdesc = umma_desc_sw128(b_addr);
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) {
+          const uint32_t accumulate = (kc == 0 && is_lo == 0 && ap == 0 && ks == 0) ? 0u : 1u;
+          umma_f16_ss(d_tmem, adesc + 2u * ks, bdesc + 2u * ks, idesc, accumulate);   // +32 bytes per K=16 step
+        }
+      }
+      umma_commit(sm.bar(BAR_EMPTY + st.rs.stage));   // frees the ring slot when these MMAs are done
+      st.rs.advance();
+    }
+  }
+  umma_commit(sm.bar(BAR_ACC + (st.layer_ctr & 1u)));   // accumulator complete -> epilogue
+  st.layer_ctr++;
+}
+
+// Per-thread state of an epilogue thread.
+struct EpiCtx {
+  int warp, lane, q, hsel, row, tid;   // tid: 0..255 within the epilogue group
+  uint32_t acc_phase = 0;              // bit b: parity to wait for on accumulator b
+  uint32_t layer_ctr = 0;
+  uint32_t tmem_base;
+  uint32_t lane_taddr;                 // TMEM lane field for this warp's quarter
+};
+
+__device__ __forceinline__ void epi_signal(const Smem& sm, const EpiCtx& c, int which) {
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(sm.bar(BAR_AREADY + which));
+}
+
+struct HeadOut { float h0, h1, h2, sig; };
+
+// Epilogue of one MMA layer for this thread's row and its half of the columns.
+//   g: ray index inside the group of this thread's row (for per-ray bias), valid: row has a real sample
+__device__ __forceinline__ void epilogue_layer(const Smem& sm, const RenderParams& P, const NetPlan& net, const float* f32,
+                                               const float* rb_base, const Layer& L, EpiCtx& c, int g, HeadOut& ho,
+                                               bool& overflow) {
+  const uint32_t buf = c.layer_ctr & 1u;
+  const uint32_t acc = c.tmem_base + buf * 256u + c.lane_taddr;
+  const bool fast = P.fast != 0;
+  const int nch = L.n_out >> 6;
+  const bool relu = (L.epi != EPI_LINEAR);
+  const bool write_a = (L.epi == EPI_RELU || L.epi == EPI_LINEAR);
+  const bool head3 = (L.epi == EPI_RGB || L.epi == EPI_WARP);
+  const bool sig_head = (L.flags & LF_SIGMA_HEAD) != 0;
+  const float* bias_g = f32 + L.bias_ofs;
+  const float* bias_s = (L.ray_slot >= 0) ? rb_base + (static_cast<int>(L.ray_slot) * P.G + g) * kWidth : nullptr;
+  const float* wh = f32 + net.head_ofs;     // [3][n_out]
+  const float* ws = f32 + net.sigma_ofs;    // [256]
+  float h0 = 0.f, h1 = 0.f, h2 = 0.f, sg = 0.f, amax = 0.f;
+
+  mbar_wait(sm.bar(BAR_ACC + buf), (c.acc_phase >> buf) & 1u);
+  c.acc_phase ^= 1u << buf;
+  tc_fence_after_sync();
+
+  for (int j = 0; j < nch; ++j) {
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      const int col0 = 64 * j + 32 * c.hsel + 16 * sub;
+      // issue the TMEM load, then fetch biases / head weights while it is in flight
+      uint32_t v[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(acc + static_cast<uint32_t>(col0))
+          : "memory");
+      float b[16];
+      if (bias_s) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = *reinterpret_cast<const float4*>(bias_s + col0 + 4 * i);
+          b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(bias_g + col0) + i);
+          b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+        }
+      }
+      tmem_ld_wait();
+      float x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float t = __uint_as_float(v[i]) + b[i];
+        if (relu) t = fmaxf(t, 0.f);
+        x[i] = t;
+      }
+      if (sig_head) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(ws + col0) + i);
+          sg = fmaf(x[4 * i], w.x, sg); sg = fmaf(x[4 * i + 1], w.y, sg);
+          sg = fmaf(x[4 * i + 2], w.z, sg); sg = fmaf(x[4 * i + 3], w.w, sg);
+        }
+      }
+      if (head3) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wh + col0) + i);
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wh + L.n_out + col0) + i);
+          const float4 w2 = __ldg(reinterpret_cast<const float4*>(wh + 2 * L.n_out + col0) + i);
+          h0 = fmaf(x[4 * i], w0.x, h0); h0 = fmaf(x[4 * i + 1], w0.y, h0); h0 = fmaf(x[4 * i + 2], w0.z, h0); h0 = fmaf(x[4 * i + 3], w0.w, h0);
+          h1 = fmaf(x[4 * i], w1.x, h1); h1 = fmaf(x[4 * i + 1], w1.y, h1); h1 = fmaf(x[4 * i + 2], w1.z, h1); h1 = fmaf(x[4 * i + 3], w1.w, h1);
+          h2 = fmaf(x[4 * i], w2.x, h2); h2 = fmaf(x[4 * i + 1], w2.y, h2); h2 = fmaf(x[4 * i + 2], w2.z, h2); h2 = fmaf(x[4 * i + 3], w2.w, h2);
+        }
+      }
+      if (write_a) {
+        const uint32_t tile = smem_u32(sm.base) + kOffA + static_cast<uint32_t>(j) * 2u * kChunkBytes;
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float t = x[8 * h8 + i];
+            amax = fmaxf(amax, fabsf(t));
+            f[i] = fminf(fmaxf(t, -65000.f), 65000.f);   // keep the fp16 split finite
+          }
+          store_feat8(tile, c.row, 4 * c.hsel + 2 * sub + h8, f, fast);
+        }
+      }
+    }
+    if (write_a) epi_signal(sm, c, j);   // chunk j of the next layer's A operand is ready
+  }
+  if (!write_a) tc_fence_before_sync();
+  if (amax > 65000.f) overflow = true;
+  ho.h0 = h0; ho.h1 = h1; ho.h2 = h2; if (sig_head) ho.sig = sg;
+  c.layer_ctr++;
+}
+
+// ---------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_constant__ RenderParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem sm;
+  sm.base = smem_raw;
+  sm.misc = reinterpret_cast<float*>(smem_raw + kOffMisc + 128);   // 128 B reserved for barriers + tmem ptr
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kOffMisc + 8 * BAR_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool fast = P.fast != 0;
+  const bool smpl = P.kind == NRF_KIND_SMPL;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kNumStages; ++s) { mbar_init(sm.bar(BAR_FULL + s), 1); mbar_init(sm.bar(BAR_EMPTY + s), 1); }
+    mbar_init(sm.bar(BAR_ACC + 0), 1); mbar_init(sm.bar(BAR_ACC + 1), 1);
+    for (int j = 0; j < 5; ++j) mbar_init(sm.bar(BAR_AREADY + j), 8);   // one arrival per epilogue warp
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_pass = P.run_fine ? 2 : 1;
+
+  if (warp == 0) {
+    // =========================== weight producer ===========================
+    if (lane == 0) {
+      RingState rs;
+      for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x)
+        for (int pass = 0; pass < n_pass; ++pass) {
+          const int tiles = pass == 0 ? 1 : P.tiles_f;
+          for (int t = 0; t < tiles; ++t) {
+            if (smpl) producer_layer(sm, P.blob[2], P.warp.layers[0], rs, fast);
+            for (int l = 0; l < P.net[pass].n_layers; ++l) producer_layer(sm, P.blob[pass], P.net[pass].layers[l], rs, fast);
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      MmaState st;
+      for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x)
+        for (int pass = 0; pass < n_pass; ++pass) {
+          const int tiles = pass == 0 ? 1 : P.tiles_f;
+          for (int t = 0; t < tiles; ++t) {
+            if (smpl) mma_layer(sm, tmem_base, P.warp.layers[0], st, fast);
+            for (int l = 0; l < P.net[pass].n_layers; ++l) mma_layer(sm, tmem_base, P.net[pass].layers[l], st, fast);
+          }
+        }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    EpiCtx c;
+    c.warp = warp; c.lane = lane; c.q = warp & 3; c.hsel = (warp - 2) >> 2; c.row = 32 * c.q + lane;
+    c.tid = threadIdx.x - 64; c.tmem_base = tmem_base; c.lane_taddr = static_cast<uint32_t>(32 * c.q) << 16;
+    const int ew = warp - 2;   // 0..7
+    float* ray = sm.misc + P.o_ray;          // [G][kRayFloats]
+    float* rb = sm.misc + P.o_rb;            // [slots][G][256]
+    float* rbw = sm.misc + P.o_rbw;          // warp net: [G][256]
+    float4* raw4 = reinterpret_cast<float4*>(sm.misc + P.o_raw);   // [G * n_all]
+    float* zc = sm.misc + P.o_zc;            // [G][n_coarse]
+    float* zf = sm.misc + P.o_zf;            // [G][n_all]
+    float* dnorm = sm.misc + P.o_dnorm;      // [G * n_coarse] (smpl coarse pass)
+    float* scratch = sm.misc + P.o_scratch;  // tile phase: head partials [128][4]; ray phase: cdf + zs
+    const uint32_t aux_tile = smem_u32(sm.base) + kOffAux;
+    const int G = P.G, nc = P.n_coarse, nf = P.n_fine, na = P.n_all;
+    bool overflow = false;
+
+    for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
+      const int64_t ray0 = static_cast<int64_t>(grp) * G;
+      // ---- per-ray constants: origin, direction, |d|, raw pose pair
+      if (c.tid < G) {
+        const int g = c.tid;
+        float* r = ray + g * kRayFloats;
+        const int64_t ri = ray0 + g;
+        const bool valid = ri < P.n_rays;
+        float o[3] = {0, 0, 0}, d[3] = {0, 0, 1};
+        if (valid) for (int k = 0; k < 3; ++k) { o[k] = P.io.ray_origin[ri * 3 + k]; d[k] = P.io.ray_dir[ri * 3 + k]; }
+        const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+        for (int k = 0; k < 3; ++k) { r[k] = o[k]; r[3 + k] = d[k]; r[kRayVec + k] = __fdiv_rn(d[k], nrm); }
+        r[6] = nrm; r[7] = valid ? 1.f : 0.f;
+        float pz0 = 0.f, pz1 = 0.f;
+        if (valid && P.pose_dim > 0) { pz0 = P.io.goal_pose[ri * P.pose_stride + P.pose_col0]; pz1 = P.io.goal_pose[ri * P.pose_stride + P.pose_col1]; }
+        r[kRayVec + 3] = pz0; r[kRayVec + 4] = pz1;
+      }
+      named_bar_sync(1, kEpiThreads);
+      // ---- per-ray feature vectors in REFERENCE column order, one sin/cos per thread
+      {
+        const int n_dirf = smpl ? 0 : enc_dim(P.net[0].dir_freqs, P.net[0].dir_identity);
+        const int per_ray = P.pose_dim + n_dirf;
+        for (int idx = c.tid; idx < G * per_ray; idx += kEpiThreads) {
+          const int g = idx / per_ray;
+          int i = idx - g * per_ray;
+          float* r = ray + g * kRayFloats;
+          const bool is_dir = i >= P.pose_dim;
+          if (is_dir) i -= P.pose_dim;
+          const int ncomp = is_dir ? 3 : 2;
+          const float* v = r + kRayVec + (is_dir ? 0 : 3);
+          const int ident = is_dir ? P.net[0].dir_identity : (P.pose_encoded ? P.pose_identity : 1);
+          float val;
+          if (ident && i < ncomp) val = v[i];
+          else {
+            const int j = i - (ident ? ncomp : 0);
+            const int k = j / (2 * ncomp), rem = j - k * 2 * ncomp;
+            const float a = v[rem % ncomp] * static_cast<float>(1u << k);
+            val = rem < ncomp ? sinf(a) : cosf(a);
+          }
+          r[8 + (is_dir ? kMaxRayFeat : 0) + i] = val;
+        }
+      }
+      for (int i = c.tid; i < G * nc; i += kEpiThreads) {
+        const int64_t ri = ray0 + i / nc;
+        zc[i] = ri < P.n_rays ? P.io.z_vals[ri * nc + (i % nc)] : static_cast<float>(i % nc);
+      }
+      named_bar_sync(1, kEpiThreads);
+      if (smpl && P.warp.layers[0].ray_slot >= 0) {   // warp net pose bias, shared by both passes
+        const Layer& L = P.warp.layers[0];
+        const float* f32 = reinterpret_cast<const float*>(P.blob[2] + P.warp.f32_ofs);
+        for (int i = c.tid; i < G * kWidth; i += kEpiThreads) {
+          const int g = i >> 8, col = i & 255;
+          float acc = f32[L.bias_ofs + col];
+          const float* feat = ray + g * kRayFloats + 8;
+          for (int k = 0; k < L.ray_k; ++k) acc = fmaf(f32[L.rayw_ofs + k * kWidth + col], feat[k], acc);
+          rbw[i] = acc;
+        }
+      }
+
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const NetPlan& net = P.net[pass];
+        const float* f32 = reinterpret_cast<const float*>(P.blob[pass] + net.f32_ofs);
+        const bool last_pass = (pass == n_pass - 1);
+        const int n = pass == 0 ? nc : na;
+        const int tiles = pass == 0 ? 1 : P.tiles_f;
+        // ---- per-ray bias vectors of this net (pose / direction contributions)
+        for (int l = 0; l < net.n_layers; ++l) {
+          const Layer& L = net.layers[l];
+          if (L.ray_slot < 0) continue;
+          for (int i = c.tid; i < G * L.n_out; i += kEpiThreads) {
+            const int g = i / L.n_out, col = i % L.n_out;
+            float acc = f32[L.bias_ofs + col];
+            const float* feat = ray + g * kRayFloats + 8 + (L.ray_src == RAY_DIR ? kMaxRayFeat : 0);
+            for (int k = 0; k < L.ray_k; ++k) acc = fmaf(f32[L.rayw_ofs + k * L.n_out + col], feat[k], acc);
+            rb[(static_cast<int>(L.ray_slot) * G + g) * kWidth + col] = acc;
+          }
+        }
+        named_bar_sync(1, kEpiThreads);
+
+        for (int t = 0; t < tiles; ++t) {
+          const int R = t * kTileRows + c.row;
+          const bool in_rows = R < G * n;
+          const int g = in_rows ? R / n : 0;
+          const int s = in_rows ? R - g * n : 0;
+          const int64_t ri = ray0 + g;
+          const bool valid = in_rows && ri < P.n_rays;
+          const float* r = ray + g * kRayFloats;
+          float x = 0.f, y = 0.f, z = 0.f;
+          if (valid) {
+            if (pass == 0) {
+              const float* ps = P.io.ray_samples + (ri * nc + s) * 3;
+              x = ps[0]; y = ps[1]; z = ps[2];
+            } else {
+              const float zz = zf[g * na + s];
+              x = __fadd_rn(r[0], __fmul_rn(r[3], zz)); y = __fadd_rn(r[1], __fmul_rn(r[4], zz)); z = __fadd_rn(r[2], __fmul_rn(r[5], zz));
+              if (c.hsel == 0 && P.io.samples_out) { float* po = P.io.samples_out + (ri * na + s) * 3; po[0] = x; po[1] = y; po[2] = z; }
+            }
+          }
+          float ux = 0.f, uy = 0.f, uz = 1.f;   // unit view direction of this sample (smpl)
+          HeadOut ho = {0.f, 0.f, 0.f, 0.f};
+          if (smpl) {
+            // ---- warp field: x -> x + W2 relu(W1 [enc(x), pose] + b1) + b2
+            write_encoding(aux_tile, c.row, c.hsel, x, y, z, P.warp.in_freqs, P.warp.in_identity, fast);
+            epi_signal(sm, c, kSrcAux);
+            epilogue_layer(sm, P, P.warp, reinterpret_cast<const float*>(P.blob[2] + P.warp.f32_ofs), rbw, P.warp.layers[0], c, g, ho, overflow);
+            // both threads of a row need the full 256-column dot products: exchange the two
+            // column-half partials through smem and add them in the same order -> identical bits
+            float4* part = reinterpret_cast<float4*>(scratch);   // [2][128]
+            part[c.hsel * kTileRows + c.row] = make_float4(ho.h0, ho.h1, ho.h2, 0.f);
+            named_bar_sync(1, kEpiThreads);
+            float w0, w1, w2;
+            {
+              const float* b2 = reinterpret_cast<const float*>(P.blob[2] + P.warp.f32_ofs) + P.warp.head_ofs + 3 * kWidth;
+              const float4 p0 = part[c.row], p1 = part[kTileRows + c.row];
+              w0 = __fadd_rn(__fadd_rn(p0.x, p1.x), __ldg(b2 + 0));
+              w1 = __fadd_rn(__fadd_rn(p0.y, p1.y), __ldg(b2 + 1));
+              w2 = __fadd_rn(__fadd_rn(p0.z, p1.z), __ldg(b2 + 2));
+            }
+            const float wx = __fadd_rn(x, w0), wy = __fadd_rn(y, w1), wz = __fadd_rn(z, w2);
+            if (valid && last_pass && c.hsel == 0) {
+              if (P.io.warp_out) { float* po = P.io.warp_out + (ri * n + s) * 3; po[0] = w0; po[1] = w1; po[2] = w2; }
+              if (P.io.warped_out) { float* po = P.io.warped_out + (ri * n + s) * 3; po[0] = wx; po[1] = wy; po[2] = wz; }
+            }
+            x = wx; y = wy; z = wz;
+            const float dx = __fsub_rn(x, r[0]), dy = __fsub_rn(y, r[1]), dz = __fsub_rn(z, r[2]);
+            const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+            if (in_rows) { ux = __fdiv_rn(dx, nrm); uy = __fdiv_rn(dy, nrm); uz = __fdiv_rn(dz, nrm); }
+            if (pass == 0 && c.hsel == 0 && in_rows) dnorm[R] = nrm;
+            named_bar_sync(1, kEpiThreads);   // everyone is done with the exchange buffer
+          }
+          // ---- encoded position -> aux (first layer and skip layer read it)
+          write_encoding(aux_tile, c.row, c.hsel, x, y, z, net.in_freqs, net.in_identity, fast);
+          epi_signal(sm, c, kSrcAux);
+
+          ho = {0.f, 0.f, 0.f, 0.f};
+          float sigma_part = 0.f;
+          for (int l = 0; l < net.n_layers; ++l) {
+            const Layer& L = net.layers[l];
+            HeadOut hl = {0.f, 0.f, 0.f, 0.f};
+            epilogue_layer(sm, P, net, f32, rb, L, c, g, hl, overflow);
+            if (L.flags & LF_SIGMA_HEAD) sigma_part = hl.sig;
+            if (L.epi == EPI_RGB) ho = hl;
+            if (L.flags & LF_WRITE_DIRPE) {
+              // the skip layer's MMAs are long done: aux can now take the per-sample direction encoding
+              write_encoding(aux_tile, c.row, c.hsel, ux, uy, uz, net.dir_freqs, net.dir_identity, fast);
+              epi_signal(sm, c, kSrcAux);
+            }
+          }
+          // ---- combine the two column-halves of the heads: raw = (rgb_raw, sigma_raw)
+          float4* part = reinterpret_cast<float4*>(scratch);
+          if (c.hsel == 1) part[c.row] = make_float4(ho.h0, ho.h1, ho.h2, sigma_part);
+          named_bar_sync(1, kEpiThreads);
+          if (c.hsel == 0) {
+            const float4 p1 = part[c.row];
+            const float* hb = f32 + net.head_ofs + 3 * (kWidth / 2);
+            float4 o4;
+            o4.x = __fadd_rn(__fadd_rn(ho.h0, p1.x), __ldg(hb + 0));
+            o4.y = __fadd_rn(__fadd_rn(ho.h1, p1.y), __ldg(hb + 1));
+            o4.z = __fadd_rn(__fadd_rn(ho.h2, p1.z), __ldg(hb + 2));
+            o4.w = __fadd_rn(__fadd_rn(sigma_part, p1.w), __ldg(f32 + net.sigma_ofs + kWidth));
+            if (in_rows) raw4[R] = o4;
+            if (valid) {
+              float* tap = pass == 0 ? P.io.raw_coarse : P.io.raw_fine;
+              if (tap) *reinterpret_cast<float4*>(tap + (ri * n + s) * 4) = o4;
+            }
+          }
+          named_bar_sync(1, kEpiThreads);
+        }
+
+        // ---- per-ray: compositing (+ sampling after the coarse pass); one warp per ray
+        if (ew < G) {
+          const int g = ew;
+          const int64_t ri = ray0 + g;
+          const bool valid = ri < P.n_rays;
+          const float* r = ray + g * kRayFloats;
+          const float* zz = pass == 0 ? zc + g * nc : zf + g * na;
+          const float* nz = nullptr;
+          if (valid) { const float* nb = pass == 0 ? P.io.noise_coarse : P.io.noise_fine; if (nb) nz = nb + ri * n; }
+          float* rgb_dst = valid ? (pass == 0 ? P.io.rgb : P.io.rgb_fine) : nullptr;
+          if (rgb_dst) rgb_dst += ri * 3;
+          float* a_dst = (valid && last_pass && P.io.alpha_out) ? P.io.alpha_out + ri * n : nullptr;
+          float* w_dst = (valid && pass == 0 && P.io.weights_coarse) ? P.io.weights_coarse + ri * nc : nullptr;
+          composite_ray(raw4 + g * n, zz, (smpl && pass == 0) ? dnorm + g * nc : nullptr, r[6], n, nz, P.white_bkgd, rgb_dst,
+                        a_dst, w_dst, lane);
+          if (pass == 0 && P.run_fine) {
+            float* zfg = zf + g * na;
+            if (P.io.z_all_in && valid) {
+              for (int i = lane; i < na; i += 32) zfg[i] = P.io.z_all_in[ri * na + i];
+            } else {
+              float* cdf = scratch + g * (nc + nf);
+              float* zs = cdf + nc;
+              sample_ray(raw4 + g * nc, zc + g * nc, nc, nf, P.io.u_fine, cdf, zs, zfg,
+                         (valid && P.io.z_new) ? P.io.z_new + ri * nf : nullptr, lane);
+            }
+            if (valid && P.io.z_all) for (int i = lane; i < na; i += 32) P.io.z_all[ri * na + i] = zfg[i];
+          }
+        }
+        named_bar_sync(1, kEpiThreads);
+      }
+    }
+    if (overflow && P.io.status) atomicOr(P.io.status, 1);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------- host launcher
+static int check_ptr(const void* p, const char* name) {
+  if (!p) { set_error("%s is NULL", name); return NRF_E_INVALID; }
+  return NRF_OK;
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" int nrf_render_launches(void) { return 1; }
+
+extern "C" int nrf_render(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, const void* packed_coarse,
+                          const NrfRayNetDesc* fine, const void* packed_fine, const NrfWarpNetDesc* warp,
+                          const void* packed_warp, const NrfRenderIO* io, int64_t n_rays, int n_sms, void* stream) {
+  if (!pipe || !coarse || !io) { set_error("pipe/coarse/io is NULL"); return NRF_E_INVALID; }
+  if (n_rays < 0) { set_error("n_rays < 0"); return NRF_E_INVALID; }
+  if (n_rays == 0) return NRF_OK;
+  static thread_local RenderParams P;
+  memset(&P, 0, sizeof(P));
+  int rc;
+  if ((rc = plan_raynet(coarse, &P.net[0])) != NRF_OK) return rc;
+  if ((rc = check_ptr(packed_coarse, "packed_coarse")) != NRF_OK) return rc;
+  P.blob[0] = static_cast<const uint8_t*>(packed_coarse);
+  const bool smpl = pipe->kind == NRF_KIND_SMPL;
+  if (pipe->kind != NRF_KIND_NERF && pipe->kind != NRF_KIND_SMPL && pipe->kind != NRF_KIND_APPEND) { set_error("unknown pipeline kind %d", pipe->kind); return NRF_E_INVALID; }
+  if (pipe->run_fine) {
+    if (!fine) { set_error("run_fine=1 needs the fine net"); return NRF_E_INVALID; }
+    if ((rc = plan_raynet(fine, &P.net[1])) != NRF_OK) return rc;
+    if ((rc = check_ptr(packed_fine, "packed_fine")) != NRF_OK) return rc;
+    P.blob[1] = static_cast<const uint8_t*>(packed_fine);
+  }
+  if (smpl) {
+    if (!warp) { set_error("smpl pipeline needs the warp net"); return NRF_E_INVALID; }
+    if ((rc = plan_warpnet(warp, &P.warp)) != NRF_OK) return rc;
+    if ((rc = check_ptr(packed_warp, "packed_warp")) != NRF_OK) return rc;
+    P.blob[2] = static_cast<const uint8_t*>(packed_warp);
+    if (!coarse->per_sample_dirs || (pipe->run_fine && !fine->per_sample_dirs)) { set_error("smpl pipeline needs per_sample_dirs=1 nets"); return NRF_E_INVALID; }
+    if (pipe->run_fine && !pipe->pose_encoded) { set_error("smpl pipeline with run_fine=1 requires human_pose_encoding=1 (the reference feeds the warp net encoded inputs in the fine pass, smpl_nerf_pipeline.py:71-77)"); return NRF_E_INVALID; }
+  } else if (coarse->per_sample_dirs) { set_error("per_sample_dirs=1 is only valid for the smpl pipeline"); return NRF_E_INVALID; }
+  for (int i = 0; i < 3; ++i) if (P.blob[i] && (reinterpret_cast<uintptr_t>(P.blob[i]) & 1023u)) { set_error("packed buffers must be 1024-byte aligned"); return NRF_E_INVALID; }
+
+  const int nc = pipe->n_coarse, nf = pipe->run_fine ? pipe->n_fine : 0;
+  if (nc < 16 || nc > kTileRows) { set_error("n_coarse %d unsupported (16..%d)", nc, kTileRows); return NRF_E_INVALID; }
+  if (pipe->run_fine && nf < 1) { set_error("n_fine %d invalid", nf); return NRF_E_INVALID; }
+  if (pipe->run_fine && nc < 3) { set_error("hierarchical sampling needs n_coarse >= 3"); return NRF_E_INVALID; }
+  const int G = kTileRows / nc, na = nc + nf;
+  if (G * na > kMaxFineRows) { set_error("n_coarse + n_fine = %d too large for %d rays per group (max %d rows)", na, G, kMaxFineRows); return NRF_E_INVALID; }
+  P.io = *io;
+  P.n_rays = n_rays;
+  P.kind = pipe->kind; P.n_coarse = nc; P.n_fine = nf; P.n_all = na; P.run_fine = pipe->run_fine ? 1 : 0;
+  P.white_bkgd = pipe->white_background ? 1 : 0; P.fast = pipe->precision == 1 ? 1 : 0;
+  P.pose_freqs = pipe->pose_freqs; P.pose_identity = pipe->pose_identity; P.pose_encoded = pipe->pose_encoded ? 1 : 0;
+  P.pose_stride = pipe->pose_stride; P.pose_col0 = pipe->pose_col0; P.pose_col1 = pipe->pose_col1;
+  P.pose_dim = 0;
+  if (pipe->kind != NRF_KIND_NERF) {
+    P.pose_dim = pipe->pose_encoded ? 2 * (2 * pipe->pose_freqs + (pipe->pose_identity ? 1 : 0)) : 2;
+    const int want = smpl ? warp->pose_dim : coarse->additional_input_dim;
+    if (P.pose_dim != want) { set_error("pose feature count %d does not match the net's pose input dim %d", P.pose_dim, want); return NRF_E_INVALID; }
+    if (P.pose_dim > kMaxRayFeat) { set_error("pose feature count %d > %d", P.pose_dim, kMaxRayFeat); return NRF_E_INVALID; }
+    if ((rc = check_ptr(io->goal_pose, "goal_pose")) != NRF_OK) return rc;
+    if (pipe->pose_col0 < 0 || pipe->pose_col1 < 0 || pipe->pose_col0 >= pipe->pose_stride || pipe->pose_col1 >= pipe->pose_stride) { set_error("pose columns out of range"); return NRF_E_INVALID; }
+  } else if (coarse->additional_input_dim != 0) { set_error("nerf pipeline with additional_input_dim != 0"); return NRF_E_INVALID; }
+  if (pipe->run_fine && (fine->additional_input_dim != coarse->additional_input_dim)) { set_error("coarse/fine additional_input_dim differ"); return NRF_E_INVALID; }
+  if ((rc = check_ptr(io->ray_samples, "ray_samples")) || (rc = check_ptr(io->ray_origin, "ray_origin")) ||
+      (rc = check_ptr(io->ray_dir, "ray_dir")) || (rc = check_ptr(io->z_vals, "z_vals")) || (rc = check_ptr(io->rgb, "rgb"))) return rc;
+  if (pipe->run_fine) {
+    if ((rc = check_ptr(io->rgb_fine, "rgb_fine")) != NRF_OK) return rc;
+    if (!io->z_all_in && (rc = check_ptr(io->u_fine, "u_fine")) != NRF_OK) return rc;
+  }
+  P.G = G;
+  P.tiles_f = (G * na + kTileRows - 1) / kTileRows;
+  P.n_groups = static_cast<int32_t>((n_rays + G - 1) / G);
+
+  // shared-memory layout of the misc area (floats, 16-byte aligned pieces)
+  uint32_t f = 0;
+  auto take = [&](uint32_t n) { uint32_t o = f; f = (f + n + 3u) & ~3u; return o; };
+  const int slots = P.net[0].n_ray_slots > P.net[1].n_ray_slots ? P.net[0].n_ray_slots : P.net[1].n_ray_slots;
+  P.o_ray = take(G * kRayFloats);
+  P.o_rb = take(slots * G * kWidth);
+  P.o_rbw = take(smpl ? G * kWidth : 0);
+  P.o_raw = take(G * na * 4);
+  P.o_zc = take(G * nc);
+  P.o_zf = take(G * na);
+  P.o_dnorm = take(smpl ? G * nc : 0);
+  uint32_t scr = 2 * kTileRows * 4;
+  if (static_cast<uint32_t>(G * (nc + nf)) > scr) scr = G * (nc + nf);
+  P.o_scratch = take(scr);
+  const uint32_t smem_bytes = kOffMisc + 128 + f * 4;
+  if (smem_bytes > kSmemLimit) { set_error("configuration needs %u bytes of shared memory per CTA (limit %u)", smem_bytes, kSmemLimit); return NRF_E_INVALID; }
+
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  if (n_sms > 0 && n_sms < sms) sms = n_sms;
+  const int grid = P.n_groups < sms ? P.n_groups : sms;
+  e = cudaFuncSetAttribute(nrf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)");
+  nrf_fused_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "nrf_fused_kernel launch");
+  return NRF_OK;
+}

@@ -1,0 +1,232 @@
+// Stand-alone ops with the same arithmetic as the fused kernel's stages, exported so that the
+// reference's utils.py functions and torchsearchsorted can be replaced one by one:
+//   nrf_positional_encoding  <- utils.py:127-131  PositionalEncoder.encode
+//   nrf_raw2outputs          <- utils.py:134-191  raw2outputs
+//   nrf_sample_pdf           <- utils.py:194-228  sample_pdf
+//   nrf_searchsorted         <- torchsearchsorted/src/cuda/searchsorted_cuda_kernel.cu:83-142
+// plus nrf_selftest_umma, a one-tile tcgen05 GEMM through the renderer's operand layout.
+// These are HBM-bound streaming kernels: coalesced loads, one warp per ray where a scan is needed.
+#include <cuda_runtime.h>
+
+#include "nrf_plan.h"
+#include "nrf_ptx.cuh"
+#include "nrf_stages.cuh"
+
+namespace nrf {
+
+// ------------------------------------------------------------------------------ positional encoding
+// out[i, :] = [x_i ?] ++ for k: sin(2^k x_i) ++ cos(2^k x_i)    (x_i has c components)
+__global__ void pe_kernel(const float* __restrict__ x, int64_t n, int c, int freqs, int identity, float* __restrict__ out) {
+  const int width = c * (2 * freqs + (identity ? 1 : 0));
+  const int64_t total = n * width;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = idx / width;
+    int col = static_cast<int>(idx - row * width);
+    float val;
+    if (identity && col < c) val = x[row * c + col];
+    else {
+      col -= identity ? c : 0;
+      const int k = col / (2 * c), rem = col - k * 2 * c;
+      const float a = x[row * c + rem % c] * static_cast<float>(1u << k);
+      val = rem < c ? sinf(a) : cosf(a);
+    }
+    out[idx] = val;
+  }
+}
+
+// ------------------------------------------------------------------------------ raw2outputs
+// one warp per ray; raw staged in smem as float4
+__global__ void raw2outputs_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ dirs,
+                                   const float* __restrict__ noise, int64_t B, int n, int white, float* __restrict__ rgb,
+                                   float* __restrict__ weights, float* __restrict__ alpha) {
+  extern __shared__ __align__(16) float smem[];
+  const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* raw4 = reinterpret_cast<float4*>(smem) + static_cast<size_t>(w) * n;
+  float* zs = smem + static_cast<size_t>(wpb) * n * 4 + static_cast<size_t>(w) * 2 * n;
+  float* dn = zs + n;
+  for (int64_t ray = blockIdx.x * static_cast<int64_t>(wpb) + w; ray < B; ray += static_cast<int64_t>(gridDim.x) * wpb) {
+    for (int i = lane; i < n; i += 32) {
+      raw4[i] = *reinterpret_cast<const float4*>(raw + (ray * n + i) * 4);
+      zs[i] = z[ray * n + i];
+      const float* d = dirs + (ray * n + i) * 3;
+      dn[i] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+    }
+    __syncwarp();
+    composite_ray(raw4, zs, dn, 0.f, n, noise ? noise + ray * n : nullptr, white, rgb + ray * 3, alpha + ray * n,
+                  weights + ray * n, lane);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------ sample_pdf
+// one warp per ray: pdf -> sequential cdf -> right-sided bisection -> guarded lerp
+__global__ void sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, const float* __restrict__ u,
+                                  int64_t B, int m, int nf, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* cdf = smem + static_cast<size_t>(w) * 2 * m;
+  float* bn = cdf + m;
+  for (int64_t ray = blockIdx.x * static_cast<int64_t>(wpb) + w; ray < B; ray += static_cast<int64_t>(gridDim.x) * wpb) {
+    float part = 0.f;
+    for (int i = lane; i < m; i += 32) bn[i] = bins[ray * m + i];
+    for (int i = 1 + lane; i < m; i += 32) { const float v = __fadd_rn(weights[ray * (m - 1) + i - 1], 1e-5f); cdf[i] = v; part += v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncwarp();
+    for (int i = 1 + lane; i < m; i += 32) cdf[i] = __fdiv_rn(cdf[i], part);
+    __syncwarp();
+    if (lane == 0) { float run = 0.f; cdf[0] = 0.f; for (int i = 1; i < m; ++i) { run = __fadd_rn(run, cdf[i]); cdf[i] = run; } }
+    __syncwarp();
+    for (int j = lane; j < nf; j += 32) {
+      const float uu = u[j];
+      int lo = 0, hi = m;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= uu) lo = mid + 1; else hi = mid; }
+      const int below = max(0, lo - 1), above = min(m - 1, lo);
+      const float c0 = cdf[below], c1 = cdf[above], b0 = bn[below], b1 = bn[above];
+      float denom = __fsub_rn(c1, c0);
+      if (denom < 1e-5f) denom = 1.f;
+      const float t = __fdiv_rn(__fsub_rn(uu, c0), denom);
+      out[ray * nf + j] = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------ searchsorted
+// res[r, c] = #{ j : a[r, j] < v[r, c] } (side left)  or  #{ j : a[r, j] <= v[r, c] } (side right).
+// Same results as the reference's bisection for sorted rows; one thread per query, queries of a row
+// are contiguous so loads of v and stores of res coalesce.
+__global__ void searchsorted_kernel(const float* __restrict__ a, int64_t rows_a, int64_t na, const float* __restrict__ v,
+                                    int64_t rows_v, int64_t nv, int64_t* __restrict__ res, int side_left, int64_t rows) {
+  const int64_t total = rows * nv;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / nv, c = idx - r * nv;
+    const float* ar = a + (rows_a == 1 ? 0 : r) * na;
+    const float val = v[(rows_v == 1 ? 0 : r) * nv + c];
+    int64_t lo = 0, hi = na;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const float am = ar[mid];
+      const bool go_right = side_left ? (am < val) : (am <= val);
+      if (go_right) lo = mid + 1; else hi = mid;
+    }
+    res[idx] = lo;
+  }
+}
+
+// ------------------------------------------------------------------------------ tcgen05 self-test
+// D[128,128] = A[128,64] x B[128,64]^T, fp16 operands written to smem with the renderer's swizzle
+// helper, one K=64 chain of four tcgen05.mma, accumulator read back with tcgen05.ld.
+__global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                float* __restrict__ d) {
+  extern __shared__ __align__(1024) uint8_t smem_st[];
+  uint8_t* sa = smem_st;             // 16 KB
+  uint8_t* sb = smem_st + 16384;     // 16 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_st + 32768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_st + 32768 + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int idx = threadIdx.x; idx < 128 * 64; idx += 128) {
+    const int r = idx >> 6, k = idx & 63;
+    *reinterpret_cast<__half*>(sa + sw128_offset(r, k)) = __float2half_rn(a[idx]);
+    *reinterpret_cast<__half*>(sb + sw128_offset(r, k)) = __float2half_rn(b[idx]);
+  }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<128>(smem_u32(tmem_slot));
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, 128);
+    const uint64_t ad = umma_desc_sw128(smem_u32(sa)), bd = umma_desc_sw128(smem_u32(sb));
+    for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem, ad + 2u * ks, bd + 2u * ks, idesc, ks ? 1u : 0u);
+    umma_commit(smem_u32(bar));
+  }
+  mbar_wait(smem_u32(bar), 0);
+  tc_fence_after_sync();
+  const int row = 32 * (warp & 3) + lane;
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) d[row * 128 + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
+static int grid_for(int64_t total, int block) {
+  int64_t g = (total + block - 1) / block;
+  return static_cast<int>(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" int nrf_positional_encoding(const float* x, int64_t n, int32_t c, int32_t freqs, int32_t identity, float* out,
+                                       void* stream) {
+  if (!x || !out) { set_error("x/out is NULL"); return NRF_E_INVALID; }
+  if (n < 0 || c < 1 || freqs < 0 || freqs > 24 || (freqs == 0 && !identity)) { set_error("bad positional-encoding shape (n=%lld c=%d L=%d id=%d)", (long long)n, c, freqs, identity); return NRF_E_INVALID; }
+  if (n == 0) return NRF_OK;
+  const int64_t total = n * c * (2 * freqs + (identity ? 1 : 0));
+  pe_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, c, freqs, identity, out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "pe_kernel launch");
+}
+
+extern "C" int nrf_raw2outputs(const float* raw, const float* z, const float* dirs, const float* noise, int64_t B, int32_t n,
+                               int32_t white_background, float* rgb, float* weights, float* alpha, void* stream) {
+  if (!raw || !z || !dirs || !rgb || !weights || !alpha) { set_error("raw2outputs: NULL argument"); return NRF_E_INVALID; }
+  if (B < 0 || n < 2 || n > 1024) { set_error("raw2outputs: unsupported shape B=%lld n=%d (n in 2..1024)", (long long)B, n); return NRF_E_INVALID; }
+  if (B == 0) return NRF_OK;
+  const int wpb = 4;
+  const size_t smem = static_cast<size_t>(wpb) * n * 6 * sizeof(float);
+  const int grid = static_cast<int>(B / wpb + 1 > 148 * 8 ? 148 * 8 : B / wpb + 1);
+  cudaError_t e = cudaFuncSetAttribute(raw2outputs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  raw2outputs_kernel<<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(raw, z, dirs, noise, B, n, white_background, rgb, weights, alpha);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "raw2outputs_kernel launch");
+}
+
+extern "C" int nrf_sample_pdf(const float* bins, const float* weights, const float* u, int64_t B, int32_t m, int32_t n_fine,
+                              float* samples, void* stream) {
+  if (!bins || !weights || !u || !samples) { set_error("sample_pdf: NULL argument"); return NRF_E_INVALID; }
+  if (B < 0 || m < 2 || m > 4096 || n_fine < 1) { set_error("sample_pdf: unsupported shape B=%lld m=%d n_fine=%d", (long long)B, m, n_fine); return NRF_E_INVALID; }
+  if (B == 0) return NRF_OK;
+  const int wpb = 4;
+  const size_t smem = static_cast<size_t>(wpb) * 2 * m * sizeof(float);
+  const int grid = static_cast<int>(B / wpb + 1 > 148 * 8 ? 148 * 8 : B / wpb + 1);
+  cudaError_t e = cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  sample_pdf_kernel<<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(bins, weights, u, B, m, n_fine, samples);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "sample_pdf_kernel launch");
+}
+
+extern "C" int nrf_searchsorted(const float* a, int64_t rows_a, int64_t na, const float* v, int64_t rows_v, int64_t nv,
+                                int64_t* res, int32_t side_left, void* stream) {
+  if (!a || !v || !res) { set_error("searchsorted: NULL argument"); return NRF_E_INVALID; }
+  if (rows_a < 1 || rows_v < 1 || na < 0 || nv < 0) { set_error("searchsorted: bad shape"); return NRF_E_INVALID; }
+  if (rows_a != rows_v && rows_a != 1 && rows_v != 1) { set_error("searchsorted: `a` and `v` must have the same number of rows or one of them must have only one"); return NRF_E_INVALID; }
+  const int64_t rows = rows_a > rows_v ? rows_a : rows_v;
+  if (rows * nv == 0) return NRF_OK;
+  searchsorted_kernel<<<grid_for(rows * nv, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, rows_a, na, v, rows_v, nv, res, side_left, rows);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "searchsorted_kernel launch");
+}
+
+extern "C" int nrf_selftest_umma(const float* a, const float* b, float* d, void* stream) {
+  if (!a || !b || !d) { set_error("selftest: NULL argument"); return NRF_E_INVALID; }
+  const int smem = 32768 + 64;
+  cudaError_t e = cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  selftest_umma_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(a, b, d);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "selftest_umma_kernel launch");
+}

@@ -1,0 +1,5 @@
+"""Drop-in pipeline classes (same constructor and ``forward(data)`` contracts as the reference's
+``models/*_pipeline.py``)."""
+from .nerf_pipeline import NerfPipeline  # noqa: F401
+from .smpl_nerf_pipeline import SmplNerfPipeline  # noqa: F401
+from .append_to_nerf_pipeline import AppendToNerfPipeline  # noqa: F401

@@ -1,0 +1,29 @@
+"""NerfPipeline -- drop-in for models/nerf_pipeline.py:7-67, computed by the fused sm_100a kernel."""
+from .. import engine
+from .singe_sample_pipeline import SmplPipeline
+
+
+class NerfPipeline(SmplPipeline):
+    """``NerfPipeline(model_coarse, model_fine, args, position_encoder, direction_encoder)``.
+
+    ``forward(data)`` with ``data = [ray_samples, ray_translation, ray_direction, z_vals, rgb]`` returns
+    ``(rgb, rgb_fine, ray_samples_fine, densities)``; with ``args.run_fine == 0`` it returns
+    ``(rgb, rgb, ray_samples, densities)`` exactly like the reference (``densities`` is alpha).
+    """
+
+    kind = 'nerf'
+
+    def __init__(self, model_coarse, model_fine, args, position_encoder, direction_encoder):
+        super().__init__(model_coarse, args, position_encoder, direction_encoder)
+        self.model_fine = model_fine
+
+    def _render(self, data, **kw):
+        return engine.render(self.kind, self.model_coarse, self.model_fine, getattr(self, 'model_warp_field', None),
+                             self.args, self.position_encoder, self.direction_encoder,
+                             getattr(self, 'human_pose_encoder', None), data, **kw)
+
+    def forward(self, data):
+        if len(data) < 5:
+            raise ValueError('data must be [ray_samples, ray_translation, ray_direction, z_vals, rgb]')
+        o = self._render(data)
+        return o['rgb'], o['rgb_fine'], o['samples_out'], o['alpha_out']
