@@ -9,6 +9,7 @@
  *   utils.py:114-131  PositionalEncoder.encode         -> nrf_positional_encoding()
  *   utils.py:134-191  raw2outputs                      -> nrf_raw2outputs()
  *   utils.py:194-228  sample_pdf                       -> nrf_sample_pdf()
+ *   utils.py:231-264  fine_sampling                    -> nrf_fine_sampling()
  *   torchsearchsorted/src/cuda/searchsorted_cuda_wrapper.cpp:18-20
  *       searchsorted_cuda_wrapper(a, v, res, side_left) -> nrf_searchsorted()
  *
@@ -151,6 +152,9 @@ int nrf_raw2outputs(const float* raw, const float* z, const float* dirs, const f
 /* utils.py:194-228: bins[B,m], weights[B,m-1], u[n_fine] -> samples[B,n_fine] */
 int nrf_sample_pdf(const float* bins, const float* weights, const float* u, int64_t B, int32_t m, int32_t n_fine,
                    float* samples, void* stream);
+/* utils.py:231-264: origin[B,3], dir[B,3], z[B,nc], weights[B,nc], u[n_fine] -> z_all[B,nc+nf], pts[B,nc+nf,3] */
+int nrf_fine_sampling(const float* origin, const float* dir, const float* z, const float* weights, const float* u,
+                      int64_t B, int32_t n_coarse, int32_t n_fine, float* z_all, float* pts, void* stream);
 /* torchsearchsorted: a[rows_a, na], v[rows_v, nv] (rows broadcast when one side has 1 row) -> res int64 */
 int nrf_searchsorted(const float* a, int64_t rows_a, int64_t na, const float* v, int64_t rows_v, int64_t nv,
                      int64_t* res, int32_t side_left, void* stream);

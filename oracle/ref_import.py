@@ -72,8 +72,12 @@ def load(use_compiled_searchsorted: bool = False):
     # the same names are not already imported under those names
     for name in ('utils', 'models'):
         mod = sys.modules.get(name)
-        if mod is not None and not str(getattr(mod, '__file__', '')).startswith(REFERENCE_ROOT):
-            raise RuntimeError(f'module name clash: {name} already imported from {mod.__file__}')
+        if mod is None:
+            continue
+        # `models` is a namespace package in the reference (no __init__.py): it has __path__, no __file__
+        where = getattr(mod, '__file__', None) or ''.join(list(getattr(mod, '__path__', []))[:1])
+        if not str(where).startswith(REFERENCE_ROOT):
+            raise RuntimeError(f'module name clash: {name} already imported from {where}')
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import utils as ref_utils                                            # noqa: E402

@@ -56,7 +56,8 @@ class RenderIO(C.Structure):
 
 EXPORTS = ['nrf_last_error', 'nrf_abi_version', 'nrf_device_supported', 'nrf_raynet_packed_bytes',
            'nrf_warpnet_packed_bytes', 'nrf_pack_raynet', 'nrf_pack_warpnet', 'nrf_render', 'nrf_render_launches',
-           'nrf_positional_encoding', 'nrf_raw2outputs', 'nrf_sample_pdf', 'nrf_searchsorted', 'nrf_selftest_umma']
+           'nrf_positional_encoding', 'nrf_raw2outputs', 'nrf_sample_pdf', 'nrf_fine_sampling', 'nrf_searchsorted',
+           'nrf_selftest_umma']
 
 
 def _stale() -> bool:
@@ -112,6 +113,8 @@ def lib() -> C.CDLL:
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nrf_sample_pdf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                  C.c_void_p]
+    L.nrf_fine_sampling.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nrf_searchsorted.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                    C.c_int32, C.c_void_p]
     L.nrf_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

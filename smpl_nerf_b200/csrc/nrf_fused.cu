@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
             } else {
               float* cdf = scratch + g * (nc + nf);
               float* zs = cdf + nc;
-              sample_ray(raw4 + g * nc, zc + g * nc, nc, nf, P.io.u_fine, cdf, zs, zfg,
+              sample_ray(&raw4[g * nc].w, 4, zc + g * nc, nc, nf, P.io.u_fine, cdf, zs, zfg,
                          (valid && P.io.z_new) ? P.io.z_new + ri * nf : nullptr, lane);
             }
             if (valid && P.io.z_all) for (int i = lane; i < na; i += 32) P.io.z_all[ri * na + i] = zfg[i];

@@ -93,6 +93,32 @@ __global__ void sample_pdf_kernel(const float* __restrict__ bins, const float* _
   }
 }
 
+// ------------------------------------------------------------------------------ fine_sampling
+// utils.py:231-264: z_mid, sample_pdf, sort(cat(z, z_samples)), points = o + d * z   (one warp per ray)
+__global__ void fine_sampling_kernel(const float* __restrict__ origin, const float* __restrict__ dir, const float* __restrict__ z,
+                                     const float* __restrict__ weights, const float* __restrict__ u, int64_t B, int nc, int nf,
+                                     float* __restrict__ z_all, float* __restrict__ pts) {
+  extern __shared__ __align__(16) float smem[];
+  const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int na = nc + nf;
+  float* base = smem + static_cast<size_t>(w) * (3 * nc + nf + na);
+  float* zc = base; float* wc = zc + nc; float* cdf = wc + nc; float* zs = cdf + nc; float* zf = zs + nf;
+  for (int64_t ray = blockIdx.x * static_cast<int64_t>(wpb) + w; ray < B; ray += static_cast<int64_t>(gridDim.x) * wpb) {
+    for (int i = lane; i < nc; i += 32) { zc[i] = z[ray * nc + i]; wc[i] = weights[ray * nc + i]; }
+    __syncwarp();
+    sample_ray(wc, 1, zc, nc, nf, u, cdf, zs, zf, nullptr, lane);
+    const float ox = origin[ray * 3], oy = origin[ray * 3 + 1], oz = origin[ray * 3 + 2];
+    const float dx = dir[ray * 3], dy = dir[ray * 3 + 1], dz = dir[ray * 3 + 2];
+    for (int i = lane; i < na; i += 32) {
+      const float zz = zf[i];
+      z_all[ray * na + i] = zz;
+      float* po = pts + (ray * na + i) * 3;
+      po[0] = __fadd_rn(ox, __fmul_rn(dx, zz)); po[1] = __fadd_rn(oy, __fmul_rn(dy, zz)); po[2] = __fadd_rn(oz, __fmul_rn(dz, zz));
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------ searchsorted
 // res[r, c] = #{ j : a[r, j] < v[r, c] } (side left)  or  #{ j : a[r, j] <= v[r, c] } (side right).
 // Same results as the reference's bisection for sorted rows; one thread per query, queries of a row
@@ -207,6 +233,21 @@ extern "C" int nrf_sample_pdf(const float* bins, const float* weights, const flo
   sample_pdf_kernel<<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(bins, weights, u, B, m, n_fine, samples);
   e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "sample_pdf_kernel launch");
+}
+
+extern "C" int nrf_fine_sampling(const float* origin, const float* dir, const float* z, const float* weights, const float* u,
+                                 int64_t B, int32_t n_coarse, int32_t n_fine, float* z_all, float* pts, void* stream) {
+  if (!origin || !dir || !z || !weights || !u || !z_all || !pts) { set_error("fine_sampling: NULL argument"); return NRF_E_INVALID; }
+  if (B < 0 || n_coarse < 3 || n_coarse > 1024 || n_fine < 1 || n_fine > 4096) { set_error("fine_sampling: unsupported shape B=%lld n_coarse=%d n_fine=%d", (long long)B, n_coarse, n_fine); return NRF_E_INVALID; }
+  if (B == 0) return NRF_OK;
+  const int wpb = 4;
+  const size_t smem = static_cast<size_t>(wpb) * (4 * n_coarse + 2 * n_fine) * sizeof(float);
+  const int grid = static_cast<int>(B / wpb + 1 > 148 * 8 ? 148 * 8 : B / wpb + 1);
+  cudaError_t e = cudaFuncSetAttribute(fine_sampling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  fine_sampling_kernel<<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(origin, dir, z, weights, u, B, n_coarse, n_fine, z_all, pts);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "fine_sampling_kernel launch");
 }
 
 extern "C" int nrf_searchsorted(const float* a, int64_t rows_a, int64_t na, const float* v, int64_t rows_v, int64_t nv,

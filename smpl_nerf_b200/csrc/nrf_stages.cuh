@@ -46,13 +46,13 @@ __device__ inline void composite_ray(float4* raw4, const float* z, const float* 
 }
 
 // Inverse-CDF sampling + sorted merge of one ray by one warp (utils.py:194-264, torchsearchsorted
-// side='right').  w4[i].w = coarse weights; zc[nc] coarse depths; writes zf[nc+nf].
-__device__ inline void sample_ray(const float4* w4, const float* zc, int nc, int nf, const float* u_fine, float* cdf, float* zs,
+// side='right').  w[i*wstride] = coarse weights; zc[nc] coarse depths; writes zf[nc+nf].
+__device__ inline void sample_ray(const float* w, int wstride, const float* zc, int nc, int nf, const float* u_fine, float* cdf, float* zs,
                            float* zf, float* z_new_out, int lane) {
   const int m = nc - 1;     // bins = midpoints (m of them); cdf has m entries; m-1 weights
   // pdf numerators into cdf[1..m-1]; their sum with a butterfly so every lane agrees
   float part = 0.f;
-  for (int i = 1 + lane; i < m; i += 32) { const float w = __fadd_rn(w4[i].w, 1e-5f); cdf[i] = w; part += w; }
+  for (int i = 1 + lane; i < m; i += 32) { const float wi = __fadd_rn(w[i * wstride], 1e-5f); cdf[i] = wi; part += wi; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   __syncwarp();

@@ -1,0 +1,134 @@
+"""Drop-in replacements for the reference's ``utils.py`` hot-path functions and for
+``torchsearchsorted.searchsorted``, each a thin wrapper over one C-ABI call:
+
+    utils.py:114-131  PositionalEncoder   -> PositionalEncoder (encode runs nrf_positional_encoding)
+    utils.py:134-191  raw2outputs         -> raw2outputs
+    utils.py:194-228  sample_pdf          -> sample_pdf
+    utils.py:231-264  fine_sampling       -> fine_sampling
+    torchsearchsorted/src/torchsearchsorted/searchsorted.py:20-53 -> searchsorted (same asserts)
+
+CUDA tensors only -- there is no CPU path in this package.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check
+from .engine import _f32, _u_fine
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'smpl_nerf_b200.ops: {name} must be a CUDA tensor (no CPU fallback)')
+
+
+class PositionalEncoder:
+    """Same constructor/attributes as utils.py:114-125; ``encode`` is one CUDA kernel instead of
+    2L pointwise launches and a cat."""
+
+    def __init__(self, number_frequencies, include_identity):
+        self.number_frequencies = int(number_frequencies)
+        self.include_identity = include_identity
+        self.output_dim = (1 if include_identity else 0) + 2 * self.number_frequencies
+
+    def encode(self, coordinate: torch.Tensor) -> torch.Tensor:
+        _need_cuda(coordinate, 'coordinate')
+        x = _f32(coordinate, 'coordinate', coordinate.device)
+        c = int(x.shape[-1])
+        n = x.numel() // c
+        out = torch.empty(*x.shape[:-1], c * self.output_dim, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(_lib.lib().nrf_positional_encoding(x.data_ptr(), n, c, self.number_frequencies,
+                                                     1 if self.include_identity else 0, out.data_ptr(),
+                                                     _stream(x.device)), 'nrf_positional_encoding')
+        return out
+
+
+def raw2outputs(raw: torch.Tensor, z_vals: torch.Tensor, samples_directions: torch.Tensor, args
+                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (rgb[B,3], weights[B,n], density(alpha)[B,n]); noise is drawn like utils.py:172-174."""
+    _need_cuda(raw, 'raw')
+    dev = raw.device
+    B, n = int(raw.shape[0]), int(raw.shape[1])
+    raw = _f32(raw, 'raw', dev, (B, n, 4))
+    z = _f32(z_vals, 'z_vals', dev, (B, n))
+    dirs = _f32(samples_directions.expand(B, n, 3), 'samples_directions', dev, (B, n, 3))
+    noise = None
+    if float(getattr(args, 'sigma_noise_std', 0.) or 0.) > 0.:
+        noise = torch.normal(0, float(args.sigma_noise_std), (B, n), device=dev)
+    rgb = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    weights = torch.empty(B, n, dtype=torch.float32, device=dev)
+    alpha = torch.empty(B, n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().nrf_raw2outputs(raw.data_ptr(), z.data_ptr(), dirs.data_ptr(),
+                                         noise.data_ptr() if noise is not None else None, B, n,
+                                         1 if args.white_background else 0, rgb.data_ptr(), weights.data_ptr(),
+                                         alpha.data_ptr(), _stream(dev)), 'nrf_raw2outputs')
+    return rgb, weights, alpha
+
+
+def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, args) -> torch.Tensor:
+    _need_cuda(bins, 'bins')
+    dev = bins.device
+    B, m = int(bins.shape[0]), int(bins.shape[1])
+    bins = _f32(bins, 'bins', dev)
+    w = _f32(weights, 'weights', dev, (B, m - 1))
+    nf = int(args.number_fine_samples)
+    out = torch.empty(B, nf, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().nrf_sample_pdf(bins.data_ptr(), w.data_ptr(), _u_fine(nf, dev).data_ptr(), B, m, nf,
+                                        out.data_ptr(), _stream(dev)), 'nrf_sample_pdf')
+    return out
+
+
+def fine_sampling(ray_translation: torch.Tensor, samples_directions: torch.Tensor, z_vals: torch.Tensor,
+                  weights: torch.Tensor, args) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (z_vals[B, nc+nf] sorted, ray_samples_fine[B, nc+nf, 3])."""
+    _need_cuda(z_vals, 'z_vals')
+    dev = z_vals.device
+    B, nc = int(z_vals.shape[0]), int(z_vals.shape[1])
+    nf = int(args.number_fine_samples)
+    o = _f32(ray_translation, 'ray_translation', dev, (B, 3))
+    d = _f32(samples_directions, 'samples_directions', dev, (B, 3))
+    z = _f32(z_vals, 'z_vals', dev)
+    w = _f32(weights, 'weights', dev, (B, nc))
+    z_all = torch.empty(B, nc + nf, dtype=torch.float32, device=dev)
+    pts = torch.empty(B, nc + nf, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().nrf_fine_sampling(o.data_ptr(), d.data_ptr(), z.data_ptr(), w.data_ptr(),
+                                           _u_fine(nf, dev).data_ptr(), B, nc, nf, z_all.data_ptr(), pts.data_ptr(),
+                                           _stream(dev)), 'nrf_fine_sampling')
+    return z_all, pts
+
+
+def searchsorted(a: torch.Tensor, v: torch.Tensor, out: Optional[torch.Tensor] = None, side='left') -> torch.Tensor:
+    """Same contract and assertions as torchsearchsorted.searchsorted (float32 CUDA inputs)."""
+    assert len(a.shape) == 2, "input `a` must be 2-D."
+    assert len(v.shape) == 2, "input `v` must be 2-D."
+    assert (a.shape[0] == v.shape[0] or a.shape[0] == 1 or v.shape[0] == 1), \
+        "`a` and `v` must have the same number of rows or one of them must have only one "
+    assert a.device == v.device, '`a` and `v` must be on the same device'
+    _need_cuda(a, 'a')
+    result_shape = (max(a.shape[0], v.shape[0]), v.shape[1])
+    if out is not None:
+        assert out.device == a.device, "`out` must be on the same device as `a`"
+        assert out.dtype == torch.long, "out.dtype must be torch.long"
+        assert tuple(out.shape) == result_shape, "If the output tensor is provided, its shape must be correct."
+        assert out.is_contiguous(), "`out` must be contiguous"
+    else:
+        out = torch.empty(result_shape, device=v.device, dtype=torch.long)
+    # the reference silently returns garbage for non-contiguous inputs (its README says so); copy instead
+    a32 = _f32(a, 'a', a.device)
+    v32 = _f32(v, 'v', a.device)
+    with torch.cuda.device(a.device):
+        check(_lib.lib().nrf_searchsorted(a32.data_ptr(), a32.shape[0], a32.shape[1], v32.data_ptr(), v32.shape[0],
+                                          v32.shape[1], out.data_ptr(), 1 if side == 'left' else 0,
+                                          _stream(a.device)), 'nrf_searchsorted')
+    return out

@@ -1,0 +1,60 @@
+"""Shared helpers for the test-suite (tests may use oracle/ as the checker)."""
+import glob
+import os
+
+import torch
+
+from oracle import nerf_oracle as O
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+# Tolerances from BASELINE.json north_star: 1e-3 abs on RGB, 1e-4 abs on sigma (and on alpha, which is
+# what the pipelines expose as "densities").
+TOL_RGB = 1e-3
+TOL_SIGMA = 1e-4
+TOL_ALPHA = 1e-4
+
+
+def fixtures():
+    return sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.pt')))
+
+
+def load_fixture(name):
+    return torch.load(os.path.join(GOLDEN_DIR, name + '.pt'), weights_only=False)
+
+
+def nets_for(fx):
+    """Rebuild the fixture's nets from its seed and check the weight checksum."""
+    nets = O.build_nets(fx['kind'], fx['seed'], fx['variant'], **fx['build'])
+    assert O.weight_checksum(list(nets[:3])) == fx['weight_checksum'], \
+        'default-init weights are not reproducible from the seed on this torch build'
+    return nets
+
+
+def args_for(fx, **kw):
+    return O.make_args(run_fine=fx['run_fine'], human_pose_encoding=1 if fx['pose_encoded'] else 0, **kw)
+
+
+def run_oracle(kind, nets, args, data, **kw):
+    c, f, w, pe, de, he = nets
+    if kind == 'nerf':
+        return O.nerf_forward(c, f, pe, de, args, data, **kw)
+    if kind == 'append':
+        return O.append_to_nerf_forward(c, f, pe, de, he, args, data, **kw)
+    return O.smpl_nerf_forward(c, f, w, pe, de, he, args, data, **kw)
+
+
+def to_cuda(nets, data, dev='cuda:0'):
+    c, f, w, pe, de, he = nets
+    import copy
+    g = [copy.deepcopy(m).to(dev) if m is not None else None for m in (c, f, w)]
+    return (g[0], g[1], g[2], pe, de, he), [t.to(dev) for t in data]
+
+
+def alpha_mask_well_conditioned(sigma_ref, thresh=1e-3):
+    """The last sample's alpha is 1-exp(-relu(sigma)*1e10): a step function of sigma at 0, so any
+    implementation (including the reference in another precision) may flip it when |sigma| ~ 0.
+    Compare alpha there only where the reference sigma is clearly away from the kink."""
+    m = torch.ones_like(sigma_ref, dtype=torch.bool)
+    m[..., -1] = sigma_ref[..., -1].abs() > thresh
+    return m

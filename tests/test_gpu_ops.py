@@ -1,0 +1,76 @@
+"""Stand-alone ops of the C ABI against the oracle / numpy (GPU)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from smpl_nerf_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.mark.parametrize('L,ident,c', [(10, False, 3), (4, False, 3), (10, False, 2), (3, True, 3), (0, True, 3)])
+def test_positional_encoding(L, ident, c):
+    torch.manual_seed(0)
+    x = torch.randn(37, 5, c) * 2
+    want = O.Encoder(L, ident).encode(x)
+    got = ops.PositionalEncoder(L, ident).encode(x.to(DEV)).cpu()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize('white', [0, 1])
+def test_raw2outputs(white):
+    torch.manual_seed(1)
+    B, n = 50, 192
+    raw = torch.randn(B, n, 4)
+    z = torch.sort(torch.rand(B, n) * 3 + 1, -1)[0]
+    dirs = torch.randn(B, n, 3)
+    want = O.composite(raw, z, dirs, white_background=white)
+    args = O.make_args(white_background=white)
+    got = ops.raw2outputs(raw.to(DEV), z.to(DEV), dirs.to(DEV), args)
+    for a, b, tol in zip(got, want, (1e-5, 1e-6, 1e-6)):
+        assert float((a.cpu() - b).abs().max()) <= tol
+
+
+def test_sample_pdf():
+    torch.manual_seed(2)
+    B = 64
+    z = torch.sort(torch.rand(B, 64) * 3 + 1, -1)[0]
+    bins = .5 * (z[:, 1:] + z[:, :-1])
+    w = torch.rand(B, 62) ** 6
+    w[0] = 0
+    w[1, 5:] = 0
+    want = O.inverse_cdf(bins, w, 128)
+    got = ops.sample_pdf(bins.to(DEV), w.to(DEV), O.make_args()).cpu()
+    err = (got - want).abs()
+    assert float(torch.quantile(err, 0.99)) <= 1e-5 and float(err.max()) <= 1e-3
+
+
+@pytest.mark.parametrize('Ba,Bv', [(1, 1), (100, 100), (1, 100), (100, 1)])
+@pytest.mark.parametrize('A,V', [(1, 1), (50, 12), (500, 120), (63, 128)])
+@pytest.mark.parametrize('side', ['left', 'right'])
+def test_searchsorted_matches_numpy(Ba, Bv, A, V, side):
+    """Same grid as torchsearchsorted/test/test_searchsorted.py:34-44 (numpy row-wise oracle), seeded."""
+    rng = np.random.RandomState(A * 1000 + V + Ba)
+    a = np.sort(rng.rand(Ba, A).astype(np.float32), -1)
+    v = rng.rand(Bv, V).astype(np.float32)
+    got = ops.searchsorted(torch.from_numpy(a).to(DEV), torch.from_numpy(v).to(DEV), side=side)
+    assert got.dtype == torch.int64 and tuple(got.shape) == (max(Ba, Bv), V)
+    want = np.stack([np.searchsorted(a[i if Ba > 1 else 0], v[i if Bv > 1 else 0], side=side) for i in range(max(Ba, Bv))])
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_searchsorted_ties_and_out_argument():
+    a = torch.tensor([[0., 1., 1., 1., 2., 3.]], device=DEV)
+    v = torch.tensor([[-1., 0., 1., 1.5, 3., 4.]], device=DEV)
+    assert ops.searchsorted(a, v, side='left').tolist() == [[0, 0, 1, 4, 5, 6]]
+    assert ops.searchsorted(a, v, side='right').tolist() == [[0, 1, 4, 4, 6, 6]]
+    out = torch.empty(1, 6, dtype=torch.long, device=DEV)
+    res = ops.searchsorted(a, v, out=out, side='right')
+    assert res is out
+    with pytest.raises(AssertionError):
+        ops.searchsorted(a, v, out=torch.empty(1, 6, dtype=torch.int32, device=DEV))
+    with pytest.raises(AssertionError):
+        ops.searchsorted(a[0], v)
