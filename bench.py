@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- rays/sec of the fused SMPL-NeRF forward on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pipeline forward over one 128x128 view (16,384 rays) of the synthetic scene
+(smpl_nerf_b200/scene.py), BASELINE.json configs[1] by default:
+SmplNerfPipeline, netdepth 8, 64 coarse + 128 fine samples, random-init ("dense" variant) weights.
+
+Printed JSON line (rank 0):
+  value      rays/s with inputs resident in HBM (CUDA events over exactly K steps, max over ranks)
+  e2e        rays/s through the public pipeline API with HOST (pinned) inputs: H2D of the step's
+             inputs and D2H of rgb_fine inside the timed region
+  roofline   algorithmic MLP FLOPs (2 x MACs of the reference's nn.Linear layers, un-folded,
+             un-hoisted) per launch / average kernel duration, against the measured bf16 peak
+  cpu_baseline  the oracle port of the reference's PyTorch-CPU path on this box's host cores
+`--impl reference` times that CPU path alone (rank 0 only), on bounded samples of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: kind, image side, n_coarse, n_fine, run_fine, netdepth, skips
+    'cfg2': dict(kind='smpl', side=128, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4],
+                 text='smpl_nerf_pipeline, 128x128, netdepth=8, 64 coarse + 128 fine (BASELINE configs[1])'),
+    'cfg4': dict(kind='append', side=128, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4],
+                 text='append_to_nerf_pipeline, 128x128, netdepth=8, 64+128 (BASELINE configs[3])'),
+    'nerf': dict(kind='nerf', side=128, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4],
+                 text='nerf_pipeline, 128x128, netdepth=8, 64+128'),
+    'cfg1': dict(kind='nerf', side=128, n_coarse=32, n_fine=0, run_fine=0, n_layers=4, skips=[],
+                 text='vanilla nerf_pipeline, 128x128, netdepth=4, 32 coarse, run_fine=0 (BASELINE configs[0])'),
+    'cfg5': dict(kind='smpl', side=512, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4],
+                 text='smpl_nerf_pipeline, 512x512 frame (BASELINE configs[4])'),
+}
+N_VIEWS = 8          # rotating distinct input views so that consecutive steps never reuse inputs
+
+
+def build_models(w, seed=0):
+    """Random-init nets of the workload's architecture ("dense" variant: sigma head x20, bias +1 so
+    that alpha spans 0..1 and the hierarchical sampler has structure to follow)."""
+    from smpl_nerf_b200.models import RenderRayNet, WarpFieldNet
+    from smpl_nerf_b200.ops import PositionalEncoder
+    torch.manual_seed(seed)
+    pe, de, he = PositionalEncoder(10, False), PositionalEncoder(4, False), PositionalEncoder(10, False)
+    A = 2 * he.output_dim if w['kind'] == 'append' else 0
+    coarse = RenderRayNet(w['n_layers'], 256, 3 * pe.output_dim, 3 * de.output_dim, A, list(w['skips']))
+    fine = RenderRayNet(w['n_layers'], 256, 3 * pe.output_dim, 3 * de.output_dim, A, list(w['skips']))
+    warp = WarpFieldNet(8, 256, 3 * pe.output_dim, 2 * he.output_dim) if w['kind'] == 'smpl' else None
+    with torch.no_grad():
+        for net in (coarse, fine):
+            net.sigma_out_layer.weight.mul_(20.)
+            net.sigma_out_layer.bias.add_(1.)
+    return coarse, fine, warp, pe, de, he
+
+
+def make_args(w):
+    from types import SimpleNamespace
+    return SimpleNamespace(default_device=None, sigma_noise_std=0., white_background=1, run_fine=w['run_fine'],
+                           number_fine_samples=w['n_fine'] if w['run_fine'] else 128, human_pose_encoding=1)
+
+
+def flops_per_ray(w, coarse, fine, warp):
+    mac = lambda net: sum(m.weight.numel() for m in net.modules() if isinstance(m, torch.nn.Linear))
+    nc, na = w['n_coarse'], w['n_coarse'] + (w['n_fine'] if w['run_fine'] else 0)
+    total = mac(coarse) * nc + (mac(fine) * na if w['run_fine'] else 0)
+    if warp is not None:
+        total += mac(warp) * (nc + (na if w['run_fine'] else 0))
+    return 2.0 * total
+
+
+def make_views(w, rank, n_views):
+    from smpl_nerf_b200 import scene
+    views = []
+    for v in range(n_views):
+        rays = scene.make_rays(w['side'], w['side'], w['n_coarse'], phi=5.0 + 3 * v, theta=(37.0 * (v + 1) + 11 * rank) % 360,
+                               arm_angle_deg=(60.0 / 9) * ((v + rank) % 10), seed=1000 * rank + v)
+        views.append(scene.data_list(rays, w['kind']))
+    return views
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_reference_rays_per_s(w, state, n_batches, batch, warmup=1, seed=0):
+    """The reference's PyTorch-CPU pipeline (oracle port, bit-identical to it on the build box) on
+    this machine's host cores.  The ONLY place bench.py touches oracle/."""
+    from oracle import nerf_oracle as O
+    from smpl_nerf_b200 import scene
+    torch.set_num_threads(os.cpu_count() or 1)
+    c, f, wn, pe, de, he = O.build_nets(w['kind'], seed, 'default', n_layers=w['n_layers'], skips=tuple(w['skips']))
+    for net, sd in zip((c, f, wn), state):
+        if net is not None:
+            net.load_state_dict(sd)
+    args = O.make_args(run_fine=w['run_fine'], number_fine_samples=w['n_fine'] if w['run_fine'] else 128)
+    rays = scene.make_rays(w['side'], w['side'], w['n_coarse'], seed=seed)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + n_batches):
+            lo = (i * batch) % max(1, rays['z_vals'].shape[0] - batch + 1)
+            data = scene.data_list(rays, w['kind'], slice(lo, lo + batch))
+            t0 = time.perf_counter()
+            if w['kind'] == 'nerf':
+                O.nerf_forward(c, f, pe, de, args, data)
+            elif w['kind'] == 'append':
+                O.append_to_nerf_forward(c, f, pe, de, he, args, data)
+            else:
+                O.smpl_nerf_forward(c, f, wn, pe, de, he, args, data)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return batch / statistics.median(times), times
+
+
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
+
+
+def run_reference(a, w, rank, world):
+    """--impl reference: the CPU path of the reference, rank 0 only, bounded sample per step."""
+    if rank != 0:
+        return
+    coarse, fine, warp, *_ = build_models(w)
+    state = [m.state_dict() if m is not None else None for m in (coarse, fine, warp)]
+    batch = 256 if w is WORKLOADS['cfg1'] else 1024
+    t0 = time.perf_counter()
+    rps, times = cpu_reference_rays_per_s(w, state, a.steps, batch, warmup=a.warmup)
+    cores = os.cpu_count() or 1
+    line = {
+        'impl': 'reference', 'metric': 'rays/sec', 'value': rps, 'unit': 'rays/s', 'n_gpus': a.gpus, 'steps': a.steps,
+        'warmup': a.warmup, 'ms_per_step': 1e3 * statistics.median(times), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': w['text'], 'rays_per_step': batch, 'timing': 'time.perf_counter, median over steps'},
+        'cpu_baseline': {'value': rps, 'unit': 'rays/s', 'cores': cores, 'kind': 'port', 'cpu': cpu_model(),
+                         'sample': f'{a.steps} steps x {batch} rays of the workload, torch {torch.__version__} CPU, '
+                                   f'{cores} threads; oracle/nerf_oracle.py = bit-identical restatement of the reference '
+                                   f'pipeline (reference tree is not on this box)'},
+        'e2e': {'value': rps, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'wall_s': time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(a, w, rank, world, local_rank):
+    import torch.distributed as dist
+    from smpl_nerf_b200 import dist as nd
+    from smpl_nerf_b200 import engine
+    from smpl_nerf_b200.models import AppendToNerfPipeline, NerfPipeline, SmplNerfPipeline
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    coarse, fine, warp, pe, de, he = build_models(w)
+    state = [m.state_dict() if m is not None else None for m in (coarse, fine, warp)]
+    fl_ray = flops_per_ray(w, coarse, fine, warp)
+    coarse, fine = coarse.to(dev), fine.to(dev)
+    warp = warp.to(dev) if warp is not None else None
+    pargs = make_args(w)
+    if w['kind'] == 'smpl':
+        pipe = SmplNerfPipeline(coarse, fine, warp, pargs, pe, de, he)
+    elif w['kind'] == 'append':
+        pipe = AppendToNerfPipeline(coarse, fine, pargs, pe, de, he)
+    else:
+        pipe = NerfPipeline(coarse, fine, pargs, pe, de)
+    views_host = [[t.pin_memory() for t in v] for v in make_views(w, rank, N_VIEWS)]
+    views = [[t.to(dev) for t in v] for v in views_host]
+    rays = int(views[0][0].shape[0])
+    n_total = rays * world
+    stream = torch.cuda.current_stream(dev)
+    precision = 1 if a.precision == 'fast' else 0
+
+    def step(i, data):
+        out = engine.render(w['kind'], coarse, fine, warp, pargs, pe, de, he, data, precision=precision)
+        img = out['rgb_fine']
+        if world > 1:
+            img = nd.gather_tiles(img, n_total)     # one all-gather of the rendered tiles over NVLink
+        return img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for i in range(a.warmup):
+            step(i, views[i % N_VIEWS])
+        # ---------------- device-resident throughput: exactly K steps
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(a.steps):
+            ev[i][0].record(stream)
+            img = step(i, views[(a.warmup + i) % N_VIEWS])
+            ev[i][1].record(stream)
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms_total = e0.elapsed_time(e1)
+        ms_steps = [x.elapsed_time(y) for x, y in ev]
+        # ---------------- end to end through the public API: host inputs, H2D + D2H inside the timed region
+        host_img = torch.empty(n_total if world > 1 else rays, 3).pin_memory()
+        for i in range(min(2, a.warmup)):
+            data = [t.to(dev, non_blocking=True) for t in views_host[i % N_VIEWS]]
+            host_img.copy_(step(i, data), non_blocking=True)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for i in range(a.steps):
+            data = [t.to(dev, non_blocking=True) for t in views_host[(a.warmup + i) % N_VIEWS]]
+            host_img.copy_(step(i, data), non_blocking=True)
+        f1.record(stream)
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+    h2d = sum(t.numel() * t.element_size() for t in views_host[0])
+    d2h = host_img.numel() * host_img.element_size()
+    t = torch.tensor([ms_total, ms_e2e, statistics.mean(ms_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e, ms_kernel = [float(x) for x in t.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        pass
+    peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a multi-second loop)' if peaks else \
+        'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
+    value = n_total * a.steps / (ms_total / 1e3)
+    achieved_tf = rays * fl_ray / (ms_kernel / 1e3) / 1e12     # per launch, per GPU
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'latest_traffic.json'))).get(a.workload)
+    except (OSError, ValueError):
+        pass
+    line = {
+        'metric': 'rays/sec', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+        'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16x3-split (fp32-equivalent), fp32 accumulate' if not precision else 'f16 (1 pass), fp32 accumulate',
+        'data': 'synthetic',
+        'config': {'workload': w['text'], 'rays_per_step_per_gpu': rays, 'precision_mode': a.precision,
+                   'weights': 'random init (seed 0, sigma head x20, bias +1)', 'algebraic_fold': False,
+                   'l2_policy': f'rotating over {N_VIEWS} distinct views; each step reads {h2d / 1e6:.1f} MB of inputs and '
+                                f'writes >120 MB of outputs (> 126 MB L2 together)',
+                   'parallelism': f'rays sharded over {world} GPU(s), weights replicated, one all-gather of rgb_fine per step'},
+        'clocks': clocks,
+        'e2e': {'value': n_total * a.steps / (ms_e2e / 1e3), 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': a.steps * engine.launches_per_render(),
+        'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
+                     'traffic': traffic, 'flop_per_ray': fl_ray, 'kernel': 'nrf_fused_kernel', 'kernel_ms': ms_kernel,
+                     'peak_source': peak_src,
+                     'note': 'algorithmic FLOPs = 2 x MACs of the reference nn.Linear layers; the parity mode executes 3 fp16 '
+                             'MMA passes per algorithmic MAC, so the tensor pipe does 3x this work'},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        batch = 256 if a.workload == 'cfg1' else 1024
+        rps, times = cpu_reference_rays_per_s(w, state, 3, batch, warmup=1)
+        cores = os.cpu_count() or 1
+        line['cpu_baseline'] = {'value': rps, 'unit': 'rays/s', 'cores': cores, 'kind': 'port', 'cpu': cpu_model(),
+                                'sample': f'median of 3 batches of {batch} rays of the same workload after 1 warm-up batch, '
+                                          f'{cores} torch threads'}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--precision', default='parity', choices=['parity', 'fast'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == 'ours' else max(a.warmup, 1)
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world == 1 and a.gpus > 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={a.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29541'), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    w = WORKLOADS[a.workload]
+    if a.impl == 'reference':
+        run_reference(a, w, rank, world)
+    else:
+        run_ours(a, w, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()
