@@ -159,9 +159,15 @@ int nrf_fine_sampling(const float* origin, const float* dir, const float* z, con
 int nrf_searchsorted(const float* a, int64_t rows_a, int64_t na, const float* v, int64_t rows_v, int64_t nv,
                      int64_t* res, int32_t side_left, void* stream);
 
-/* tcgen05 self-test: D[128,128] = A[128,64] * B[128,64]^T with fp16 operands staged through the same
- * swizzled shared-memory layout / descriptors the renderer uses.  a, b: fp32 (rounded to fp16 inside). */
+/* tcgen05 self-test: D[128,256] = A[128,64] * B[256,64]^T with fp16 operands staged through the same
+ * swizzled shared-memory layouts / descriptors the renderer uses (A: SWIZZLE_128B tile, B: two
+ * [256 x 32] SWIZZLE_64B weight stages, N = 256 per instruction).  a, b: fp32 (rounded to fp16 inside). */
 int nrf_selftest_umma(const float* a, const float* b, float* d, void* stream);
+
+/* Developer diagnostic: tcgen05.mma issue-rate probe on n_ctas SMs (one CTA each).  mode bit0: N=256 per
+ * instruction (else 128); bit1: stream `wsrc` (device, >= 64 KiB) through a TMA ring concurrently;
+ * bit2: two A passes per B stage.  cycles[n_ctas] receives the SM-clock cycles of `iters` K=64 steps. */
+int nrf_bench_umma(int mode, int iters, const void* wsrc, size_t wsrc_bytes, long long* cycles, int n_ctas, void* stream);
 
 #ifdef __cplusplus
 }

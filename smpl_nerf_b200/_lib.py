@@ -15,7 +15,7 @@ from typing import List
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libnrf_b200.so')
-SOURCES = ['nrf_pack.cu', 'nrf_fused.cu', 'nrf_ops.cu']
+SOURCES = ['nrf_pack.cu', 'nrf_fused.cu', 'nrf_ops.cu', 'nrf_diag.cu']
 HEADERS = ['nrf_plan.h', 'nrf_ptx.cuh', 'nrf_stages.cuh', os.path.join('..', '..', 'include', 'nrf_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
@@ -57,7 +57,7 @@ class RenderIO(C.Structure):
 EXPORTS = ['nrf_last_error', 'nrf_abi_version', 'nrf_device_supported', 'nrf_raynet_packed_bytes',
            'nrf_warpnet_packed_bytes', 'nrf_pack_raynet', 'nrf_pack_warpnet', 'nrf_render', 'nrf_render_launches',
            'nrf_positional_encoding', 'nrf_raw2outputs', 'nrf_sample_pdf', 'nrf_fine_sampling', 'nrf_searchsorted',
-           'nrf_selftest_umma']
+           'nrf_selftest_umma', 'nrf_bench_umma']
 
 
 def _stale() -> bool:
@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
     L.nrf_searchsorted.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                    C.c_int32, C.c_void_p]
     L.nrf_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nrf_bench_umma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     if L.nrf_abi_version() != 1:
         raise RuntimeError('libnrf_b200.so ABI version mismatch; rebuild')
     _lib = L

@@ -31,15 +31,16 @@
 
 namespace nrf {
 
-constexpr int kNumStages = 3;
+constexpr int kNumStages = 3;                     // weight ring slots (2 when the per-ray tables need the room)
 constexpr uint32_t kStageBytes = 16384;            // 128 rows x 128 B
 constexpr uint32_t kChunkBytes = 16384;            // one [128 x 64] fp16 operand tile
 constexpr uint32_t kOffA = 0;                      // 4 chunks x (hi, lo)
 constexpr uint32_t kOffAux = 4 * 2 * kChunkBytes;  // 131072
 constexpr uint32_t kOffRing = kOffAux + 2 * kChunkBytes;
-constexpr uint32_t kOffMisc = kOffRing + kNumStages * kStageBytes;  // 212992
+constexpr uint32_t kOffXchg = kOffA + 3 * 2 * kChunkBytes;   // head-partial exchange: aliases A chunk 3 (hi) while it is dead
 constexpr uint32_t kSmemLimit = 232448;            // 227 KB opt-in maximum per CTA
-constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kRayVec = 8 + kMaxRayFeat + 32;      // unit direction[3], raw pose pair[2]
 constexpr int kRayFloats = kRayVec + 8;            // o[3] d[3] |d| valid | pose feats[64] | dir feats[32] | unit d, pose
@@ -56,7 +57,8 @@ struct RenderParams {
   int64_t n_rays;
   int32_t kind, n_coarse, n_fine, n_all, run_fine, white_bkgd, fast;
   int32_t pose_freqs, pose_identity, pose_encoded, pose_stride, pose_col0, pose_col1, pose_dim;
-  int32_t G, tiles_f, n_groups;
+  int32_t G, tiles_f, n_groups, n_stages;
+  uint32_t off_misc;   // byte offset of the barrier + per-ray area (behind the weight ring)
   // float offsets inside the misc area (after the barriers)
   uint32_t o_ray, o_rb, o_rbw, o_raw, o_zc, o_zf, o_dnorm, o_scratch;
 };
@@ -64,86 +66,119 @@ struct RenderParams {
 struct Smem {
   uint8_t* base;
   float* misc;
-  __device__ uint32_t bar(int i) const { return smem_u32(base + kOffMisc) + 8u * i; }
+  uint32_t bar0;
+  uint32_t n_stages;
+  __device__ uint32_t bar(int i) const { return bar0 + 8u * i; }
 };
 
 // ---------------------------------------------------------------------------------- small helpers
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-  return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
-}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-
-// Write 8 consecutive features (one 16-byte swizzle chunk `cc` of row `row`) as hi/lo fp16 into an
-// operand tile pair (hi tile at `tile`, lo tile at `tile + kChunkBytes`).
-__device__ __forceinline__ void store_feat8(uint32_t tile, int row, int cc, const float (&x)[8], bool fast) {
-  __half h[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) split_f16(x[i], h[i], l[i]);
-  const uint32_t ofs = static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>((cc ^ row) & 7) << 4);
-  st_shared_v4(tile + ofs, pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
-  if (!fast)
-    st_shared_v4(tile + kChunkBytes + ofs, pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7]));
+// {x0 -> low half, x1 -> high half}, round-to-nearest, clamped to +-65504 (SASS: F2FP.SATFINITE.F16.F32.PACK_AB)
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float x0, float x1) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
+}
+// fp32 pair -> packed fp16 hi pair and packed fp16 residual pair (x ~= hi + lo, ~22 significant bits)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& h, uint32_t& l) {
+  h = cvt_f16x2_sat(x0, x1);
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+  l = cvt_f16x2_sat(x0 - f.x, x1 - f.y);
 }
 
-// Encoder features [32*HSEL, 32*HSEL+32) of vector v in ENGINE order (see enc_ref_col) -> aux tile.
-template <int HSEL>
-__device__ __forceinline__ void write_encoding_half(uint32_t aux_tile, int row, float vx, float vy, float vz, int freqs,
-                                                    int identity, bool fast) {
+// Write 16 consecutive features (16-byte swizzle chunks cc0, cc0+1 of row `row`; cc0 even) as hi/lo fp16
+// into an operand tile pair (hi tile at `tile`, lo tile at `tile + kChunkBytes`).  amax2 accumulates
+// max |hi| (packed halves) for the fp16-range status flag.
+__device__ __forceinline__ void store_feat16(uint32_t tile, int row, int cc0, const float (&x)[16], bool fast, __half2& amax2) {
+  uint32_t h[8], l[8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float f[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int p = 16 * HSEL + 4 * q + i;   // (freq, comp) pair index; compile-time after unrolling
-      const int k = p / 3, comp = p % 3;
-      const float v = comp == 0 ? vx : (comp == 1 ? vy : vz);
-      if (p < 3 * freqs) {
-        float s, c;
-        sincosf(v * static_cast<float>(1u << k), &s, &c);
-        f[2 * i] = s; f[2 * i + 1] = c;
-      } else {
-        const int c0 = 2 * p - 6 * freqs;   // identity components follow the sin/cos block
-        const float id0 = (identity && c0 >= 0 && c0 < 3) ? (c0 == 0 ? vx : (c0 == 1 ? vy : vz)) : 0.f;
-        const int c1 = c0 + 1;
-        const float id1 = (identity && c1 >= 0 && c1 < 3) ? (c1 == 0 ? vx : (c1 == 1 ? vy : vz)) : 0.f;
-        f[2 * i] = id0; f[2 * i + 1] = id1;
-      }
-    }
-    store_feat8(aux_tile, row, 4 * HSEL + q, f, fast);
+  for (int i = 0; i < 8; ++i) {
+    split2(x[2 * i], x[2 * i + 1], h[i], l[i]);
+    amax2 = __hmax2(amax2, __habs2(*reinterpret_cast<const __half2*>(&h[i])));
+  }
+  const uint32_t rofs = static_cast<uint32_t>(row) * 128u;
+  const uint32_t o0 = rofs + (static_cast<uint32_t>((cc0 ^ row) & 7) << 4);
+  const uint32_t o1 = rofs + (static_cast<uint32_t>(((cc0 + 1) ^ row) & 7) << 4);
+  st_shared_v4(tile + o0, h[0], h[1], h[2], h[3]);
+  st_shared_v4(tile + o1, h[4], h[5], h[6], h[7]);
+  if (!fast) {
+    st_shared_v4(tile + kChunkBytes + o0, l[0], l[1], l[2], l[3]);
+    st_shared_v4(tile + kChunkBytes + o1, l[4], l[5], l[6], l[7]);
   }
 }
-__device__ __forceinline__ void write_encoding(uint32_t aux_tile, int row, int hsel, float vx, float vy, float vz, int freqs,
+
+// sin and cos of a (|a| < ~1e5) to ~1.2 ulp: 2-term Cody-Waite reduction by pi/2 (exact under FMA for
+// the encoder's arguments x * 2^k) and the Cephes sinf/cosf minimax polynomials on [-pi/4, pi/4].
+// Replaces libdevice sincosf, whose slow path (Payne-Hanek) bloats the kernel when inlined 100x.
+__device__ __forceinline__ void sincos_pe(float a, float& s_out, float& c_out) {
+  const float t = fmaf(a, 0.636619747f, 12582912.f);
+  const int qi = __float_as_int(t);
+  const float q = t - 12582912.f;
+  float r = fmaf(q, -1.57079637050628662109375f, a);
+  r = fmaf(q, 4.37113900018624283e-8f, r);
+  const float z = r * r;
+  float s = fmaf(fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f), z, -1.6666654611e-1f);
+  s = fmaf(s * z, r, r);
+  float c = fmaf(fmaf(fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z, -0.5f);
+  c = fmaf(c, z, 1.0f);
+  float ss = (qi & 1) ? c : s, cc = (qi & 1) ? s : c;
+  if (qi & 2) ss = -ss;
+  if ((qi + 1) & 2) cc = -cc;
+  s_out = ss; c_out = cc;
+}
+
+// Encoder features [16*cg, 16*cg+16) of vector v in ENGINE order (see enc_ref_col) -> aux tile:
+// (freq k, component) pair p owns features 2p (sin) and 2p+1 (cos); identity components follow.
+__device__ __forceinline__ void write_encoding(uint32_t aux_tile, int row, int cg, float vx, float vy, float vz, int freqs,
                                                int identity, bool fast) {
-  if (hsel == 0) write_encoding_half<0>(aux_tile, row, vx, vy, vz, freqs, identity, fast);
-  else write_encoding_half<1>(aux_tile, row, vx, vy, vz, freqs, identity, fast);
+  float f[16];
+  int p = 8 * cg, k = p / 3, comp = p - 3 * k;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float v = comp == 0 ? vx : (comp == 1 ? vy : vz);
+    if (p < 3 * freqs) {
+      sincos_pe(v * __int_as_float((127 + k) << 23), f[2 * i], f[2 * i + 1]);
+    } else {
+      const int c0 = 2 * p - 6 * freqs, c1 = c0 + 1;   // identity components follow the sin/cos block
+      f[2 * i] = (identity && c0 < 3) ? (c0 == 0 ? vx : (c0 == 1 ? vy : vz)) : 0.f;
+      f[2 * i + 1] = (identity && c1 < 3) ? (c1 == 1 ? vy : vz) : 0.f;
+    }
+    ++p;
+    if (++comp == 3) { comp = 0; ++k; }
+  }
+  __half2 dummy = __floats2half2_rn(0.f, 0.f);
+  store_feat16(aux_tile, row, 2 * cg, f, fast, dummy);
 }
 
 // ---------------------------------------------------------------------------------- roles
-struct RingState { uint32_t stage = 0, phase = 0; __device__ void advance() { if (++stage == kNumStages) { stage = 0; phase ^= 1; } } };
+struct RingState { uint32_t stage = 0, phase = 0; __device__ void advance(uint32_t n) { if (++stage == n) { stage = 0; phase ^= 1; } } };
 
 __device__ __forceinline__ void producer_layer(const Smem& sm, const uint8_t* blob, const Layer& L, RingState& rs, bool fast) {
-  const uint32_t stage_bytes = (L.n_out / 2u) * 128u;
+  const uint32_t stage_bytes = L.n_out * 64u;      // one [n_out x 32] fp16 tile
   const uint8_t* src = blob + L.stream_ofs;
   for (int kc = 0; kc < L.nk; ++kc) {
     for (int part = 0; part < 4; ++part, src += stage_bytes) {
-      if (fast && part >= 2) continue;
+      if (fast && (part & 1)) continue;            // lo stages are not streamed in fast mode
       mbar_wait(sm.bar(BAR_EMPTY + rs.stage), rs.phase ^ 1);
       mbar_arrive_expect_tx(sm.bar(BAR_FULL + rs.stage), stage_bytes);
       bulk_g2s(smem_u32(sm.base + kOffRing) + rs.stage * kStageBytes, src, stage_bytes, sm.bar(BAR_FULL + rs.stage));
-      rs.advance();
+      rs.advance(sm.n_stages);
     }
   }
 }
 
 struct MmaState { RingState rs; uint32_t a_phase = 0; uint32_t layer_ctr = 0; };
 
+// One layer: for every 64-feature K-chunk, four weight stages (hi/lo x two 32-feature halves); the hi
+// stage multiplies both the hi and the lo activations, the lo stage only the hi activations:
+//   x*w ~= xh*wh + xl*wh + xh*wl.     Every instruction is M=128 x N=n_out x K=16.
 __device__ __forceinline__ void mma_layer(const Smem& sm, uint32_t tmem_base, const Layer& L, MmaState& st, bool fast) {
   const uint32_t acc = tmem_base + (st.layer_ctr & 1u) * 256u;
-  const uint32_t n_half = L.n_out / 2u;
-  const uint32_t idesc = umma_idesc_f16(128, n_half);
+  const uint32_t idesc = umma_idesc_f16(128, L.n_out);
   const uint32_t a_base = smem_u32(sm.base);
+  uint32_t accumulate = 0;
   for (int kc = 0; kc < L.nk; ++kc) {
     const int src = L.ksrc[kc];
     if (src != kSrcAux || (L.flags & LF_AUX_WAIT)) {
@@ -154,37 +189,38 @@ __device__ __forceinline__ void mma_layer(const Smem& sm, uint32_t tmem_base, co
     const uint32_t a_hi = a_base + (src == kSrcAux ? kOffAux : kOffA + static_cast<uint32_t>(src) * 2u * kChunkBytes);
     const uint32_t a_lo = a_hi + kChunkBytes;
     for (int part = 0; part < 4; ++part) {
-      if (fast && part >= 2) continue;
-      const uint32_t half = part & 1, is_lo = part >> 1;
+      if (fast && (part & 1)) continue;
+      const uint32_t kh = part >> 1, is_lo = part & 1;
       mbar_wait(sm.bar(BAR_FULL + st.rs.stage), st.rs.phase);
       tc_fence_after_sync();
-      const uint32_t b_addr = a_base + kOffRing + st.rs.stage * kStageBytes;
-      const uint32_t d_tmem = acc + half * n_half;
+      const uint64_t bdesc = umma_desc_sw64(a_base + kOffRing + st.rs.stage * kStageBytes);
       const int n_apass = (is_lo || fast) ? 1 : 2;
       for (int ap = 0; ap < n_apass; ++ap) {
-        const uint64_t adesc = umma_desc_sw128(ap == 0 ? a_hi : a_lo);
-        const uint64_t bdesc = umma_desc_sw128(b_addr);
+        const uint64_t adesc = umma_desc_sw128(ap == 0 ? a_hi : a_lo) + 4u * kh;   // +64 bytes per 32-feature half
 #pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks) {
-          const uint32_t accumulate = (kc == 0 && is_lo == 0 && ap == 0 && ks == 0) ? 0u : 1u;
-          umma_f16_ss(d_tmem, adesc + 2u * ks, bdesc + 2u * ks, idesc, accumulate);   // +32 bytes per K=16 step
+        for (uint32_t ks = 0; ks < 2; ++ks) {
+          umma_f16_ss(acc, adesc + 2u * ks, bdesc + 2u * ks, idesc, accumulate);   // +32 bytes per K=16 step
+          accumulate = 1;
         }
       }
       umma_commit(sm.bar(BAR_EMPTY + st.rs.stage));   // frees the ring slot when these MMAs are done
-      st.rs.advance();
+      st.rs.advance(sm.n_stages);
     }
   }
   umma_commit(sm.bar(BAR_ACC + (st.layer_ctr & 1u)));   // accumulator complete -> epilogue
   st.layer_ctr++;
 }
 
-// Per-thread state of an epilogue thread.
+// Per-thread state of an epilogue thread: row = 32*q + lane (q = warp % 4 selects the TMEM lane
+// quarter this warp may read), cg = column group: the thread owns columns 64j + 16cg .. +16 of every
+// 64-feature chunk j, so chunk j of the next layer's A operand completes after 1/nch of the epilogue.
 struct EpiCtx {
-  int warp, lane, q, hsel, row, tid;   // tid: 0..255 within the epilogue group
+  int warp, lane, q, cg, row, tid;     // tid: 0..511 within the epilogue group
   uint32_t acc_phase = 0;              // bit b: parity to wait for on accumulator b
   uint32_t layer_ctr = 0;
   uint32_t tmem_base;
   uint32_t lane_taddr;                 // TMEM lane field for this warp's quarter
+  __half2 amax2;                       // running max |activation| (fp16-range status flag)
 };
 
 __device__ __forceinline__ void epi_signal(const Smem& sm, const EpiCtx& c, int which) {
@@ -196,103 +232,95 @@ __device__ __forceinline__ void epi_signal(const Smem& sm, const EpiCtx& c, int 
 
 struct HeadOut { float h0, h1, h2, sig; };
 
-// Epilogue of one MMA layer for this thread's row and its half of the columns.
-//   g: ray index inside the group of this thread's row (for per-ray bias), valid: row has a real sample
+__device__ __forceinline__ void ld_f16(const float* p, float (&b)[16]) {   // 16 consecutive floats, 16-byte aligned
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+    b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void ldg_f16(const float* p, float (&b)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+    b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ float dot16(const float (&x)[16], const float (&w)[16], float acc) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc = fmaf(x[i], w[i], acc);
+  return acc;
+}
+
+// Epilogue of one MMA layer for this thread's row and its 16-column slice of every chunk.
+//   kRelu: out = relu(acc + bias) (else acc + bias)     kWriteA: out -> next layer's A operand chunks
+//   kHead3: 3-row head dot products (rgb / warp)        kSigma: sigma head dot product
+//   g: ray index inside the group of this thread's row (selects the per-ray bias vector)
+template <bool kRelu, bool kWriteA, bool kHead3, bool kSigma>
 __device__ __forceinline__ void epilogue_layer(const Smem& sm, const RenderParams& P, const NetPlan& net, const float* f32,
-                                               const float* rb_base, const Layer& L, EpiCtx& c, int g, HeadOut& ho,
-                                               bool& overflow) {
+                                               const float* rb_base, const Layer& L, EpiCtx& c, int g, HeadOut& ho) {
   const uint32_t buf = c.layer_ctr & 1u;
   const uint32_t acc = c.tmem_base + buf * 256u + c.lane_taddr;
   const bool fast = P.fast != 0;
   const int nch = L.n_out >> 6;
-  const bool relu = (L.epi != EPI_LINEAR);
-  const bool write_a = (L.epi == EPI_RELU || L.epi == EPI_LINEAR);
-  const bool head3 = (L.epi == EPI_RGB || L.epi == EPI_WARP);
-  const bool sig_head = (L.flags & LF_SIGMA_HEAD) != 0;
   const float* bias_g = f32 + L.bias_ofs;
   const float* bias_s = (L.ray_slot >= 0) ? rb_base + (static_cast<int>(L.ray_slot) * P.G + g) * kWidth : nullptr;
   const float* wh = f32 + net.head_ofs;     // [3][n_out]
   const float* ws = f32 + net.sigma_ofs;    // [256]
-  float h0 = 0.f, h1 = 0.f, h2 = 0.f, sg = 0.f, amax = 0.f;
+  float h0 = 0.f, h1 = 0.f, h2 = 0.f, sg = 0.f;
 
   mbar_wait(sm.bar(BAR_ACC + buf), (c.acc_phase >> buf) & 1u);
   c.acc_phase ^= 1u << buf;
   tc_fence_after_sync();
 
+#pragma unroll 1
   for (int j = 0; j < nch; ++j) {
+    const int col0 = 64 * j + 16 * c.cg;
+    // issue the TMEM load, then fetch the biases while it is in flight
+    uint32_t v[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(acc + static_cast<uint32_t>(col0))
+        : "memory");
+    float b[16];
+    if (bias_s) ld_f16(bias_s + col0, b);
+    else ldg_f16(bias_g + col0, b);
+    tmem_ld_wait();
+    float x[16];
 #pragma unroll
-    for (int sub = 0; sub < 2; ++sub) {
-      const int col0 = 64 * j + 32 * c.hsel + 16 * sub;
-      // issue the TMEM load, then fetch biases / head weights while it is in flight
-      uint32_t v[16];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(acc + static_cast<uint32_t>(col0))
-          : "memory");
-      float b[16];
-      if (bias_s) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 t = *reinterpret_cast<const float4*>(bias_s + col0 + 4 * i);
-          b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(bias_g + col0) + i);
-          b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
-        }
-      }
-      tmem_ld_wait();
-      float x[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float t = __uint_as_float(v[i]) + b[i];
-        if (relu) t = fmaxf(t, 0.f);
-        x[i] = t;
-      }
-      if (sig_head) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 w = __ldg(reinterpret_cast<const float4*>(ws + col0) + i);
-          sg = fmaf(x[4 * i], w.x, sg); sg = fmaf(x[4 * i + 1], w.y, sg);
-          sg = fmaf(x[4 * i + 2], w.z, sg); sg = fmaf(x[4 * i + 3], w.w, sg);
-        }
-      }
-      if (head3) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wh + col0) + i);
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wh + L.n_out + col0) + i);
-          const float4 w2 = __ldg(reinterpret_cast<const float4*>(wh + 2 * L.n_out + col0) + i);
-          h0 = fmaf(x[4 * i], w0.x, h0); h0 = fmaf(x[4 * i + 1], w0.y, h0); h0 = fmaf(x[4 * i + 2], w0.z, h0); h0 = fmaf(x[4 * i + 3], w0.w, h0);
-          h1 = fmaf(x[4 * i], w1.x, h1); h1 = fmaf(x[4 * i + 1], w1.y, h1); h1 = fmaf(x[4 * i + 2], w1.z, h1); h1 = fmaf(x[4 * i + 3], w1.w, h1);
-          h2 = fmaf(x[4 * i], w2.x, h2); h2 = fmaf(x[4 * i + 1], w2.y, h2); h2 = fmaf(x[4 * i + 2], w2.z, h2); h2 = fmaf(x[4 * i + 3], w2.w, h2);
-        }
-      }
-      if (write_a) {
-        const uint32_t tile = smem_u32(sm.base) + kOffA + static_cast<uint32_t>(j) * 2u * kChunkBytes;
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float t = x[8 * h8 + i];
-            amax = fmaxf(amax, fabsf(t));
-            f[i] = fminf(fmaxf(t, -65000.f), 65000.f);   // keep the fp16 split finite
-          }
-          store_feat8(tile, c.row, 4 * c.hsel + 2 * sub + h8, f, fast);
-        }
-      }
+    for (int i = 0; i < 16; ++i) {
+      const float t = __uint_as_float(v[i]) + b[i];
+      x[i] = kRelu ? fmaxf(t, 0.f) : t;
     }
-    if (write_a) epi_signal(sm, c, j);   // chunk j of the next layer's A operand is ready
+    if (kSigma) {
+      ldg_f16(ws + col0, b);
+      sg = dot16(x, b, sg);
+    }
+    if (kHead3) {
+      ldg_f16(wh + col0, b);             h0 = dot16(x, b, h0);
+      ldg_f16(wh + L.n_out + col0, b);   h1 = dot16(x, b, h1);
+      ldg_f16(wh + 2 * L.n_out + col0, b); h2 = dot16(x, b, h2);
+    }
+    if (kWriteA) {
+      const uint32_t tile = smem_u32(sm.base) + kOffA + static_cast<uint32_t>(j) * 2u * kChunkBytes;
+      store_feat16(tile, c.row, 2 * c.cg, x, fast, c.amax2);
+      epi_signal(sm, c, j);   // this warp's share of chunk j of the next layer's A operand is ready
+    }
   }
-  if (!write_a) tc_fence_before_sync();
-  if (amax > 65000.f) overflow = true;
-  ho.h0 = h0; ho.h1 = h1; ho.h2 = h2; if (sig_head) ho.sig = sg;
+  if (!kWriteA) tc_fence_before_sync();
+  ho.h0 = h0; ho.h1 = h1; ho.h2 = h2; if (kSigma) ho.sig = sg;
   c.layer_ctr++;
+}
+
+__device__ __forceinline__ void epilogue_dispatch(const Smem& sm, const RenderParams& P, const NetPlan& net, const float* f32,
+                                                  const float* rb_base, const Layer& L, EpiCtx& c, int g, HeadOut& ho) {
+  if (L.epi == EPI_RELU) epilogue_layer<true, true, false, false>(sm, P, net, f32, rb_base, L, c, g, ho);
+  else if (L.epi == EPI_LINEAR) {
+    if (L.flags & LF_SIGMA_HEAD) epilogue_layer<false, true, false, true>(sm, P, net, f32, rb_base, L, c, g, ho);
+    else epilogue_layer<false, true, false, false>(sm, P, net, f32, rb_base, L, c, g, ho);
+  } else epilogue_layer<true, false, true, false>(sm, P, net, f32, rb_base, L, c, g, ho);
 }
 
 // ---------------------------------------------------------------------------------- the kernel
@@ -300,8 +328,10 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem sm;
   sm.base = smem_raw;
-  sm.misc = reinterpret_cast<float*>(smem_raw + kOffMisc + 128);   // 128 B reserved for barriers + tmem ptr
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kOffMisc + 8 * BAR_COUNT);
+  sm.misc = reinterpret_cast<float*>(smem_raw + P.off_misc + 128);   // 128 B reserved for barriers + tmem ptr
+  sm.bar0 = smem_u32(smem_raw + P.off_misc);
+  sm.n_stages = static_cast<uint32_t>(P.n_stages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + P.off_misc + 8 * BAR_COUNT);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool fast = P.fast != 0;
   const bool smpl = P.kind == NRF_KIND_SMPL;
@@ -309,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < kNumStages; ++s) { mbar_init(sm.bar(BAR_FULL + s), 1); mbar_init(sm.bar(BAR_EMPTY + s), 1); }
     mbar_init(sm.bar(BAR_ACC + 0), 1); mbar_init(sm.bar(BAR_ACC + 1), 1);
-    for (int j = 0; j < 5; ++j) mbar_init(sm.bar(BAR_AREADY + j), 8);   // one arrival per epilogue warp
+    for (int j = 0; j < 5; ++j) mbar_init(sm.bar(BAR_AREADY + j), kEpiWarps);   // one arrival per epilogue warp
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
@@ -349,9 +379,10 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
   } else {
     // =========================== epilogue warps ===========================
     EpiCtx c;
-    c.warp = warp; c.lane = lane; c.q = warp & 3; c.hsel = (warp - 2) >> 2; c.row = 32 * c.q + lane;
+    c.warp = warp; c.lane = lane; c.q = warp & 3; c.cg = (warp - 2) >> 2; c.row = 32 * c.q + lane;
     c.tid = threadIdx.x - 64; c.tmem_base = tmem_base; c.lane_taddr = static_cast<uint32_t>(32 * c.q) << 16;
-    const int ew = warp - 2;   // 0..7
+    c.amax2 = __floats2half2_rn(0.f, 0.f);
+    const int ew = warp - 2;   // 0..15
     float* ray = sm.misc + P.o_ray;          // [G][kRayFloats]
     float* rb = sm.misc + P.o_rb;            // [slots][G][256]
     float* rbw = sm.misc + P.o_rbw;          // warp net: [G][256]
@@ -359,10 +390,11 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
     float* zc = sm.misc + P.o_zc;            // [G][n_coarse]
     float* zf = sm.misc + P.o_zf;            // [G][n_all]
     float* dnorm = sm.misc + P.o_dnorm;      // [G * n_coarse] (smpl coarse pass)
-    float* scratch = sm.misc + P.o_scratch;  // tile phase: head partials [128][4]; ray phase: cdf + zs
+    float* scratch = sm.misc + P.o_scratch;  // ray phase: cdf + zs
+    // head-partial exchange: 8 float4 slots per row inside A chunk 3 (dead whenever it is used)
+    float4* xchg = reinterpret_cast<float4*>(sm.base + kOffXchg) + 8 * c.row;
     const uint32_t aux_tile = smem_u32(sm.base) + kOffAux;
     const int G = P.G, nc = P.n_coarse, nf = P.n_fine, na = P.n_all;
-    bool overflow = false;
 
     for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
       const int64_t ray0 = static_cast<int64_t>(grp) * G;
@@ -400,8 +432,9 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
           else {
             const int j = i - (ident ? ncomp : 0);
             const int k = j / (2 * ncomp), rem = j - k * 2 * ncomp;
-            const float a = v[rem % ncomp] * static_cast<float>(1u << k);
-            val = rem < ncomp ? sinf(a) : cosf(a);
+            float sv, cv;
+            sincos_pe(v[rem % ncomp] * __int_as_float((127 + k) << 23), sv, cv);
+            val = rem < ncomp ? sv : cv;
           }
           r[8 + (is_dir ? kMaxRayFeat : 0) + i] = val;
         }
@@ -459,31 +492,31 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
             } else {
               const float zz = zf[g * na + s];
               x = __fadd_rn(r[0], __fmul_rn(r[3], zz)); y = __fadd_rn(r[1], __fmul_rn(r[4], zz)); z = __fadd_rn(r[2], __fmul_rn(r[5], zz));
-              if (c.hsel == 0 && P.io.samples_out) { float* po = P.io.samples_out + (ri * na + s) * 3; po[0] = x; po[1] = y; po[2] = z; }
+              if (c.cg == 0 && P.io.samples_out) { float* po = P.io.samples_out + (ri * na + s) * 3; po[0] = x; po[1] = y; po[2] = z; }
             }
           }
           float ux = 0.f, uy = 0.f, uz = 1.f;   // unit view direction of this sample (smpl)
           HeadOut ho = {0.f, 0.f, 0.f, 0.f};
           if (smpl) {
             // ---- warp field: x -> x + W2 relu(W1 [enc(x), pose] + b1) + b2
-            write_encoding(aux_tile, c.row, c.hsel, x, y, z, P.warp.in_freqs, P.warp.in_identity, fast);
+            write_encoding(aux_tile, c.row, c.cg, x, y, z, P.warp.in_freqs, P.warp.in_identity, fast);
             epi_signal(sm, c, kSrcAux);
-            epilogue_layer(sm, P, P.warp, reinterpret_cast<const float*>(P.blob[2] + P.warp.f32_ofs), rbw, P.warp.layers[0], c, g, ho, overflow);
-            // both threads of a row need the full 256-column dot products: exchange the two
-            // column-half partials through smem and add them in the same order -> identical bits
-            float4* part = reinterpret_cast<float4*>(scratch);   // [2][128]
-            part[c.hsel * kTileRows + c.row] = make_float4(ho.h0, ho.h1, ho.h2, 0.f);
+            const float* wf32 = reinterpret_cast<const float*>(P.blob[2] + P.warp.f32_ofs);
+            epilogue_layer<true, false, true, false>(sm, P, P.warp, wf32, rbw, P.warp.layers[0], c, g, ho);
+            // all four threads of a row need the full 256-column dot products: exchange the column-group
+            // partials through smem and add them in the same order -> identical bits in every thread
+            xchg[c.cg] = make_float4(ho.h0, ho.h1, ho.h2, 0.f);
             named_bar_sync(1, kEpiThreads);
             float w0, w1, w2;
             {
-              const float* b2 = reinterpret_cast<const float*>(P.blob[2] + P.warp.f32_ofs) + P.warp.head_ofs + 3 * kWidth;
-              const float4 p0 = part[c.row], p1 = part[kTileRows + c.row];
-              w0 = __fadd_rn(__fadd_rn(p0.x, p1.x), __ldg(b2 + 0));
-              w1 = __fadd_rn(__fadd_rn(p0.y, p1.y), __ldg(b2 + 1));
-              w2 = __fadd_rn(__fadd_rn(p0.z, p1.z), __ldg(b2 + 2));
+              const float* b2 = wf32 + P.warp.head_ofs + 3 * kWidth;
+              const float4 p0 = xchg[0], p1 = xchg[1], p2 = xchg[2], p3 = xchg[3];
+              w0 = __fadd_rn(__fadd_rn(__fadd_rn(p0.x, p1.x), __fadd_rn(p2.x, p3.x)), __ldg(b2 + 0));
+              w1 = __fadd_rn(__fadd_rn(__fadd_rn(p0.y, p1.y), __fadd_rn(p2.y, p3.y)), __ldg(b2 + 1));
+              w2 = __fadd_rn(__fadd_rn(__fadd_rn(p0.z, p1.z), __fadd_rn(p2.z, p3.z)), __ldg(b2 + 2));
             }
             const float wx = __fadd_rn(x, w0), wy = __fadd_rn(y, w1), wz = __fadd_rn(z, w2);
-            if (valid && last_pass && c.hsel == 0) {
+            if (valid && last_pass && c.cg == 1) {
               if (P.io.warp_out) { float* po = P.io.warp_out + (ri * n + s) * 3; po[0] = w0; po[1] = w1; po[2] = w2; }
               if (P.io.warped_out) { float* po = P.io.warped_out + (ri * n + s) * 3; po[0] = wx; po[1] = wy; po[2] = wz; }
             }
@@ -491,11 +524,12 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
             const float dx = __fsub_rn(x, r[0]), dy = __fsub_rn(y, r[1]), dz = __fsub_rn(z, r[2]);
             const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
             if (in_rows) { ux = __fdiv_rn(dx, nrm); uy = __fdiv_rn(dy, nrm); uz = __fdiv_rn(dz, nrm); }
-            if (pass == 0 && c.hsel == 0 && in_rows) dnorm[R] = nrm;
-            named_bar_sync(1, kEpiThreads);   // everyone is done with the exchange buffer
+            if (pass == 0 && c.cg == 2 && in_rows) dnorm[R] = nrm;
+            // (no barrier needed before the exchange slots are reused: every later writer of A chunk 3
+            //  sits behind an mbarrier that all 16 warps arrive on only after these reads)
           }
           // ---- encoded position -> aux (first layer and skip layer read it)
-          write_encoding(aux_tile, c.row, c.hsel, x, y, z, net.in_freqs, net.in_identity, fast);
+          write_encoding(aux_tile, c.row, c.cg, x, y, z, net.in_freqs, net.in_identity, fast);
           epi_signal(sm, c, kSrcAux);
 
           ho = {0.f, 0.f, 0.f, 0.f};
@@ -503,35 +537,35 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
           for (int l = 0; l < net.n_layers; ++l) {
             const Layer& L = net.layers[l];
             HeadOut hl = {0.f, 0.f, 0.f, 0.f};
-            epilogue_layer(sm, P, net, f32, rb, L, c, g, hl, overflow);
+            epilogue_dispatch(sm, P, net, f32, rb, L, c, g, hl);
             if (L.flags & LF_SIGMA_HEAD) sigma_part = hl.sig;
             if (L.epi == EPI_RGB) ho = hl;
             if (L.flags & LF_WRITE_DIRPE) {
               // the skip layer's MMAs are long done: aux can now take the per-sample direction encoding
-              write_encoding(aux_tile, c.row, c.hsel, ux, uy, uz, net.dir_freqs, net.dir_identity, fast);
+              write_encoding(aux_tile, c.row, c.cg, ux, uy, uz, net.dir_freqs, net.dir_identity, fast);
               epi_signal(sm, c, kSrcAux);
             }
           }
-          // ---- combine the two column-halves of the heads: raw = (rgb_raw, sigma_raw)
-          float4* part = reinterpret_cast<float4*>(scratch);
-          if (c.hsel == 1) part[c.row] = make_float4(ho.h0, ho.h1, ho.h2, sigma_part);
+          // ---- combine the four column-group partials of the heads: raw = (rgb_raw, sigma_raw)
+          if (c.cg != 0) xchg[c.cg] = make_float4(ho.h0, ho.h1, ho.h2, sigma_part);
           named_bar_sync(1, kEpiThreads);
-          if (c.hsel == 0) {
-            const float4 p1 = part[c.row];
+          if (c.cg == 0) {
+            const float4 p1 = xchg[1], p2 = xchg[2], p3 = xchg[3];
             const float* hb = f32 + net.head_ofs + 3 * (kWidth / 2);
             float4 o4;
-            o4.x = __fadd_rn(__fadd_rn(ho.h0, p1.x), __ldg(hb + 0));
-            o4.y = __fadd_rn(__fadd_rn(ho.h1, p1.y), __ldg(hb + 1));
-            o4.z = __fadd_rn(__fadd_rn(ho.h2, p1.z), __ldg(hb + 2));
-            o4.w = __fadd_rn(__fadd_rn(sigma_part, p1.w), __ldg(f32 + net.sigma_ofs + kWidth));
+            o4.x = __fadd_rn(__fadd_rn(__fadd_rn(ho.h0, p1.x), __fadd_rn(p2.x, p3.x)), __ldg(hb + 0));
+            o4.y = __fadd_rn(__fadd_rn(__fadd_rn(ho.h1, p1.y), __fadd_rn(p2.y, p3.y)), __ldg(hb + 1));
+            o4.z = __fadd_rn(__fadd_rn(__fadd_rn(ho.h2, p1.z), __fadd_rn(p2.z, p3.z)), __ldg(hb + 2));
+            o4.w = __fadd_rn(__fadd_rn(__fadd_rn(sigma_part, p1.w), __fadd_rn(p2.w, p3.w)), __ldg(f32 + net.sigma_ofs + kWidth));
             if (in_rows) raw4[R] = o4;
             if (valid) {
               float* tap = pass == 0 ? P.io.raw_coarse : P.io.raw_fine;
               if (tap) *reinterpret_cast<float4*>(tap + (ri * n + s) * 4) = o4;
             }
           }
-          named_bar_sync(1, kEpiThreads);
+          // the exchange slots are next written behind an mbarrier every warp arrives on after this point
         }
+        named_bar_sync(1, kEpiThreads);   // raw4 of every tile of this pass is complete
 
         // ---- per-ray: compositing (+ sampling after the coarse pass); one warp per ray
         if (ew < G) {
@@ -564,7 +598,8 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
         named_bar_sync(1, kEpiThreads);
       }
     }
-    if (overflow && P.io.status) atomicOr(P.io.status, 1);
+    const uint32_t am = *reinterpret_cast<const uint32_t*>(&c.amax2);
+    if (((am & 0xFFFFu) >= 0x7BFFu || (am >> 16) >= 0x7BFFu) && P.io.status) atomicOr(P.io.status, 1);
   }
 
   tc_fence_before_sync();
@@ -657,10 +692,11 @@ extern "C" int nrf_render(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coar
   P.o_zc = take(G * nc);
   P.o_zf = take(G * na);
   P.o_dnorm = take(smpl ? G * nc : 0);
-  uint32_t scr = 2 * kTileRows * 4;
-  if (static_cast<uint32_t>(G * (nc + nf)) > scr) scr = G * (nc + nf);
-  P.o_scratch = take(scr);
-  const uint32_t smem_bytes = kOffMisc + 128 + f * 4;
+  P.o_scratch = take(G * (nc + nf) > 16 ? G * (nc + nf) : 16);
+  P.n_stages = kNumStages;
+  if (kOffRing + kNumStages * kStageBytes + 128 + f * 4 > kSmemLimit) P.n_stages = 2;   // big per-ray tables: shorter weight ring
+  P.off_misc = kOffRing + static_cast<uint32_t>(P.n_stages) * kStageBytes;
+  const uint32_t smem_bytes = P.off_misc + 128 + f * 4;
   if (smem_bytes > kSmemLimit) { set_error("configuration needs %u bytes of shared memory per CTA (limit %u)", smem_bytes, kSmemLimit); return NRF_E_INVALID; }
 
   int dev = 0, sms = 0;

@@ -143,46 +143,53 @@ __global__ void searchsorted_kernel(const float* __restrict__ a, int64_t rows_a,
 }
 
 // ------------------------------------------------------------------------------ tcgen05 self-test
-// D[128,128] = A[128,64] x B[128,64]^T, fp16 operands written to smem with the renderer's swizzle
-// helper, one K=64 chain of four tcgen05.mma, accumulator read back with tcgen05.ld.
+// D[128,256] = A[128,64] x B[256,64]^T through exactly the operand layouts the renderer uses: A as one
+// [128 x 64] SWIZZLE_128B tile, B as two [256 x 32] SWIZZLE_64B weight stages; four K=16 tcgen05.mma
+// with N = 256, accumulator read back with tcgen05.ld.
 __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                                 float* __restrict__ d) {
   extern __shared__ __align__(1024) uint8_t smem_st[];
   uint8_t* sa = smem_st;             // 16 KB
-  uint8_t* sb = smem_st + 16384;     // 16 KB
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_st + 32768);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_st + 32768 + 8);
+  uint8_t* sb = smem_st + 16384;     // 2 x 16 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_st + 49152);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_st + 49152 + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int idx = threadIdx.x; idx < 128 * 64; idx += 128) {
     const int r = idx >> 6, k = idx & 63;
     *reinterpret_cast<__half*>(sa + sw128_offset(r, k)) = __float2half_rn(a[idx]);
-    *reinterpret_cast<__half*>(sb + sw128_offset(r, k)) = __float2half_rn(b[idx]);
+  }
+  for (int idx = threadIdx.x; idx < 256 * 64; idx += 128) {
+    const int r = idx >> 6, k = idx & 63;
+    *reinterpret_cast<__half*>(sb + (k >> 5) * 16384 + sw64_offset(r, k & 31)) = __float2half_rn(b[idx]);
   }
   if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc<128>(smem_u32(tmem_slot));
+  if (warp == 0) tmem_alloc<256>(smem_u32(tmem_slot));
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = umma_idesc_f16(128, 128);
-    const uint64_t ad = umma_desc_sw128(smem_u32(sa)), bd = umma_desc_sw128(smem_u32(sb));
-    for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem, ad + 2u * ks, bd + 2u * ks, idesc, ks ? 1u : 0u);
+    const uint32_t idesc = umma_idesc_f16(128, 256);
+    const uint64_t ad = umma_desc_sw128(smem_u32(sa));
+    for (uint32_t kh = 0; kh < 2; ++kh) {
+      const uint64_t bd = umma_desc_sw64(smem_u32(sb) + kh * 16384u);
+      for (uint32_t ks = 0; ks < 2; ++ks) umma_f16_ss(tmem, ad + 4u * kh + 2u * ks, bd + 2u * ks, idesc, (kh | ks) ? 1u : 0u);
+    }
     umma_commit(smem_u32(bar));
   }
   mbar_wait(smem_u32(bar), 0);
   tc_fence_after_sync();
   const int row = 32 * (warp & 3) + lane;
-  for (int c0 = 0; c0 < 128; c0 += 32) {
+  for (int c0 = 0; c0 < 256; c0 += 32) {
     uint32_t v[32];
     tmem_ld32(tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + c0, v);
     tmem_ld_wait();
-    for (int i = 0; i < 32; ++i) d[row * 128 + c0 + i] = __uint_as_float(v[i]);
+    for (int i = 0; i < 32; ++i) d[row * 256 + c0 + i] = __uint_as_float(v[i]);
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<128>(tmem);
+  if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
 static int grid_for(int64_t total, int block) {
@@ -264,7 +271,7 @@ extern "C" int nrf_searchsorted(const float* a, int64_t rows_a, int64_t na, cons
 
 extern "C" int nrf_selftest_umma(const float* a, const float* b, float* d, void* stream) {
   if (!a || !b || !d) { set_error("selftest: NULL argument"); return NRF_E_INVALID; }
-  const int smem = 32768 + 64;
+  const int smem = 49152 + 64;
   cudaError_t e = cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
   selftest_umma_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(a, b, d);

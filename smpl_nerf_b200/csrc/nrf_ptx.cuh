@@ -105,6 +105,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// K-major operand tile, 64-byte swizzle: rows of 32 fp16 (64 B), 8-row groups 512 B apart; used for the
+// weight stages ([n_out x 32] tiles) so that one 16 KB ring slot holds a full N = 256 B operand.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: fp16 A/B (both K-major), fp32 accumulate, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
   return (1u << 4)            // D format: f32
@@ -135,6 +146,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // 1024-byte aligned: 16-byte chunk index (k/8) is XORed with (row % 8).
 __host__ __device__ constexpr uint32_t sw128_offset(uint32_t row, uint32_t k) {
   return row * 128u + ((((k >> 3) ^ (row & 7u)) & 7u) << 4) + ((k & 7u) << 1);
+}
+
+// Same for a [rows x 32] fp16 K-major SWIZZLE_64B tile (base 512-byte aligned): 16-byte chunk index
+// (k/8, 0..3) is XORed with address bits [7,9) = (row / 2) % 4.
+__host__ __device__ constexpr uint32_t sw64_offset(uint32_t row, uint32_t k) {
+  return row * 64u + ((((k >> 3) ^ ((row >> 1) & 3u)) & 3u) << 4) + ((k & 7u) << 1);
 }
 
 // fp32 -> (hi, lo) fp16 split: x ~= hi + lo with ~22 significant bits.  Inputs are clamped to the

@@ -45,18 +45,22 @@ def test_sample_pdf():
     want = O.inverse_cdf(bins, w, 128)
     got = ops.sample_pdf(bins.to(DEV), w.to(DEV), O.make_args()).cpu()
     err = (got - want).abs()
-    # utils.py:224 switches denom to 1 when cdf[above]-cdf[below] < 1e-5: a step function of the
-    # CDF, so an ulp of difference in the pdf normalisation flips it (the reference's own fp32 vs
-    # fp64 runs disagree there).  Compare strictly where the fp64 denom is clear of the switch.
+    # The reference's sampler is a step function of the CDF in two places: utils.py:224 switches denom
+    # to 1 when cdf[above]-cdf[below] < 1e-5, and searchsorted flips its index when u hits a CDF entry
+    # (u = 1 vs cdf[-1] ~ 1 is the usual case) -- an ulp of difference in the pdf normalisation moves
+    # the result by up to a bin there (the reference's own fp32 vs fp64 runs disagree).  Compare
+    # strictly where the fp64 CDF is clear of both switches, and bound the rest by the bin width.
     wd = w.double() + 1e-5
     cdf = torch.cat([torch.zeros(B, 1, dtype=torch.float64), torch.cumsum(wd / wd.sum(-1, keepdim=True), -1)], -1)
     u = torch.linspace(0., 1., 128, dtype=torch.float32).double().expand(B, 128).contiguous()
     idx = torch.searchsorted(cdf, u, right=True)
     denom = torch.gather(cdf, -1, idx.clamp(max=62)) - torch.gather(cdf, -1, (idx - 1).clamp(min=0))
-    clear = (denom - 1e-5).abs() > 1e-6
-    assert float(clear.float().mean()) > 0.97
+    near_entry = (u[:, :, None] - cdf[:, None, :]).abs().min(-1)[0] < 1e-6
+    clear = ((denom - 1e-5).abs() > 1e-6) & ~near_entry
+    assert float(clear.float().mean()) > 0.95
     assert float(err[clear].max()) <= 1e-3     # (u - c0) / denom amplifies an ulp of c0 by up to 1/1.1e-5
-    assert float(torch.quantile(err, 0.99)) <= 1e-5 and float(err.max()) <= float((bins[:, 1:] - bins[:, :-1]).max()) + 1e-5
+    assert float(torch.quantile(err, 0.99)) <= 1e-5
+    assert float(err.max()) <= float((bins[:, 1:] - bins[:, :-1]).max()) + 1e-5
 
 
 @pytest.mark.parametrize('Ba,Bv', [(1, 1), (100, 100), (1, 100), (100, 1)])

@@ -38,8 +38,8 @@ def test_selftest_umma():
     L = _lib.lib()
     _lib.check(L.nrf_device_supported(0))
     torch.manual_seed(0)
-    a, b = torch.randn(128, 64, device=DEV), torch.randn(128, 64, device=DEV)
-    d = torch.zeros(128, 128, device=DEV)
+    a, b = torch.randn(128, 64, device=DEV), torch.randn(256, 64, device=DEV)
+    d = torch.zeros(128, 256, device=DEV)
     _lib.check(L.nrf_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = a.half().double() @ b.half().double().t()

@@ -20,8 +20,8 @@ def selftest():
     L = _lib.lib()
     torch.manual_seed(0)
     a = torch.randn(128, 64, device='cuda')
-    b = torch.randn(128, 64, device='cuda')
-    d = torch.zeros(128, 128, device='cuda')
+    b = torch.randn(256, 64, device='cuda')
+    d = torch.zeros(128, 256, device='cuda')
     _lib.check(L.nrf_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = a.half().float() @ b.half().float().t()
