@@ -112,6 +112,8 @@ typedef struct NrfRenderIO {
   float* z_new;          /* [B,n_fine] inverse-CDF samples before the merge                  */
   float* z_all;          /* [B,n] merged depths                                              */
   int32_t* status;       /* optional [1]: bit0 set if an activation left the fp16 range      */
+  long long* trace;      /* optional [1 + 3*cap], trace[0] = cap on entry: CTA 0 appends (event, layer
+                            counter, SM clock) triples of its MMA issuer / epilogue timeline (developer tap) */
 } NrfRenderIO;
 
 const char* nrf_last_error(void);
@@ -159,15 +161,23 @@ int nrf_fine_sampling(const float* origin, const float* dir, const float* z, con
 int nrf_searchsorted(const float* a, int64_t rows_a, int64_t na, const float* v, int64_t rows_v, int64_t nv,
                      int64_t* res, int32_t side_left, void* stream);
 
-/* tcgen05 self-test: D[128,256] = A[128,64] * B[256,64]^T with fp16 operands staged through the same
- * swizzled shared-memory layouts / descriptors the renderer uses (A: SWIZZLE_128B tile, B: two
- * [256 x 32] SWIZZLE_64B weight stages, N = 256 per instruction).  a, b: fp32 (rounded to fp16 inside). */
+/* tcgen05 self-test: D[128,256] = A[128,64] * B[256,64]^T with fp16 operands staged through the swizzled
+ * shared-memory layout / descriptors the renderer uses (SWIZZLE_128B K-major tiles, N = 256 per
+ * instruction).  a, b: fp32 (rounded to fp16 inside). */
 int nrf_selftest_umma(const float* a, const float* b, float* d, void* stream);
+/* The same through a CTA pair (tcgen05.mma.cta_group::2, M = 256): D[256,256] = A[256,64] * B[256,64]^T,
+ * each CTA staging its 128 rows of A and its half of B, as the renderer does. */
+int nrf_selftest_umma2(const float* a, const float* b, float* d, void* stream);
 
 /* Developer diagnostic: tcgen05.mma issue-rate probe on n_ctas SMs (one CTA each).  mode bit0: N=256 per
  * instruction (else 128); bit1: stream `wsrc` (device, >= 64 KiB) through a TMA ring concurrently;
  * bit2: two A passes per B stage.  cycles[n_ctas] receives the SM-clock cycles of `iters` K=64 steps. */
 int nrf_bench_umma(int mode, int iters, const void* wsrc, size_t wsrc_bytes, long long* cycles, int n_ctas, void* stream);
+/* CTA-pair variant (cta_group::2, M=256, N=256, 16 KB half-stages per CTA through an n_slots-deep (<= 4) ring
+ * with the renderer's relay protocol).  mode bit1: TMA stream on; bit2: two A passes per stage; bit4: relay
+ * with a release.cluster arrive.  cycles[n_pairs]. */
+int nrf_bench_umma2(int mode, int iters, int n_slots, const void* wsrc, size_t wsrc_bytes, long long* cycles, int n_pairs,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -47,7 +47,7 @@ class PipelineDesc(C.Structure):
 _IO_IN = ['ray_samples', 'ray_origin', 'ray_dir', 'z_vals', 'goal_pose', 'u_fine', 'noise_coarse', 'noise_fine',
           'z_all_in']
 _IO_OUT = ['rgb', 'rgb_fine', 'samples_out', 'alpha_out', 'warp_out', 'warped_out', 'raw_coarse', 'raw_fine',
-           'weights_coarse', 'z_new', 'z_all', 'status']
+           'weights_coarse', 'z_new', 'z_all', 'status', 'trace']
 
 
 class RenderIO(C.Structure):
@@ -57,7 +57,7 @@ class RenderIO(C.Structure):
 EXPORTS = ['nrf_last_error', 'nrf_abi_version', 'nrf_device_supported', 'nrf_raynet_packed_bytes',
            'nrf_warpnet_packed_bytes', 'nrf_pack_raynet', 'nrf_pack_warpnet', 'nrf_render', 'nrf_render_launches',
            'nrf_positional_encoding', 'nrf_raw2outputs', 'nrf_sample_pdf', 'nrf_fine_sampling', 'nrf_searchsorted',
-           'nrf_selftest_umma', 'nrf_bench_umma']
+           'nrf_selftest_umma', 'nrf_selftest_umma2', 'nrf_bench_umma', 'nrf_bench_umma2']
 
 
 def _stale() -> bool:
@@ -118,6 +118,8 @@ def lib() -> C.CDLL:
     L.nrf_searchsorted.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                    C.c_int32, C.c_void_p]
     L.nrf_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nrf_bench_umma2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
+    L.nrf_selftest_umma2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nrf_bench_umma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     if L.nrf_abi_version() != 1:
         raise RuntimeError('libnrf_b200.so ABI version mismatch; rebuild')

@@ -10,15 +10,22 @@
 // Work item = a group of G rays (G * n_coarse <= 128) owned by one CTA from the coarse pass to the
 // final colour, so no [rays x samples x features] tensor ever exists in HBM.
 //
-// CTA = 10 warps, warp-specialised:
-//   warp 0      weight producer: streams pre-swizzled fp16 hi/lo weight stages L2 -> SMEM ring with
-//               1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx)
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, fp16 x fp16 -> fp32 in TMEM);
-//               fp32-level accuracy comes from the split  x*w ~= xh*wh + xl*wh + xh*wl  (3 passes)
-//   warps 2..9  "epilogue" warps (thread = one sample row x half of the columns): positional
-//               encoding -> SMEM operand tiles, TMEM -> bias/ReLU/hi-lo split -> next layer's A
-//               operand (in place), sigma / rgb / warp heads as fp32 dot products, then per ray:
-//               alpha compositing, inverse-CDF sampling, sorted merge.
+// CTAs run as PAIRS (cluster of 2 on one TPC, tcgen05 cta_group::2): every MMA is M = 256 -- 128 sample
+// rows of each CTA's own tile -- and each CTA stages only its half of the weight (B) operand, so the
+// L2 -> SMEM weight stream per SM is halved (a 48 KB ring of single-CTA stages could only keep
+// ~27 B/clk/SM in flight against the ~43 B/clk/SM the 3-pass MMA consumes; profiles/r1).
+//
+// CTA = 18 warps, warp-specialised:
+//   warp 0      weight producer: streams this CTA's half of the pre-swizzled fp16 hi/lo weight stages
+//               L2 -> SMEM ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx)
+//   warp 1      even CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 (M=256, N=n_out,
+//               fp16 x fp16 -> fp32 in both CTAs' TMEM); fp32-level accuracy comes from the split
+//               x*w ~= xh*wh + xl*wh + xh*wl (3 passes).  odd CTA: relay -- forwards "my half of the
+//               stage has landed" to the issuer's full barrier
+//   warps 2..17 "epilogue" warps (thread = one sample row x 16 columns of every 64-feature chunk):
+//               positional encoding -> SMEM operand tiles, TMEM -> bias/ReLU/hi-lo split -> next
+//               layer's A operand (in place), sigma / rgb / warp heads as fp32 dot products, then per
+//               ray: alpha compositing, inverse-CDF sampling, sorted merge.
 // Two 256-column TMEM accumulators ping-pong between consecutive layers, and activations are handed
 // to the MMA issuer per 64-feature K-chunk, so layer l+1's MMAs start while layer l's epilogue is
 // still draining.
@@ -31,8 +38,8 @@
 
 namespace nrf {
 
-constexpr int kNumStages = 3;                     // weight ring slots (2 when the per-ray tables need the room)
-constexpr uint32_t kStageBytes = 16384;            // 128 rows x 128 B
+constexpr int kMaxStages = 3;                      // weight ring slots (2 when the per-ray tables need the room)
+constexpr uint32_t kSlotBytes = 16384;             // this CTA's half of a [256 x 64] fp16 stage: 128 rows x 128 B
 constexpr uint32_t kChunkBytes = 16384;            // one [128 x 64] fp16 operand tile
 constexpr uint32_t kOffA = 0;                      // 4 chunks x (hi, lo)
 constexpr uint32_t kOffAux = 4 * 2 * kChunkBytes;  // 131072
@@ -46,8 +53,10 @@ constexpr int kRayVec = 8 + kMaxRayFeat + 32;      // unit direction[3], raw pos
 constexpr int kRayFloats = kRayVec + 8;            // o[3] d[3] |d| valid | pose feats[64] | dir feats[32] | unit d, pose
 
 // barrier slots inside the misc area (8 bytes each)
-enum { BAR_FULL = 0, BAR_EMPTY = kNumStages, BAR_ACC = 2 * kNumStages, BAR_AREADY = 2 * kNumStages + 2,
-       BAR_COUNT = 2 * kNumStages + 2 + 5 };
+enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC = 2 * kMaxStages, BAR_AREADY = 2 * kMaxStages + 2,
+       BAR_COUNT = 2 * kMaxStages + 2 + 5 };
+constexpr uint32_t kBarBytes = 256;                // barriers + TMEM base slot
+static_assert(8 * BAR_COUNT + 8 <= kBarBytes, "barrier area too small");
 
 struct RenderParams {
   NetPlan net[2];
@@ -57,7 +66,7 @@ struct RenderParams {
   int64_t n_rays;
   int32_t kind, n_coarse, n_fine, n_all, run_fine, white_bkgd, fast;
   int32_t pose_freqs, pose_identity, pose_encoded, pose_stride, pose_col0, pose_col1, pose_dim;
-  int32_t G, tiles_f, n_groups, n_stages;
+  int32_t G, tiles_f, n_groups, n_pairs, n_stages;
   uint32_t off_misc;   // byte offset of the barrier + per-ray area (behind the weight ring)
   // float offsets inside the misc area (after the barriers)
   uint32_t o_ray, o_rb, o_rbw, o_raw, o_zc, o_zf, o_dnorm, o_scratch;
@@ -68,6 +77,7 @@ struct Smem {
   float* misc;
   uint32_t bar0;
   uint32_t n_stages;
+  uint32_t rank;       // rank of this CTA in its pair (0 = issuer)
   __device__ uint32_t bar(int i) const { return bar0 + 8u * i; }
 };
 
@@ -152,62 +162,101 @@ __device__ __forceinline__ void write_encoding(uint32_t aux_tile, int row, int c
   store_feat16(aux_tile, row, 2 * cg, f, fast, dummy);
 }
 
+// Developer tap: CTA 0 appends (event, counter, SM clock) to io.trace ([0] = capacity, [1] = count).
+__device__ __forceinline__ void trace_ev(const RenderParams& P, int ev, uint32_t ctr) {
+  if (P.io.trace && blockIdx.x == 0) {
+    const long long t = clock64();
+    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(P.io.trace) + 1, 1ull);
+    if (static_cast<long long>(i) < P.io.trace[0]) { long long* e = P.io.trace + 2 + 3 * i; e[0] = ev; e[1] = ctr; e[2] = t; }
+  }
+}
+
 // ---------------------------------------------------------------------------------- roles
 struct RingState { uint32_t stage = 0, phase = 0; __device__ void advance(uint32_t n) { if (++stage == n) { stage = 0; phase ^= 1; } } };
 
 __device__ __forceinline__ void producer_layer(const Smem& sm, const uint8_t* blob, const Layer& L, RingState& rs, bool fast) {
-  const uint32_t stage_bytes = L.n_out * 64u;      // one [n_out x 32] fp16 tile
-  const uint8_t* src = blob + L.stream_ofs;
+  const uint32_t half_bytes = L.n_out * 64u;       // this CTA's [n_out/2 x 64] fp16 half of a stage
+  const uint8_t* src = blob + L.stream_ofs + sm.rank * half_bytes;
   for (int kc = 0; kc < L.nk; ++kc) {
-    for (int part = 0; part < 4; ++part, src += stage_bytes) {
-      if (fast && (part & 1)) continue;            // lo stages are not streamed in fast mode
+    for (int is_lo = 0; is_lo < 2; ++is_lo, src += 2u * half_bytes) {
+      if (fast && is_lo) continue;                 // lo stages are not streamed in fast mode
       mbar_wait(sm.bar(BAR_EMPTY + rs.stage), rs.phase ^ 1);
-      mbar_arrive_expect_tx(sm.bar(BAR_FULL + rs.stage), stage_bytes);
-      bulk_g2s(smem_u32(sm.base + kOffRing) + rs.stage * kStageBytes, src, stage_bytes, sm.bar(BAR_FULL + rs.stage));
+      mbar_arrive_expect_tx(sm.bar(BAR_FULL + rs.stage), half_bytes);
+      bulk_g2s(smem_u32(sm.base + kOffRing) + rs.stage * kSlotBytes, src, half_bytes, sm.bar(BAR_FULL + rs.stage));
       rs.advance(sm.n_stages);
     }
   }
 }
 
+// Odd CTA: once this CTA's half of a stage has landed, arrive on the issuer's full barrier (which
+// also counts the issuer's own producer + its bytes), so the issuer waits on ONE barrier per stage.
+// (A cp.async.bulk naming the peer's mbarrier directly hangs; a release.cluster arrive costs ~1000
+// cycles per stage -- both measured with nrf_bench_umma2.)
+__device__ __forceinline__ void relay_layer(const Smem& sm, const Layer& L, RingState& rs, bool fast) {
+  for (int kc = 0; kc < L.nk; ++kc)
+    for (int is_lo = 0; is_lo < 2; ++is_lo) {
+      if (fast && is_lo) continue;
+      mbar_wait(sm.bar(BAR_FULL + rs.stage), rs.phase);
+      mbar_arrive_cluster_relaxed_warp(sm.bar(BAR_FULL + rs.stage), 0);
+      rs.advance(sm.n_stages);
+    }
+}
+
 struct MmaState { RingState rs; uint32_t a_phase = 0; uint32_t layer_ctr = 0; };
 
-// One layer: for every 64-feature K-chunk, four weight stages (hi/lo x two 32-feature halves); the hi
-// stage multiplies both the hi and the lo activations, the lo stage only the hi activations:
-//   x*w ~= xh*wh + xl*wh + xh*wl.     Every instruction is M=128 x N=n_out x K=16.
-__device__ __forceinline__ void mma_layer(const Smem& sm, uint32_t tmem_base, const Layer& L, MmaState& st, bool fast) {
+// One layer: for every 64-feature K-chunk, a hi and a lo weight stage; the hi stage multiplies both the
+// hi and the lo activations, the lo stage only the hi activations:  x*w ~= xh*wh + xl*wh + xh*wl.
+// Every instruction is M=256 (pair) x N=n_out x K=16; 8 + 4 of them per chunk, one commit per stage.
+// Executed by all 32 lanes of warp 1 (warp-uniform); an elected lane issues.
+__device__ __forceinline__ void mma_layer(const Smem& sm, const RenderParams& P, uint32_t tmem_base, const Layer& L, MmaState& st, bool fast) {
   const uint32_t acc = tmem_base + (st.layer_ctr & 1u) * 256u;
-  const uint32_t idesc = umma_idesc_f16(128, L.n_out);
+  const uint32_t idesc = umma_idesc_f16(256, L.n_out);
   const uint32_t a_base = smem_u32(sm.base);
+  const bool tracing = P.io.trace != nullptr && blockIdx.x == 0;
+  long long w_ops = 0, w_full = 0, t_in = 0;
+  if (tracing) t_in = clock64();
   uint32_t accumulate = 0;
   for (int kc = 0; kc < L.nk; ++kc) {
     const int src = L.ksrc[kc];
     if (src != kSrcAux || (L.flags & LF_AUX_WAIT)) {
+      const long long t0 = tracing ? clock64() : 0;
       mbar_wait(sm.bar(BAR_AREADY + src), (st.a_phase >> src) & 1u);
+      if (tracing) w_ops += clock64() - t0;
       st.a_phase ^= 1u << src;
       tc_fence_after_sync();
     }
     const uint32_t a_hi = a_base + (src == kSrcAux ? kOffAux : kOffA + static_cast<uint32_t>(src) * 2u * kChunkBytes);
     const uint32_t a_lo = a_hi + kChunkBytes;
-    for (int part = 0; part < 4; ++part) {
-      if (fast && (part & 1)) continue;
-      const uint32_t kh = part >> 1, is_lo = part & 1;
+    for (int is_lo = 0; is_lo < 2; ++is_lo) {
+      if (fast && is_lo) continue;
+      const long long t0 = tracing ? clock64() : 0;
       mbar_wait(sm.bar(BAR_FULL + st.rs.stage), st.rs.phase);
+      if (tracing) w_full += clock64() - t0;
       tc_fence_after_sync();
-      const uint64_t bdesc = umma_desc_sw64(a_base + kOffRing + st.rs.stage * kStageBytes);
+      const uint64_t bdesc = umma_desc_sw128(a_base + kOffRing + st.rs.stage * kSlotBytes);
       const int n_apass = (is_lo || fast) ? 1 : 2;
       for (int ap = 0; ap < n_apass; ++ap) {
-        const uint64_t adesc = umma_desc_sw128(ap == 0 ? a_hi : a_lo) + 4u * kh;   // +64 bytes per 32-feature half
+        const uint64_t adesc = umma_desc_sw128(ap == 0 ? a_hi : a_lo);
 #pragma unroll
-        for (uint32_t ks = 0; ks < 2; ++ks) {
-          umma_f16_ss(acc, adesc + 2u * ks, bdesc + 2u * ks, idesc, accumulate);   // +32 bytes per K=16 step
+        for (uint32_t ks = 0; ks < 4; ++ks) {
+          umma2_f16_ss_warp(acc, adesc + 2u * ks, bdesc + 2u * ks, idesc, accumulate);   // +32 bytes per K=16 step
           accumulate = 1;
         }
       }
-      umma_commit(sm.bar(BAR_EMPTY + st.rs.stage));   // frees the ring slot when these MMAs are done
+      umma2_commit_warp(sm.bar(BAR_EMPTY + st.rs.stage));   // frees the ring slot in both CTAs when these MMAs are done
       st.rs.advance(sm.n_stages);
     }
   }
-  umma_commit(sm.bar(BAR_ACC + (st.layer_ctr & 1u)));   // accumulator complete -> epilogue
+  umma2_commit_warp(sm.bar(BAR_ACC + (st.layer_ctr & 1u)));   // accumulators complete -> both CTAs' epilogues
+  if (tracing && (threadIdx.x & 31) == 0) {   // one record per layer: issue window, cycles blocked on operands / on the weight ring
+    const long long t_out = clock64();
+    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(P.io.trace) + 1, 4ull);
+    if (static_cast<long long>(i) + 4 <= P.io.trace[0]) {
+      long long* e = P.io.trace + 2 + 3 * i;
+      e[0] = 0; e[1] = st.layer_ctr; e[2] = t_in;  e[3] = 8; e[4] = st.layer_ctr; e[5] = t_out;
+      e[6] = 20; e[7] = st.layer_ctr; e[8] = w_ops; e[9] = 21; e[10] = st.layer_ctr; e[11] = w_full;
+    }
+  }
   st.layer_ctr++;
 }
 
@@ -223,11 +272,18 @@ struct EpiCtx {
   __half2 amax2;                       // running max |activation| (fp16-range status flag)
 };
 
-__device__ __forceinline__ void epi_signal(const Smem& sm, const EpiCtx& c, int which) {
+// Publish an operand tile (A chunk `which` or the aux tile) this CTA's 16 epilogue warps just wrote:
+// generic-proxy stores -> async proxy, CTA-wide named barrier (keeps the warps in lockstep so chunk j is
+// ready after (j+1)/nch of the epilogue even though the warp scheduler is not fair), then ONE arrival
+// on the issuer CTA's barrier (expected count 2: one per CTA of the pair).
+__device__ __forceinline__ void epi_publish(const Smem& sm, const EpiCtx& c, int which) {
   fence_proxy_async_smem();
   tc_fence_before_sync();
-  __syncwarp();
-  if (c.lane == 0) mbar_arrive(sm.bar(BAR_AREADY + which));
+  named_bar_sync(2, kEpiThreads);
+  if (c.tid == 0) {
+    if (sm.rank == 0) mbar_arrive(sm.bar(BAR_AREADY + which));
+    else mbar_arrive_cluster_relaxed(sm.bar(BAR_AREADY + which), 0);
+  }
 }
 
 struct HeadOut { float h0, h1, h2, sig; };
@@ -272,6 +328,7 @@ __device__ __forceinline__ void epilogue_layer(const Smem& sm, const RenderParam
   mbar_wait(sm.bar(BAR_ACC + buf), (c.acc_phase >> buf) & 1u);
   c.acc_phase ^= 1u << buf;
   tc_fence_after_sync();
+  if (c.tid == 0) trace_ev(P, 10, c.layer_ctr);
 
 #pragma unroll 1
   for (int j = 0; j < nch; ++j) {
@@ -306,10 +363,11 @@ __device__ __forceinline__ void epilogue_layer(const Smem& sm, const RenderParam
     if (kWriteA) {
       const uint32_t tile = smem_u32(sm.base) + kOffA + static_cast<uint32_t>(j) * 2u * kChunkBytes;
       store_feat16(tile, c.row, 2 * c.cg, x, fast, c.amax2);
-      epi_signal(sm, c, j);   // this warp's share of chunk j of the next layer's A operand is ready
+      epi_publish(sm, c, j);
+      if (c.tid == 0) trace_ev(P, 11 + j, c.layer_ctr);
     }
   }
-  if (!kWriteA) tc_fence_before_sync();
+  if (!kWriteA) { tc_fence_before_sync(); if (c.tid == 0) trace_ev(P, 15, c.layer_ctr); }
   ho.h0 = h0; ho.h1 = h1; ho.h2 = h2; if (kSigma) ho.sig = sg;
   c.layer_ctr++;
 }
@@ -324,37 +382,39 @@ __device__ __forceinline__ void epilogue_dispatch(const Smem& sm, const RenderPa
 }
 
 // ---------------------------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem sm;
   sm.base = smem_raw;
-  sm.misc = reinterpret_cast<float*>(smem_raw + P.off_misc + 128);   // 128 B reserved for barriers + tmem ptr
+  sm.misc = reinterpret_cast<float*>(smem_raw + P.off_misc + kBarBytes);
   sm.bar0 = smem_u32(smem_raw + P.off_misc);
   sm.n_stages = static_cast<uint32_t>(P.n_stages);
+  sm.rank = cluster_ctarank();
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + P.off_misc + 8 * BAR_COUNT);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool fast = P.fast != 0;
   const bool smpl = P.kind == NRF_KIND_SMPL;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kNumStages; ++s) { mbar_init(sm.bar(BAR_FULL + s), 1); mbar_init(sm.bar(BAR_EMPTY + s), 1); }
+    // issuer CTA: a stage is full when its own producer (arrive + bytes) and the peer's relay have arrived
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(sm.bar(BAR_FULL + s), sm.rank == 0 ? 2 : 1); mbar_init(sm.bar(BAR_EMPTY + s), 1); }
     mbar_init(sm.bar(BAR_ACC + 0), 1); mbar_init(sm.bar(BAR_ACC + 1), 1);
-    for (int j = 0; j < 5; ++j) mbar_init(sm.bar(BAR_AREADY + j), kEpiWarps);   // one arrival per epilogue warp
+    for (int j = 0; j < 5; ++j) mbar_init(sm.bar(BAR_AREADY + j), 2);   // one arrival per CTA of the pair
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  if (warp == 1) tmem_alloc2<512>(smem_u32(tmem_slot));
   tc_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();          // barriers of both CTAs are initialised before any remote arrival
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_pass = P.run_fine ? 2 : 1;
 
   if (warp == 0) {
-    // =========================== weight producer ===========================
+    // =========================== weight producer (both CTAs: own half of every stage) ===========================
     if (lane == 0) {
       RingState rs;
-      for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x)
+      for (int pr = blockIdx.x >> 1; pr < P.n_pairs; pr += gridDim.x >> 1)
         for (int pass = 0; pass < n_pass; ++pass) {
           const int tiles = pass == 0 ? 1 : P.tiles_f;
           for (int t = 0; t < tiles; ++t) {
@@ -364,15 +424,21 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
         }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (even CTA) / stage relay (odd CTA) ===========================
+    // the whole warp runs these loops convergently; one elected lane issues each instruction
+    {
       MmaState st;
-      for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x)
+      for (int pr = blockIdx.x >> 1; pr < P.n_pairs; pr += gridDim.x >> 1)
         for (int pass = 0; pass < n_pass; ++pass) {
           const int tiles = pass == 0 ? 1 : P.tiles_f;
           for (int t = 0; t < tiles; ++t) {
-            if (smpl) mma_layer(sm, tmem_base, P.warp.layers[0], st, fast);
-            for (int l = 0; l < P.net[pass].n_layers; ++l) mma_layer(sm, tmem_base, P.net[pass].layers[l], st, fast);
+            if (sm.rank == 0) {
+              if (smpl) mma_layer(sm, P, tmem_base, P.warp.layers[0], st, fast);
+              for (int l = 0; l < P.net[pass].n_layers; ++l) mma_layer(sm, P, tmem_base, P.net[pass].layers[l], st, fast);
+            } else {
+              if (smpl) relay_layer(sm, P.warp.layers[0], st.rs, fast);
+              for (int l = 0; l < P.net[pass].n_layers; ++l) relay_layer(sm, P.net[pass].layers[l], st.rs, fast);
+            }
           }
         }
     }
@@ -396,8 +462,10 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
     const uint32_t aux_tile = smem_u32(sm.base) + kOffAux;
     const int G = P.G, nc = P.n_coarse, nf = P.n_fine, na = P.n_all;
 
-    for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
-      const int64_t ray0 = static_cast<int64_t>(grp) * G;
+    for (int pr = blockIdx.x >> 1; pr < P.n_pairs; pr += gridDim.x >> 1) {
+      // the pair renders ray groups 2*pr and 2*pr+1 in lockstep; a group past the end has no valid
+      // rays (every load/store is guarded) but still runs its MMAs, which the pair shares
+      const int64_t ray0 = (static_cast<int64_t>(pr) * 2 + sm.rank) * G;
       // ---- per-ray constants: origin, direction, |d|, raw pose pair
       if (c.tid < G) {
         const int g = c.tid;
@@ -500,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
           if (smpl) {
             // ---- warp field: x -> x + W2 relu(W1 [enc(x), pose] + b1) + b2
             write_encoding(aux_tile, c.row, c.cg, x, y, z, P.warp.in_freqs, P.warp.in_identity, fast);
-            epi_signal(sm, c, kSrcAux);
+            epi_publish(sm, c, kSrcAux);
             const float* wf32 = reinterpret_cast<const float*>(P.blob[2] + P.warp.f32_ofs);
             epilogue_layer<true, false, true, false>(sm, P, P.warp, wf32, rbw, P.warp.layers[0], c, g, ho);
             // all four threads of a row need the full 256-column dot products: exchange the column-group
@@ -530,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
           }
           // ---- encoded position -> aux (first layer and skip layer read it)
           write_encoding(aux_tile, c.row, c.cg, x, y, z, net.in_freqs, net.in_identity, fast);
-          epi_signal(sm, c, kSrcAux);
+          epi_publish(sm, c, kSrcAux);
 
           ho = {0.f, 0.f, 0.f, 0.f};
           float sigma_part = 0.f;
@@ -543,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
             if (L.flags & LF_WRITE_DIRPE) {
               // the skip layer's MMAs are long done: aux can now take the per-sample direction encoding
               write_encoding(aux_tile, c.row, c.cg, ux, uy, uz, net.dir_freqs, net.dir_identity, fast);
-              epi_signal(sm, c, kSrcAux);
+              epi_publish(sm, c, kSrcAux);
             }
           }
           // ---- combine the four column-group partials of the heads: raw = (rgb_raw, sigma_raw)
@@ -603,8 +671,8 @@ __global__ void __launch_bounds__(kThreads, 1) nrf_fused_kernel(const __grid_con
   }
 
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  cluster_sync_all();          // neither CTA may exit (or free TMEM) while its peer can still address it
+  if (warp == 1) tmem_dealloc2<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------- host launcher
@@ -680,6 +748,7 @@ extern "C" int nrf_render(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coar
   P.G = G;
   P.tiles_f = (G * na + kTileRows - 1) / kTileRows;
   P.n_groups = static_cast<int32_t>((n_rays + G - 1) / G);
+  P.n_pairs = (P.n_groups + 1) / 2;
 
   // shared-memory layout of the misc area (floats, 16-byte aligned pieces)
   uint32_t f = 0;
@@ -693,10 +762,10 @@ extern "C" int nrf_render(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coar
   P.o_zf = take(G * na);
   P.o_dnorm = take(smpl ? G * nc : 0);
   P.o_scratch = take(G * (nc + nf) > 16 ? G * (nc + nf) : 16);
-  P.n_stages = kNumStages;
-  if (kOffRing + kNumStages * kStageBytes + 128 + f * 4 > kSmemLimit) P.n_stages = 2;   // big per-ray tables: shorter weight ring
-  P.off_misc = kOffRing + static_cast<uint32_t>(P.n_stages) * kStageBytes;
-  const uint32_t smem_bytes = P.off_misc + 128 + f * 4;
+  P.n_stages = kMaxStages;
+  while (P.n_stages > 2 && kOffRing + static_cast<uint32_t>(P.n_stages) * kSlotBytes + kBarBytes + f * 4 > kSmemLimit) --P.n_stages;   // big per-ray tables: shorter weight ring
+  P.off_misc = kOffRing + static_cast<uint32_t>(P.n_stages) * kSlotBytes;
+  const uint32_t smem_bytes = P.off_misc + kBarBytes + f * 4;
   if (smem_bytes > kSmemLimit) { set_error("configuration needs %u bytes of shared memory per CTA (limit %u)", smem_bytes, kSmemLimit); return NRF_E_INVALID; }
 
   int dev = 0, sms = 0;
@@ -705,7 +774,9 @@ extern "C" int nrf_render(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coar
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
   if (n_sms > 0 && n_sms < sms) sms = n_sms;
-  const int grid = P.n_groups < sms ? P.n_groups : sms;
+  const int pairs = P.n_pairs < sms / 2 ? P.n_pairs : sms / 2;
+  if (pairs < 1) { set_error("the engine needs at least 2 SMs (CTA pairs)"); return NRF_E_INVALID; }
+  const int grid = 2 * pairs;
   e = cudaFuncSetAttribute(nrf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)");
   nrf_fused_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P);

@@ -143,14 +143,13 @@ __global__ void searchsorted_kernel(const float* __restrict__ a, int64_t rows_a,
 }
 
 // ------------------------------------------------------------------------------ tcgen05 self-test
-// D[128,256] = A[128,64] x B[256,64]^T through exactly the operand layouts the renderer uses: A as one
-// [128 x 64] SWIZZLE_128B tile, B as two [256 x 32] SWIZZLE_64B weight stages; four K=16 tcgen05.mma
-// with N = 256, accumulator read back with tcgen05.ld.
+// D[128,256] = A[128,64] x B[256,64]^T: A one [128 x 64] SWIZZLE_128B tile, B one [256 x 64] SWIZZLE_128B
+// tile, four K=16 tcgen05.mma with N = 256, accumulator read back with tcgen05.ld.
 __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                                 float* __restrict__ d) {
   extern __shared__ __align__(1024) uint8_t smem_st[];
   uint8_t* sa = smem_st;             // 16 KB
-  uint8_t* sb = smem_st + 16384;     // 2 x 16 KB
+  uint8_t* sb = smem_st + 16384;     // 32 KB
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_st + 49152);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_st + 49152 + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -160,7 +159,7 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const float* __re
   }
   for (int idx = threadIdx.x; idx < 256 * 64; idx += 128) {
     const int r = idx >> 6, k = idx & 63;
-    *reinterpret_cast<__half*>(sb + (k >> 5) * 16384 + sw64_offset(r, k & 31)) = __float2half_rn(b[idx]);
+    *reinterpret_cast<__half*>(sb + sw128_offset(r, k)) = __float2half_rn(b[idx]);
   }
   if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc<256>(smem_u32(tmem_slot));
@@ -171,11 +170,8 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const float* __re
   const uint32_t tmem = *tmem_slot;
   if (threadIdx.x == 0) {
     const uint32_t idesc = umma_idesc_f16(128, 256);
-    const uint64_t ad = umma_desc_sw128(smem_u32(sa));
-    for (uint32_t kh = 0; kh < 2; ++kh) {
-      const uint64_t bd = umma_desc_sw64(smem_u32(sb) + kh * 16384u);
-      for (uint32_t ks = 0; ks < 2; ++ks) umma_f16_ss(tmem, ad + 4u * kh + 2u * ks, bd + 2u * ks, idesc, (kh | ks) ? 1u : 0u);
-    }
+    const uint64_t ad = umma_desc_sw128(smem_u32(sa)), bd = umma_desc_sw128(smem_u32(sb));
+    for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem, ad + 2u * ks, bd + 2u * ks, idesc, ks ? 1u : 0u);
     umma_commit(smem_u32(bar));
   }
   mbar_wait(smem_u32(bar), 0);
@@ -190,6 +186,51 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const float* __re
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// Same through a CTA pair: D[256,256] = A[256,64] x B[256,64]^T with tcgen05.mma.cta_group::2 (M = 256).
+// CTA r holds A rows [128r, 128r+128) and B rows (output features) [128r, 128r+128) as one [128 x 64]
+// SWIZZLE_128B half-stage -- the renderer's layout; the even CTA issues, the commit multicasts.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+selftest_umma2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d) {
+  extern __shared__ __align__(1024) uint8_t smem_st[];
+  uint8_t* sa = smem_st;             // 16 KB
+  uint8_t* sb = smem_st + 16384;     // 16 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_st + 32768);       // [0] accumulator ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_st + 32768 + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  for (int idx = threadIdx.x; idx < 128 * 64; idx += 128) {
+    const int r = idx >> 6, k = idx & 63;
+    *reinterpret_cast<__half*>(sa + sw128_offset(r, k)) = __float2half_rn(a[(128 * rank + r) * 64 + k]);
+    *reinterpret_cast<__half*>(sb + sw128_offset(r, k)) = __float2half_rn(b[(128 * rank + r) * 64 + k]);
+  }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); mbar_init(smem_u32(bar + 1), 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc2<256>(smem_u32(tmem_slot));
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  if (rank == 0 && threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_f16(256, 256);
+    const uint64_t ad = umma_desc_sw128(smem_u32(sa)), bd = umma_desc_sw128(smem_u32(sb));
+    for (uint32_t ks = 0; ks < 4; ++ks) umma2_f16_ss(tmem, ad + 2u * ks, bd + 2u * ks, idesc, ks ? 1u : 0u);
+    umma2_commit(smem_u32(bar));
+  }
+  mbar_wait(smem_u32(bar), 0);
+  tc_fence_after_sync();
+  const int row = 32 * (warp & 3) + lane;
+  for (int c0 = 0; c0 < 256; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) d[(128 * rank + row) * 256 + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2<256>(tmem);
 }
 
 static int grid_for(int64_t total, int block) {
@@ -267,6 +308,16 @@ extern "C" int nrf_searchsorted(const float* a, int64_t rows_a, int64_t na, cons
   searchsorted_kernel<<<grid_for(rows * nv, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, rows_a, na, v, rows_v, nv, res, side_left, rows);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "searchsorted_kernel launch");
+}
+
+extern "C" int nrf_selftest_umma2(const float* a, const float* b, float* d, void* stream) {
+  if (!a || !b || !d) { set_error("selftest: NULL argument"); return NRF_E_INVALID; }
+  const int smem = 32768 + 64;
+  cudaError_t e = cudaFuncSetAttribute(selftest_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  selftest_umma2_kernel<<<2, 128, smem, static_cast<cudaStream_t>(stream)>>>(a, b, d);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "selftest_umma2_kernel launch");
 }
 
 extern "C" int nrf_selftest_umma(const float* a, const float* b, float* d, void* stream) {

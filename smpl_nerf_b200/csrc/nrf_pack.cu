@@ -137,17 +137,17 @@ __device__ __forceinline__ int dev_enc_ref_col(int f, int freqs, int identity) {
 
 __global__ void pack_stream_kernel(const __grid_constant__ PackTable t, uint8_t* __restrict__ blob) {
   const PackChunk& c = t.c[blockIdx.x];
-  const int part = blockIdx.y, kh = part >> 1, is_lo = part & 1;   // stage order: hi/k0, lo/k0, hi/k1, lo/k1
-  const int rows = c.n_out;
-  uint8_t* stage = blob + c.dst + static_cast<uint32_t>(part) * rows * 64u;
-  for (int idx = threadIdx.x; idx < rows * 32; idx += blockDim.x) {
-    const int n = idx >> 5, kk = idx & 31, k = 32 * kh + kk;
+  const int part = blockIdx.y, half = part & 1, is_lo = part >> 1;   // stage order: hi/half0, hi/half1, lo/half0, lo/half1
+  const int rows = c.n_out / 2;
+  uint8_t* stage = blob + c.dst + static_cast<uint32_t>(part) * rows * 128u;
+  for (int idx = threadIdx.x; idx < rows * kChunkK; idx += blockDim.x) {
+    const int n = idx >> 6, k = idx & 63;
     int col = c.aux ? dev_enc_ref_col(k, c.freqs, c.identity) : k;
     float w = 0.f;
-    if (col >= 0) w = c.w[static_cast<size_t>(n) * c.ld + c.col0 + col];
+    if (col >= 0) w = c.w[static_cast<size_t>(half * rows + n) * c.ld + c.col0 + col];
     __half hi, lo;
     split_f16(w, hi, lo);
-    *reinterpret_cast<__half*>(stage + sw64_offset(n, kk)) = is_lo ? lo : hi;
+    *reinterpret_cast<__half*>(stage + sw128_offset(n, k)) = is_lo ? lo : hi;
   }
 }
 

@@ -9,14 +9,13 @@
 //
 // Packed blob of a net (device memory, 1024-byte aligned):
 //   [ weight stream | fp32 section ]
-// weight stream = for each layer, for each 64-feature K-chunk, four stages in consumption order
-//   hi/k-half0, lo/k-half0, hi/k-half1, lo/k-half1
-// where k-half h holds input features [32h, 32h+32) of the chunk for ALL n_out output features and
-// hi/lo are the fp16 split of the fp32 weight (w ~= hi + lo).  A stage is a [n_out x 32] fp16 K-major
-// tile in the UMMA SWIZZLE_64B layout (n_out * 64 bytes: 16 KB for the 256-wide layers), i.e. exactly
-// the bytes the tensor core wants in shared memory, so staging is one 1-D bulk copy and every MMA
-// instruction covers the full N (an N = 128 instruction re-reads the A tile twice as often and runs at
-// ~52 % of the tensor floor -- measured with nrf_bench_umma, profiles/r1/umma_probe.txt).
+// weight stream = for each layer, for each 64-feature K-chunk, four stages
+//   hi/half0, hi/half1, lo/half0, lo/half1
+// where half h holds output features [h*N/2, (h+1)*N/2) and hi/lo are the fp16 split of the fp32
+// weight (w ~= hi + lo).  A stage is a [N/2 x 64] fp16 K-major tile in the UMMA SWIZZLE_128B layout
+// (16 KB for the 256-wide layers), i.e. exactly the bytes the tensor core wants in shared memory, so
+// staging is one 1-D bulk copy.  The renderer runs as CTA pairs (tcgen05 cta_group::2): CTA r of a pair
+// stages only half r of every stage and each M=256 x N instruction reads both halves.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>

@@ -126,7 +126,7 @@ def _f32(t: torch.Tensor, name: str, device, shape=None) -> torch.Tensor:
 
 def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_enc, pose_enc, data,
            *, taps: bool = False, z_all_in: Optional[torch.Tensor] = None, noise=None, n_sms: int = 0,
-           precision: int = 0) -> Dict[str, torch.Tensor]:
+           precision: int = 0, trace_cap: int = 0) -> Dict[str, torch.Tensor]:
     """One fused forward.  ``data`` is the reference's per-batch list
     [ray_samples, ray_translation, ray_direction, z_vals, (goal_pose,) rgb]; returns a dict of
     freshly allocated fp32 CUDA tensors (see NrfRenderIO in include/nrf_b200.h)."""
@@ -227,6 +227,11 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
                 new('raw_fine', B, n, 4)
                 new('z_new', B, nf)
                 new('z_all', B, n)
+        if trace_cap > 0:       # developer tap: CTA 0's MMA / epilogue timeline
+            tr = torch.zeros(2 + 3 * trace_cap, dtype=torch.int64, device=device)
+            tr[0] = trace_cap
+            out['trace'] = tr
+            io.trace = tr.data_ptr()
         status = torch.zeros(1, dtype=torch.int32, device=device)
         out['status'] = status
         io.status = status.data_ptr()

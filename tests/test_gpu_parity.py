@@ -46,6 +46,18 @@ def test_selftest_umma():
     assert float((d.double() - ref.to(DEV)).abs().max()) < 1e-4
 
 
+def test_selftest_umma_cta_pair():
+    """tcgen05.mma.cta_group::2 through the renderer's operand layouts (each CTA stages half of B)."""
+    L = _lib.lib()
+    torch.manual_seed(1)
+    a, b = torch.randn(256, 64, device=DEV), torch.randn(256, 64, device=DEV)
+    d = torch.zeros(256, 256, device=DEV)
+    _lib.check(L.nrf_selftest_umma2(a.data_ptr(), b.data_ptr(), d.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = a.half().double() @ b.half().double().t()
+    assert float((d.double() - ref.to(DEV)).abs().max()) < 1e-4
+
+
 @pytest.mark.parametrize('name', H.fixtures())
 def test_fixture_stagewise(name):
     fx = H.load_fixture(name)

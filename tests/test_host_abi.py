@@ -38,7 +38,7 @@ def test_struct_sizes_match_header(L):
     assert C.sizeof(_lib.RayNetDesc) == 4 * (7 + 4 + 5)
     assert C.sizeof(_lib.WarpNetDesc) == 4 * 5
     assert C.sizeof(_lib.PipelineDesc) == 4 * 12
-    assert C.sizeof(_lib.RenderIO) == 8 * 21
+    assert C.sizeof(_lib.RenderIO) == 8 * 22
 
 
 def test_planner_sizes_and_rejections(L):
