@@ -553,6 +553,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           const bool valid = in_rows && ri < P.n_rays;
           const float* r = ray + g * kRayFloats;
           float x = 0.f, y = 0.f, z = 0.f;
+          if (c.tid == 0) trace_ev(P, 30, c.layer_ctr);
           if (valid) {
             if (pass == 0) {
               const float* ps = P.io.ray_samples + (ri * nc + s) * 3;
@@ -567,14 +568,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           HeadOut ho = {0.f, 0.f, 0.f, 0.f};
           if (smpl) {
             // ---- warp field: x -> x + W2 relu(W1 [enc(x), pose] + b1) + b2
+            if (c.tid == 0) trace_ev(P, 31, c.layer_ctr);
             write_encoding(aux_tile, c.row, c.cg, x, y, z, P.warp.in_freqs, P.warp.in_identity, fast);
+            if (c.tid == 0) trace_ev(P, 32, c.layer_ctr);
             epi_publish(sm, c, kSrcAux);
+            if (c.tid == 0) trace_ev(P, 33, c.layer_ctr);
             const float* wf32 = reinterpret_cast<const float*>(P.blob[2] + P.warp.f32_ofs);
             epilogue_layer<true, false, true, false>(sm, P, P.warp, wf32, rbw, P.warp.layers[0], c, g, ho);
             // all four threads of a row need the full 256-column dot products: exchange the column-group
             // partials through smem and add them in the same order -> identical bits in every thread
             xchg[c.cg] = make_float4(ho.h0, ho.h1, ho.h2, 0.f);
             named_bar_sync(1, kEpiThreads);
+            if (c.tid == 0) trace_ev(P, 35, c.layer_ctr);
             float w0, w1, w2;
             {
               const float* b2 = wf32 + P.warp.head_ofs + 3 * kWidth;
@@ -597,8 +602,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
             //  sits behind an mbarrier that all 16 warps arrive on only after these reads)
           }
           // ---- encoded position -> aux (first layer and skip layer read it)
+          if (c.tid == 0) trace_ev(P, 36, c.layer_ctr);
           write_encoding(aux_tile, c.row, c.cg, x, y, z, net.in_freqs, net.in_identity, fast);
+          if (c.tid == 0) trace_ev(P, 37, c.layer_ctr);
           epi_publish(sm, c, kSrcAux);
+          if (c.tid == 0) trace_ev(P, 38, c.layer_ctr);
 
           ho = {0.f, 0.f, 0.f, 0.f};
           float sigma_part = 0.f;
@@ -617,6 +625,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           // ---- combine the four column-group partials of the heads: raw = (rgb_raw, sigma_raw)
           if (c.cg != 0) xchg[c.cg] = make_float4(ho.h0, ho.h1, ho.h2, sigma_part);
           named_bar_sync(1, kEpiThreads);
+          if (c.tid == 0) trace_ev(P, 39, c.layer_ctr);
           if (c.cg == 0) {
             const float4 p1 = xchg[1], p2 = xchg[2], p3 = xchg[3];
             const float* hb = f32 + net.head_ofs + 3 * (kWidth / 2);
@@ -634,6 +643,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           // the exchange slots are next written behind an mbarrier every warp arrives on after this point
         }
         named_bar_sync(1, kEpiThreads);   // raw4 of every tile of this pass is complete
+        if (c.tid == 0) trace_ev(P, 40, c.layer_ctr);
 
         // ---- per-ray: compositing (+ sampling after the coarse pass); one warp per ray
         if (ew < G) {
@@ -664,6 +674,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           }
         }
         named_bar_sync(1, kEpiThreads);
+        if (c.tid == 0) trace_ev(P, 41, c.layer_ctr);
       }
     }
     const uint32_t am = *reinterpret_cast<const uint32_t*>(&c.amax2);

@@ -25,7 +25,9 @@ waits = {(e, c): t for e, c, t in ev if e in (20, 21)}
 ev = [e for e in ev if e[0] not in (20, 21)]
 ev.sort(key=lambda e: e[2])
 t0 = ev[0][2]
-names = {0: 'M start', 8: 'M issued', 10: 'E acc-ready', 15: 'E head done'}
+names = {0: 'M start', 8: 'M issued', 10: 'E acc-ready', 15: 'E head done', 30: 'T tile top', 31: 'T points loaded', 32: 'T warp-PE written',
+         33: 'T warp-PE published', 35: 'T warp heads exchanged', 36: 'T warped pos + dirs done', 37: 'T PE written', 38: 'T PE published',
+         39: 'T heads exchanged (tile end)', 40: 'R pass raw complete', 41: 'R ray stage done'}
 last = {}
 nl = 12 * 4 + 2
 for e, ctr, t in ev:
