@@ -14,7 +14,7 @@ from typing import List
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB_PATH = os.path.join(CSRC, 'libnrf_b200.so')
+LIB_PATH = os.environ.get('NRF_LIB_PATH') or os.path.join(CSRC, 'libnrf_b200.so')   # NRF_LIB_PATH: A/B builds (developer)
 SOURCES = ['nrf_pack.cu', 'nrf_fused.cu', 'nrf_ops.cu', 'nrf_diag.cu']
 HEADERS = ['nrf_plan.h', 'nrf_ptx.cuh', 'nrf_stages.cuh', os.path.join('..', '..', 'include', 'nrf_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
@@ -75,7 +75,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     if not os.path.isfile(nvcc):
         raise RuntimeError('nvcc not found: cannot build libnrf_b200.so (and there is no CPU fallback)')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + SOURCES
+    extra = os.environ.get('NRF_NVCC_EXTRA', '').split()     # e.g. -DNRF_SOME_EXPERIMENT=1 (developer A/B builds)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + SOURCES
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)

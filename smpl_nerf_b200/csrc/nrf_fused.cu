@@ -50,7 +50,9 @@ constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kRayVec = 8 + kMaxRayFeat + 32;      // unit direction[3], raw pose pair[2]
-constexpr int kRayFloats = kRayVec + 8;            // o[3] d[3] |d| valid | pose feats[64] | dir feats[32] | unit d, pose
+constexpr int kRayFloats = kRayVec + 8;
+constexpr int kRayScratchFloats = 2 * kMaxFineRows + (kTileRows + 16) + kTileRows + kMaxFineRows + kTeamScratch;   // tf, tt, cdf, pdf, z_samples, team partials of one ray
+static_assert((kTileRows / 16) * kRayScratchFloats * 4 <= 3 * 2 * 16384, "per-ray scratch must fit below the exchange slots in the A region");            // o[3] d[3] |d| valid | pose feats[64] | dir feats[32] | unit d, pose
 
 // barrier slots inside the misc area (8 bytes each)
 enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC = 2 * kMaxStages, BAR_AREADY = 2 * kMaxStages + 2,
@@ -69,7 +71,7 @@ struct RenderParams {
   int32_t G, tiles_f, n_groups, n_pairs, n_stages;
   uint32_t off_misc;   // byte offset of the barrier + per-ray area (behind the weight ring)
   // float offsets inside the misc area (after the barriers)
-  uint32_t o_ray, o_rb, o_rbw, o_raw, o_zc, o_zf, o_dnorm, o_scratch;
+  uint32_t o_ray, o_rb, o_rbw, o_raw, o_zc, o_zf, o_u, o_hw, o_hr, o_hs;
 };
 
 struct Smem {
@@ -162,11 +164,18 @@ __device__ __forceinline__ void write_encoding(uint32_t aux_tile, int row, int c
   store_feat16(aux_tile, row, 2 * cg, f, fast, dummy);
 }
 
-// Developer tap: CTA 0 appends (event, counter, SM clock) to io.trace ([0] = capacity, [1] = count).
+// Developer tap: CTA 0 appends (event, counter, SM clock) to io.trace ([0] = capacity, [1] = count).  The slot
+// counter lives in shared memory (a global atomic's round trip would inflate every traced segment by ~1000 cycles)
+// and is copied to trace[1] when the kernel ends.
+constexpr uint32_t kTraceCtrOfs = 128;   // inside the barrier area
+__device__ __forceinline__ uint32_t trace_slots(const RenderParams& P, uint32_t n) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  return atomicAdd(reinterpret_cast<uint32_t*>(smem_raw + P.off_misc + kTraceCtrOfs), n);
+}
 __device__ __forceinline__ void trace_ev(const RenderParams& P, int ev, uint32_t ctr) {
   if (P.io.trace && blockIdx.x == 0) {
     const long long t = clock64();
-    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(P.io.trace) + 1, 1ull);
+    const uint32_t i = trace_slots(P, 1);
     if (static_cast<long long>(i) < P.io.trace[0]) { long long* e = P.io.trace + 2 + 3 * i; e[0] = ev; e[1] = ctr; e[2] = t; }
   }
 }
@@ -250,7 +259,7 @@ __device__ __forceinline__ void mma_layer(const Smem& sm, const RenderParams& P,
   umma2_commit_warp(sm.bar(BAR_ACC + (st.layer_ctr & 1u)));   // accumulators complete -> both CTAs' epilogues
   if (tracing && (threadIdx.x & 31) == 0) {   // one record per layer: issue window, cycles blocked on operands / on the weight ring
     const long long t_out = clock64();
-    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(P.io.trace) + 1, 4ull);
+    const uint32_t i = trace_slots(P, 4);
     if (static_cast<long long>(i) + 4 <= P.io.trace[0]) {
       long long* e = P.io.trace + 2 + 3 * i;
       e[0] = 0; e[1] = st.layer_ctr; e[2] = t_in;  e[3] = 8; e[4] = st.layer_ctr; e[5] = t_out;
@@ -270,6 +279,8 @@ struct EpiCtx {
   uint32_t tmem_base;
   uint32_t lane_taddr;                 // TMEM lane field for this warp's quarter
   __half2 amax2;                       // running max |activation| (fp16-range status flag)
+  const float* head_s;                 // smem copy of the 3-row head weights of the layer being drained ([3][n_out])
+  const float* sigma_s;                // smem copy of the sigma head weights ([256])
 };
 
 // Publish an operand tile (A chunk `which` or the aux tile) this CTA's 16 epilogue warps just wrote:
@@ -312,18 +323,33 @@ __device__ __forceinline__ float dot16(const float (&x)[16], const float (&w)[16
 //   kRelu: out = relu(acc + bias) (else acc + bias)     kWriteA: out -> next layer's A operand chunks
 //   kHead3: 3-row head dot products (rgb / warp)        kSigma: sigma head dot product
 //   g: ray index inside the group of this thread's row (selects the per-ray bias vector)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 template <bool kRelu, bool kWriteA, bool kHead3, bool kSigma>
 __device__ __forceinline__ void epilogue_layer(const Smem& sm, const RenderParams& P, const NetPlan& net, const float* f32,
                                                const float* rb_base, const Layer& L, EpiCtx& c, int g, HeadOut& ho) {
   const uint32_t buf = c.layer_ctr & 1u;
-  const uint32_t acc = c.tmem_base + buf * 256u + c.lane_taddr;
+  const uint32_t acc = c.tmem_base + buf * 256u + c.lane_taddr + 16u * static_cast<uint32_t>(c.cg);
   const bool fast = P.fast != 0;
   const int nch = L.n_out >> 6;
-  const float* bias_g = f32 + L.bias_ofs;
-  const float* bias_s = (L.ray_slot >= 0) ? rb_base + (static_cast<int>(L.ray_slot) * P.G + g) * kWidth : nullptr;
-  const float* wh = f32 + net.head_ofs;     // [3][n_out]
-  const float* ws = f32 + net.sigma_ofs;    // [256]
+  const float* bias_g = f32 + L.bias_ofs + 16 * c.cg;
+  const float* bias_s = (L.ray_slot >= 0) ? rb_base + (static_cast<int>(L.ray_slot) * P.G + g) * kWidth + 16 * c.cg : nullptr;
+  const float* wh = c.head_s + 16 * c.cg;     // [3][n_out]   (shared memory: a global load here is pure latency)
+  const float* ws = c.sigma_s + 16 * c.cg;    // [256]
   float h0 = 0.f, h1 = 0.f, h2 = 0.f, sg = 0.f;
+
+  // warm L1 with this thread's bias lines while the accumulator is still being produced
+  if (!bias_s) {
+#pragma unroll 1
+    for (int j = 0; j < nch; ++j) asm volatile("prefetch.global.L1 [%0];" ::"l"(bias_g + 64 * j));
+  }
 
   mbar_wait(sm.bar(BAR_ACC + buf), (c.acc_phase >> buf) & 1u);
   c.acc_phase ^= 1u << buf;
@@ -332,18 +358,17 @@ __device__ __forceinline__ void epilogue_layer(const Smem& sm, const RenderParam
 
 #pragma unroll 1
   for (int j = 0; j < nch; ++j) {
-    const int col0 = 64 * j + 16 * c.cg;
-    // issue the TMEM load, then fetch the biases while it is in flight
+    // issue the TMEM load, then fetch the biases (and the head weights) while it is in flight.  (Hoisting the
+    // next chunk's TMEM load / bias above the publish of this one was measured slower: tcgen05.fence::
+    // before_thread_sync waits for the load, and 32 more live registers across the loop cost more than they hide.)
     uint32_t v[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(acc + static_cast<uint32_t>(col0))
-        : "memory");
+    tmem_ld16_issue(acc + 64u * static_cast<uint32_t>(j), v);
     float b[16];
-    if (bias_s) ld_f16(bias_s + col0, b);
-    else ldg_f16(bias_g + col0, b);
+    if (bias_s) ld_f16(bias_s + 64 * j, b);
+    else ldg_f16(bias_g + 64 * j, b);
+    float w[16];
+    if (kSigma) ld_f16(ws + 64 * j, w);
+    if (kHead3) ld_f16(wh + 64 * j, w);
     tmem_ld_wait();
     float x[16];
 #pragma unroll
@@ -351,14 +376,11 @@ __device__ __forceinline__ void epilogue_layer(const Smem& sm, const RenderParam
       const float t = __uint_as_float(v[i]) + b[i];
       x[i] = kRelu ? fmaxf(t, 0.f) : t;
     }
-    if (kSigma) {
-      ldg_f16(ws + col0, b);
-      sg = dot16(x, b, sg);
-    }
+    if (kSigma) sg = dot16(x, w, sg);
     if (kHead3) {
-      ldg_f16(wh + col0, b);             h0 = dot16(x, b, h0);
-      ldg_f16(wh + L.n_out + col0, b);   h1 = dot16(x, b, h1);
-      ldg_f16(wh + 2 * L.n_out + col0, b); h2 = dot16(x, b, h2);
+      ld_f16(wh + L.n_out + 64 * j, b);      h0 = dot16(x, w, h0);
+      ld_f16(wh + 2 * L.n_out + 64 * j, w);  h1 = dot16(x, b, h1);
+      h2 = dot16(x, w, h2);
     }
     if (kWriteA) {
       const uint32_t tile = smem_u32(sm.base) + kOffA + static_cast<uint32_t>(j) * 2u * kChunkBytes;
@@ -396,6 +418,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
   const bool smpl = P.kind == NRF_KIND_SMPL;
 
   if (threadIdx.x == 0) {
+    *reinterpret_cast<uint32_t*>(smem_raw + P.off_misc + kTraceCtrOfs) = 0u;
     // issuer CTA: a stage is full when its own producer (arrive + bytes) and the peer's relay have arrived
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(sm.bar(BAR_FULL + s), sm.rank == 0 ? 2 : 1); mbar_init(sm.bar(BAR_EMPTY + s), 1); }
     mbar_init(sm.bar(BAR_ACC + 0), 1); mbar_init(sm.bar(BAR_ACC + 1), 1);
@@ -448,6 +471,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
     c.warp = warp; c.lane = lane; c.q = warp & 3; c.cg = (warp - 2) >> 2; c.row = 32 * c.q + lane;
     c.tid = threadIdx.x - 64; c.tmem_base = tmem_base; c.lane_taddr = static_cast<uint32_t>(32 * c.q) << 16;
     c.amax2 = __floats2half2_rn(0.f, 0.f);
+    c.head_s = nullptr; c.sigma_s = nullptr;
     const int ew = warp - 2;   // 0..15
     float* ray = sm.misc + P.o_ray;          // [G][kRayFloats]
     float* rb = sm.misc + P.o_rb;            // [slots][G][256]
@@ -455,12 +479,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
     float4* raw4 = reinterpret_cast<float4*>(sm.misc + P.o_raw);   // [G * n_all]
     float* zc = sm.misc + P.o_zc;            // [G][n_coarse]
     float* zf = sm.misc + P.o_zf;            // [G][n_all]
-    float* dnorm = sm.misc + P.o_dnorm;      // [G * n_coarse] (smpl coarse pass)
-    float* scratch = sm.misc + P.o_scratch;  // ray phase: cdf + zs
+    float* u_s = sm.misc + P.o_u;            // [n_fine] the sampler's u = linspace(0, 1, n_fine)
+    float* hw_s = sm.misc + P.o_hw;          // warp net head weights [3][256] (smpl)
+    float* hr_s = sm.misc + P.o_hr;          // rgb head weights [3][128] of the current net
+    float* hs_s = sm.misc + P.o_hs;          // sigma head weights [256] of the current net
     // head-partial exchange: 8 float4 slots per row inside A chunk 3 (dead whenever it is used)
-    float4* xchg = reinterpret_cast<float4*>(sm.base + kOffXchg) + 8 * c.row;
+    float4* xchg = reinterpret_cast<float4*>(sm.base + kOffXchg) + c.row;   // slot of column group k: xchg[kTileRows * k] (lanes contiguous: no bank conflicts)
     const uint32_t aux_tile = smem_u32(sm.base) + kOffAux;
     const int G = P.G, nc = P.n_coarse, nf = P.n_fine, na = P.n_all;
+    // head biases live in registers (a dependent global load here sits on the tile-to-tile critical path)
+    float wb0 = 0.f, wb1 = 0.f, wb2 = 0.f;
+    if (smpl) {
+      const float* b2 = reinterpret_cast<const float*>(P.blob[2] + P.warp.f32_ofs) + P.warp.head_ofs + 3 * kWidth;
+      wb0 = __ldg(b2 + 0); wb1 = __ldg(b2 + 1); wb2 = __ldg(b2 + 2);
+      for (int i = c.tid; i < 3 * kWidth; i += kEpiThreads) hw_s[i] = __ldg(b2 - 3 * kWidth + i);
+    }
+
+    if (P.run_fine && !P.io.z_all_in) for (int i = c.tid; i < nf; i += kEpiThreads) u_s[i] = __ldg(P.io.u_fine + i);
 
     for (int pr = blockIdx.x >> 1; pr < P.n_pairs; pr += gridDim.x >> 1) {
       // the pair renders ray groups 2*pr and 2*pr+1 in lockstep; a group past the end has no valid
@@ -530,6 +565,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
         const bool last_pass = (pass == n_pass - 1);
         const int n = pass == 0 ? nc : na;
         const int tiles = pass == 0 ? 1 : P.tiles_f;
+        const float hb0 = __ldg(f32 + net.head_ofs + 3 * (kWidth / 2) + 0), hb1 = __ldg(f32 + net.head_ofs + 3 * (kWidth / 2) + 1),
+                    hb2 = __ldg(f32 + net.head_ofs + 3 * (kWidth / 2) + 2), sb = __ldg(f32 + net.sigma_ofs + kWidth);
+        for (int i = c.tid; i < 3 * (kWidth / 2); i += kEpiThreads) hr_s[i] = __ldg(f32 + net.head_ofs + i);
+        for (int i = c.tid; i < kWidth; i += kEpiThreads) hs_s[i] = __ldg(f32 + net.sigma_ofs + i);
+        c.sigma_s = hs_s;
         // ---- per-ray bias vectors of this net (pose / direction contributions)
         for (int l = 0; l < net.n_layers; ++l) {
           const Layer& L = net.layers[l];
@@ -557,14 +597,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           if (valid) {
             if (pass == 0) {
               const float* ps = P.io.ray_samples + (ri * nc + s) * 3;
-              x = ps[0]; y = ps[1]; z = ps[2];
+              x = __ldcs(ps); y = __ldcs(ps + 1); z = __ldcs(ps + 2);
             } else {
               const float zz = zf[g * na + s];
               x = __fadd_rn(r[0], __fmul_rn(r[3], zz)); y = __fadd_rn(r[1], __fmul_rn(r[4], zz)); z = __fadd_rn(r[2], __fmul_rn(r[5], zz));
-              if (c.cg == 0 && P.io.samples_out) { float* po = P.io.samples_out + (ri * na + s) * 3; po[0] = x; po[1] = y; po[2] = z; }
+              if (c.cg == 0 && P.io.samples_out) { float* po = P.io.samples_out + (ri * na + s) * 3; __stcs(po, x); __stcs(po + 1, y); __stcs(po + 2, z); }
             }
           }
           float ux = 0.f, uy = 0.f, uz = 1.f;   // unit view direction of this sample (smpl)
+          float dnorm_s = r[6];                 // |direction| that scales this sample's delta (utils.py:165-167)
           HeadOut ho = {0.f, 0.f, 0.f, 0.f};
           if (smpl) {
             // ---- warp field: x -> x + W2 relu(W1 [enc(x), pose] + b1) + b2
@@ -574,30 +615,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
             epi_publish(sm, c, kSrcAux);
             if (c.tid == 0) trace_ev(P, 33, c.layer_ctr);
             const float* wf32 = reinterpret_cast<const float*>(P.blob[2] + P.warp.f32_ofs);
+            c.head_s = hw_s;
             epilogue_layer<true, false, true, false>(sm, P, P.warp, wf32, rbw, P.warp.layers[0], c, g, ho);
             // all four threads of a row need the full 256-column dot products: exchange the column-group
             // partials through smem and add them in the same order -> identical bits in every thread
-            xchg[c.cg] = make_float4(ho.h0, ho.h1, ho.h2, 0.f);
+            xchg[kTileRows * c.cg] = make_float4(ho.h0, ho.h1, ho.h2, 0.f);
             named_bar_sync(1, kEpiThreads);
             if (c.tid == 0) trace_ev(P, 35, c.layer_ctr);
             float w0, w1, w2;
             {
-              const float* b2 = wf32 + P.warp.head_ofs + 3 * kWidth;
-              const float4 p0 = xchg[0], p1 = xchg[1], p2 = xchg[2], p3 = xchg[3];
-              w0 = __fadd_rn(__fadd_rn(__fadd_rn(p0.x, p1.x), __fadd_rn(p2.x, p3.x)), __ldg(b2 + 0));
-              w1 = __fadd_rn(__fadd_rn(__fadd_rn(p0.y, p1.y), __fadd_rn(p2.y, p3.y)), __ldg(b2 + 1));
-              w2 = __fadd_rn(__fadd_rn(__fadd_rn(p0.z, p1.z), __fadd_rn(p2.z, p3.z)), __ldg(b2 + 2));
+              const float4 p0 = xchg[0], p1 = xchg[kTileRows], p2 = xchg[2 * kTileRows], p3 = xchg[3 * kTileRows];
+              w0 = __fadd_rn(__fadd_rn(__fadd_rn(p0.x, p1.x), __fadd_rn(p2.x, p3.x)), wb0);
+              w1 = __fadd_rn(__fadd_rn(__fadd_rn(p0.y, p1.y), __fadd_rn(p2.y, p3.y)), wb1);
+              w2 = __fadd_rn(__fadd_rn(__fadd_rn(p0.z, p1.z), __fadd_rn(p2.z, p3.z)), wb2);
             }
             const float wx = __fadd_rn(x, w0), wy = __fadd_rn(y, w1), wz = __fadd_rn(z, w2);
             if (valid && last_pass && c.cg == 1) {
-              if (P.io.warp_out) { float* po = P.io.warp_out + (ri * n + s) * 3; po[0] = w0; po[1] = w1; po[2] = w2; }
-              if (P.io.warped_out) { float* po = P.io.warped_out + (ri * n + s) * 3; po[0] = wx; po[1] = wy; po[2] = wz; }
+              if (P.io.warp_out) { float* po = P.io.warp_out + (ri * n + s) * 3; __stcs(po, w0); __stcs(po + 1, w1); __stcs(po + 2, w2); }
+              if (P.io.warped_out) { float* po = P.io.warped_out + (ri * n + s) * 3; __stcs(po, wx); __stcs(po + 1, wy); __stcs(po + 2, wz); }
             }
             x = wx; y = wy; z = wz;
             const float dx = __fsub_rn(x, r[0]), dy = __fsub_rn(y, r[1]), dz = __fsub_rn(z, r[2]);
             const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
             if (in_rows) { ux = __fdiv_rn(dx, nrm); uy = __fdiv_rn(dy, nrm); uz = __fdiv_rn(dz, nrm); }
-            if (pass == 0 && c.cg == 2 && in_rows) dnorm[R] = nrm;
+            if (pass == 0) dnorm_s = nrm;       // coarse pass: per-sample |warped - o| (smpl_nerf_pipeline.py:52,63); fine: |ray_direction| (:95-98)
             // (no barrier needed before the exchange slots are reused: every later writer of A chunk 3
             //  sits behind an mbarrier that all 16 warps arrive on only after these reads)
           }
@@ -610,6 +651,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
 
           ho = {0.f, 0.f, 0.f, 0.f};
           float sigma_part = 0.f;
+          c.head_s = hr_s;
           for (int l = 0; l < net.n_layers; ++l) {
             const Layer& L = net.layers[l];
             HeadOut hl = {0.f, 0.f, 0.f, 0.f};
@@ -623,21 +665,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
             }
           }
           // ---- combine the four column-group partials of the heads: raw = (rgb_raw, sigma_raw)
-          if (c.cg != 0) xchg[c.cg] = make_float4(ho.h0, ho.h1, ho.h2, sigma_part);
+          xchg[kTileRows * c.cg] = make_float4(ho.h0, ho.h1, ho.h2, sigma_part);
           named_bar_sync(1, kEpiThreads);
           if (c.tid == 0) trace_ev(P, 39, c.layer_ctr);
-          if (c.cg == 0) {
-            const float4 p1 = xchg[1], p2 = xchg[2], p3 = xchg[3];
-            const float* hb = f32 + net.head_ofs + 3 * (kWidth / 2);
-            float4 o4;
-            o4.x = __fadd_rn(__fadd_rn(__fadd_rn(ho.h0, p1.x), __fadd_rn(p2.x, p3.x)), __ldg(hb + 0));
-            o4.y = __fadd_rn(__fadd_rn(__fadd_rn(ho.h1, p1.y), __fadd_rn(p2.y, p3.y)), __ldg(hb + 1));
-            o4.z = __fadd_rn(__fadd_rn(__fadd_rn(ho.h2, p1.z), __fadd_rn(p2.z, p3.z)), __ldg(hb + 2));
-            o4.w = __fadd_rn(__fadd_rn(__fadd_rn(sigma_part, p1.w), __fadd_rn(p2.w, p3.w)), __ldg(f32 + net.sigma_ofs + kWidth));
-            if (in_rows) raw4[R] = o4;
+          {
+            // the four threads of a row split the per-sample half of raw2outputs: thread cg owns component cg of
+            // (rgb_raw[3], sigma_raw) -- sums the four partials in a fixed order, adds the bias, applies the
+            // sigmoid (cg < 3) or the alpha formula (cg = 3) and writes its scalar of raw4[R]
+            const float* px = reinterpret_cast<const float*>(xchg) + c.cg;
+            const float q0 = px[0], q1 = px[4 * kTileRows], q2 = px[8 * kTileRows], q3 = px[12 * kTileRows];
+            const float bias = c.cg == 0 ? hb0 : (c.cg == 1 ? hb1 : (c.cg == 2 ? hb2 : sb));
+            const float val = __fadd_rn(__fadd_rn(__fadd_rn(q0, q1), __fadd_rn(q2, q3)), bias);
             if (valid) {
               float* tap = pass == 0 ? P.io.raw_coarse : P.io.raw_fine;
-              if (tap) *reinterpret_cast<float4*>(tap + (ri * n + s) * 4) = o4;
+              if (tap) tap[(ri * n + s) * 4 + c.cg] = val;
+            }
+            if (in_rows) {
+              float out;
+              if (c.cg < 3) out = sigmoidf_ref(val);
+              else {
+                const float* zz = pass == 0 ? zc + g * nc : zf + g * na;
+                const float dz = (s < n - 1) ? __fsub_rn(zz[s + 1], zz[s]) : 1e10f;
+                const float* nb = pass == 0 ? P.io.noise_coarse : P.io.noise_fine;
+                out = alpha_sample(val, dz, dnorm_s, (valid && nb) ? nb + ri * n + s : nullptr);
+                if (valid && last_pass && P.io.alpha_out) __stcs(P.io.alpha_out + ri * n + s, out);
+              }
+              reinterpret_cast<float*>(raw4 + R)[c.cg] = out;
             }
           }
           // the exchange slots are next written behind an mbarrier every warp arrives on after this point
@@ -645,32 +698,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
         named_bar_sync(1, kEpiThreads);   // raw4 of every tile of this pass is complete
         if (c.tid == 0) trace_ev(P, 40, c.layer_ctr);
 
-        // ---- per-ray: compositing (+ sampling after the coarse pass); one warp per ray
-        if (ew < G) {
-          const int g = ew;
-          const int64_t ri = ray0 + g;
-          const bool valid = ri < P.n_rays;
-          const float* r = ray + g * kRayFloats;
-          const float* zz = pass == 0 ? zc + g * nc : zf + g * na;
-          const float* nz = nullptr;
-          if (valid) { const float* nb = pass == 0 ? P.io.noise_coarse : P.io.noise_fine; if (nb) nz = nb + ri * n; }
-          float* rgb_dst = valid ? (pass == 0 ? P.io.rgb : P.io.rgb_fine) : nullptr;
-          if (rgb_dst) rgb_dst += ri * 3;
-          float* a_dst = (valid && last_pass && P.io.alpha_out) ? P.io.alpha_out + ri * n : nullptr;
-          float* w_dst = (valid && pass == 0 && P.io.weights_coarse) ? P.io.weights_coarse + ri * nc : nullptr;
-          composite_ray(raw4 + g * n, zz, (smpl && pass == 0) ? dnorm + g * nc : nullptr, r[6], n, nz, P.white_bkgd, rgb_dst,
-                        a_dst, w_dst, lane);
-          if (pass == 0 && P.run_fine) {
-            float* zfg = zf + g * na;
-            if (P.io.z_all_in && valid) {
-              for (int i = lane; i < na; i += 32) zfg[i] = P.io.z_all_in[ri * na + i];
-            } else {
-              float* cdf = scratch + g * (nc + nf);
-              float* zs = cdf + nc;
-              sample_ray(&raw4[g * nc].w, 4, zc + g * nc, nc, nf, P.io.u_fine, cdf, zs, zfg,
-                         (valid && P.io.z_new) ? P.io.z_new + ri * nf : nullptr, lane);
+        // ---- per-ray: compositing (+ sampling after the coarse pass) by a team of 16 / G warps per ray.
+        //      Scratch lives in the activation operand region, which is dead between the tiles of two passes.
+        {
+          const int W = kEpiWarps / G;
+          if (ew < G * W) {
+            const int g = ew / W;
+            const RayTeam tm = {32 * (ew - g * W) + lane, 32 * W, ew - g * W, W, lane, static_cast<uint32_t>(3 + g)};
+            const int64_t ri = ray0 + g;
+            const bool valid = ri < P.n_rays;
+            float* scr = reinterpret_cast<float*>(sm.base + kOffA) + g * kRayScratchFloats;
+            float* tf = scr, *tt = scr + kMaxFineRows, *cdfx = scr + 2 * kMaxFineRows, *pd = cdfx + kTileRows + 16, *zs = pd + kTileRows;
+            float* ts = zs + kMaxFineRows;
+            float* rgb_dst = valid ? (pass == 0 ? P.io.rgb : P.io.rgb_fine) : nullptr;
+            if (rgb_dst) rgb_dst += ri * 3;
+            float* w_dst = (valid && pass == 0 && P.io.weights_coarse) ? P.io.weights_coarse + ri * nc : nullptr;
+            composite_ray_activated(raw4 + g * n, n, P.white_bkgd, rgb_dst, w_dst, tf, tt, ts, tm);
+            if (pass == 0 && P.run_fine) {
+              float* zfg = zf + g * na;
+              if (P.io.z_all_in && valid) {
+                for (int i = tm.t; i < na; i += tm.T) zfg[i] = P.io.z_all_in[ri * na + i];
+                tm.sync();
+              } else {
+                sample_ray(&raw4[g * nc].w, 4, zc + g * nc, nc, nf, u_s, cdfx, pd, zs, zfg,
+                           (valid && P.io.z_new) ? P.io.z_new + ri * nf : nullptr, ts, tm);
+              }
+              if (valid && P.io.z_all) for (int i = tm.t; i < na; i += tm.T) P.io.z_all[ri * na + i] = zfg[i];
             }
-            if (valid && P.io.z_all) for (int i = lane; i < na; i += 32) P.io.z_all[ri * na + i] = zfg[i];
           }
         }
         named_bar_sync(1, kEpiThreads);
@@ -682,6 +736,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
   }
 
   tc_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0 && P.io.trace && blockIdx.x == 0) P.io.trace[1] = *reinterpret_cast<uint32_t*>(smem_raw + P.off_misc + kTraceCtrOfs);
   cluster_sync_all();          // neither CTA may exit (or free TMEM) while its peer can still address it
   if (warp == 1) tmem_dealloc2<512>(tmem_base);
 }
@@ -771,8 +827,10 @@ extern "C" int nrf_render(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coar
   P.o_raw = take(G * na * 4);
   P.o_zc = take(G * nc);
   P.o_zf = take(G * na);
-  P.o_dnorm = take(smpl ? G * nc : 0);
-  P.o_scratch = take(G * (nc + nf) > 16 ? G * (nc + nf) : 16);
+  P.o_u = take(nf > 0 ? nf : 4);
+  P.o_hw = take(smpl ? 3 * kWidth : 0);
+  P.o_hr = take(3 * (kWidth / 2));
+  P.o_hs = take(kWidth);
   P.n_stages = kMaxStages;
   while (P.n_stages > 2 && kOffRing + static_cast<uint32_t>(P.n_stages) * kSlotBytes + kBarBytes + f * 4 > kSmemLimit) --P.n_stages;   // big per-ray tables: shorter weight ring
   P.off_misc = kOffRing + static_cast<uint32_t>(P.n_stages) * kSlotBytes;

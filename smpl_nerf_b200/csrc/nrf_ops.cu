@@ -42,9 +42,13 @@ __global__ void raw2outputs_kernel(const float* __restrict__ raw, const float* _
                                    float* __restrict__ weights, float* __restrict__ alpha) {
   extern __shared__ __align__(16) float smem[];
   const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n4 = (n + 3) & ~3;
   float4* raw4 = reinterpret_cast<float4*>(smem) + static_cast<size_t>(w) * n;
-  float* zs = smem + static_cast<size_t>(wpb) * n * 4 + static_cast<size_t>(w) * 2 * n;
-  float* dn = zs + n;
+  float* tf = smem + static_cast<size_t>(wpb) * n * 4 + static_cast<size_t>(w) * (4 * n4 + kTeamScratch);   // 16-byte aligned scan scratch
+  float* tt = tf + n4;
+  float* ts = tf + 4 * n4;
+  float* zs = tt + n4;
+  float* dn = zs + n4;
   for (int64_t ray = blockIdx.x * static_cast<int64_t>(wpb) + w; ray < B; ray += static_cast<int64_t>(gridDim.x) * wpb) {
     for (int i = lane; i < n; i += 32) {
       raw4[i] = *reinterpret_cast<const float4*>(raw + (ray * n + i) * 4);
@@ -54,7 +58,7 @@ __global__ void raw2outputs_kernel(const float* __restrict__ raw, const float* _
     }
     __syncwarp();
     composite_ray(raw4, zs, dn, 0.f, n, noise ? noise + ray * n : nullptr, white, rgb + ray * 3, alpha + ray * n,
-                  weights + ray * n, lane);
+                  weights + ray * n, tf, tt, ts, lane);
     __syncwarp();
   }
 }
@@ -101,12 +105,15 @@ __global__ void fine_sampling_kernel(const float* __restrict__ origin, const flo
   extern __shared__ __align__(16) float smem[];
   const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int na = nc + nf;
-  float* base = smem + static_cast<size_t>(w) * (3 * nc + nf + na);
-  float* zc = base; float* wc = zc + nc; float* cdf = wc + nc; float* zs = cdf + nc; float* zf = zs + nf;
+  const int nc4 = (nc + 3) & ~3, nf4 = (nf + 3) & ~3;
+  float* base = smem + static_cast<size_t>(w) * (5 * nc4 + 2 * nf4 + 4 + kTeamScratch);
+  float* ts = base + 5 * nc4 + 2 * nf4 + 4;
+  const RayTeam tm = {lane, 32, 0, 1, lane, 0u};
+  float* cdfx = base; float* pd = cdfx + nc4 + 4; float* zc = pd + nc4; float* wc = zc + nc4; float* zs = wc + nc4; float* zf = zs + nf4;
   for (int64_t ray = blockIdx.x * static_cast<int64_t>(wpb) + w; ray < B; ray += static_cast<int64_t>(gridDim.x) * wpb) {
     for (int i = lane; i < nc; i += 32) { zc[i] = z[ray * nc + i]; wc[i] = weights[ray * nc + i]; }
     __syncwarp();
-    sample_ray(wc, 1, zc, nc, nf, u, cdf, zs, zf, nullptr, lane);
+    sample_ray(wc, 1, zc, nc, nf, u, cdfx, pd, zs, zf, nullptr, ts, tm);
     const float ox = origin[ray * 3], oy = origin[ray * 3 + 1], oz = origin[ray * 3 + 2];
     const float dx = dir[ray * 3], dy = dir[ray * 3 + 1], dz = dir[ray * 3 + 2];
     for (int i = lane; i < na; i += 32) {
@@ -259,7 +266,7 @@ extern "C" int nrf_raw2outputs(const float* raw, const float* z, const float* di
   if (B < 0 || n < 2 || n > 1024) { set_error("raw2outputs: unsupported shape B=%lld n=%d (n in 2..1024)", (long long)B, n); return NRF_E_INVALID; }
   if (B == 0) return NRF_OK;
   const int wpb = 4;
-  const size_t smem = static_cast<size_t>(wpb) * n * 6 * sizeof(float);
+  const size_t smem = static_cast<size_t>(wpb) * (4 * n + 4 * ((n + 3) & ~3) + kTeamScratch) * sizeof(float);
   const int grid = static_cast<int>(B / wpb + 1 > 148 * 8 ? 148 * 8 : B / wpb + 1);
   cudaError_t e = cudaFuncSetAttribute(raw2outputs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
@@ -289,7 +296,7 @@ extern "C" int nrf_fine_sampling(const float* origin, const float* dir, const fl
   if (B < 0 || n_coarse < 3 || n_coarse > 1024 || n_fine < 1 || n_fine > 4096) { set_error("fine_sampling: unsupported shape B=%lld n_coarse=%d n_fine=%d", (long long)B, n_coarse, n_fine); return NRF_E_INVALID; }
   if (B == 0) return NRF_OK;
   const int wpb = 4;
-  const size_t smem = static_cast<size_t>(wpb) * (4 * n_coarse + 2 * n_fine) * sizeof(float);
+  const size_t smem = static_cast<size_t>(wpb) * (5 * ((n_coarse + 3) & ~3) + 2 * ((n_fine + 3) & ~3) + 4 + kTeamScratch) * sizeof(float);
   const int grid = static_cast<int>(B / wpb + 1 > 148 * 8 ? 148 * 8 : B / wpb + 1);
   cudaError_t e = cudaFuncSetAttribute(fine_sampling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
