@@ -37,6 +37,8 @@ WORKLOADS = {
                  text='smpl_nerf_pipeline, 128x128, netdepth=8, 64 coarse + 128 fine (BASELINE configs[1])'),
     'cfg4': dict(kind='append', side=128, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4],
                  text='append_to_nerf_pipeline, 128x128, netdepth=8, 64+128 (BASELINE configs[3])'),
+    'paper': dict(kind='append_full', side=128, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4],
+                  text='append_smpl_params_pipeline (69 pose parameters, 1380 encoded features), 128x128, netdepth=8, 64+128'),
     'nerf': dict(kind='nerf', side=128, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4],
                  text='nerf_pipeline, 128x128, netdepth=8, 64+128'),
     'cfg1': dict(kind='nerf', side=128, n_coarse=32, n_fine=0, run_fine=0, n_layers=4, skips=[],
@@ -54,7 +56,7 @@ def build_models(w, seed=0):
     from smpl_nerf_b200.ops import PositionalEncoder
     torch.manual_seed(seed)
     pe, de, he = PositionalEncoder(10, False), PositionalEncoder(4, False), PositionalEncoder(10, False)
-    A = 2 * he.output_dim if w['kind'] == 'append' else 0
+    A = {'append': 2, 'append_full': 69}.get(w['kind'], 0) * he.output_dim
     coarse = RenderRayNet(w['n_layers'], 256, 3 * pe.output_dim, 3 * de.output_dim, A, list(w['skips']))
     fine = RenderRayNet(w['n_layers'], 256, 3 * pe.output_dim, 3 * de.output_dim, A, list(w['skips']))
     warp = WarpFieldNet(8, 256, 3 * pe.output_dim, 2 * he.output_dim) if w['kind'] == 'smpl' else None
@@ -154,6 +156,8 @@ def cpu_reference_rays_per_s(w, state, n_batches, batch, warmup=1, seed=0):
                 O.nerf_forward(c, f, pe, de, args, data)
             elif w['kind'] == 'append':
                 O.append_to_nerf_forward(c, f, pe, de, he, args, data)
+            elif w['kind'] == 'append_full':
+                O.append_smpl_params_forward(c, f, pe, de, he, args, data)
             else:
                 O.smpl_nerf_forward(c, f, wn, pe, de, he, args, data)
             if i >= warmup:
@@ -200,7 +204,7 @@ def run_ours(a, w, rank, world, local_rank):
     import torch.distributed as dist
     from smpl_nerf_b200 import dist as nd
     from smpl_nerf_b200 import engine
-    from smpl_nerf_b200.models import AppendToNerfPipeline, NerfPipeline, SmplNerfPipeline
+    from smpl_nerf_b200.models import AppendSmplParamsPipeline, AppendToNerfPipeline, NerfPipeline, SmplNerfPipeline
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -215,6 +219,8 @@ def run_ours(a, w, rank, world, local_rank):
         pipe = SmplNerfPipeline(coarse, fine, warp, pargs, pe, de, he)
     elif w['kind'] == 'append':
         pipe = AppendToNerfPipeline(coarse, fine, pargs, pe, de, he)
+    elif w['kind'] == 'append_full':
+        pipe = AppendSmplParamsPipeline(coarse, fine, pargs, pe, de, he)
     else:
         pipe = NerfPipeline(coarse, fine, pargs, pe, de)
     views_host = [[t.pin_memory() for t in v] for v in make_views(w, rank, N_VIEWS)]
@@ -305,7 +311,7 @@ def run_ours(a, w, rank, world, local_rank):
                    'parallelism': f'rays sharded over {world} GPU(s), weights replicated, one all-gather of rgb_fine per step'},
         'clocks': clocks,
         'e2e': {'value': n_total * a.steps / (ms_e2e / 1e3), 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-        'gpu_launches': a.steps * engine.launches_per_render(),
+        'gpu_launches': a.steps * engine.launches_per_render(w['kind'], bool(w['run_fine'])),
         'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
                      'traffic': traffic, 'flop_per_ray': fl_ray, 'kernel': 'nrf_fused_kernel', 'kernel_ms': ms_kernel,
                      'peak_source': peak_src,

@@ -4,6 +4,7 @@
  *
  *   models/nerf_pipeline.py:14-67, models/smpl_nerf_pipeline.py:16-100,
  *   models/append_to_nerf_pipeline.py:14-90          -> nrf_render()           (one fused kernel)
+ *   models/append_smpl_params_pipeline.py:14-91        -> nrf_ray_bias() + nrf_render()   (69-parameter pose hoisted per ray)
  *   models/render_ray_net.py:6-61 (weights, [out,in])  -> nrf_pack_raynet()      (fp32 -> packed fp16 hi/lo)
  *   models/warp_field_net.py:6-21                      -> nrf_pack_warpnet()
  *   utils.py:114-131  PositionalEncoder.encode         -> nrf_positional_encoding()
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NRF_ABI_VERSION 1
+#define NRF_ABI_VERSION 2
 
 enum {
   NRF_OK = 0,
@@ -60,6 +61,9 @@ typedef struct NrfRayNetDesc {
   int32_t pos_freqs, pos_identity;
   int32_t dir_freqs, dir_identity;
   int32_t per_sample_dirs;       /* 1: directions differ per sample (SmplNerfPipeline) */
+  int32_t ext_pose_bias;         /* 1: the contribution of the A additional inputs to the first and the skip layers
+                                    arrives precomputed per ray (nrf_ray_bias -> NrfRenderIO.ray_bias_*); lifts the
+                                    A <= 64 limit (AppendSmplParamsPipeline: A = 69 or 1380)                       */
 } NrfRayNetDesc;
 
 /* WarpFieldNet (models/warp_field_net.py:8-15): Linear(positions_dim + pose_dim -> width), ReLU,
@@ -98,6 +102,8 @@ typedef struct NrfRenderIO {
   const float* noise_fine;   /* optional [B, n_coarse+n_fine]                                */
   const float* z_all_in;     /* optional [B, n_coarse+n_fine]: use these fine depths instead of
                                 sampling (stage-wise parity tests, "teacher forcing")        */
+  const float* ray_bias_coarse; /* [B, nrf_raynet_ext_slots, 256] from nrf_ray_bias (ext_pose_bias nets)   */
+  const float* ray_bias_fine;   /* same for the fine net                                                    */
   /* outputs (fp32) */
   float* rgb;         /* [B,3] coarse colour                                                 */
   float* rgb_fine;    /* [B,3] (run_fine=0: may be NULL; the pipelines return rgb twice)     */
@@ -134,6 +140,15 @@ size_t nrf_warpnet_packed_bytes(const NrfWarpNetDesc* d);
 int nrf_pack_raynet(const NrfRayNetDesc* d, const float* const* params, int n_params, void* packed, void* stream);
 /* params: linear1.{weight,bias}, linear2.{weight,bias} */
 int nrf_pack_warpnet(const NrfWarpNetDesc* d, const float* const* params, int n_params, void* packed, void* stream);
+
+/* Per-ray bias vectors of the layers that read the A additional inputs (first layer and every skip layer):
+ *   out[b, e, :] = bias_e + W_e[:, pose columns] * feats[b, :]        (fp32 FMA, CUDA cores)
+ * feats: [B, A] (pose parameters, positionally encoded by the caller when the pipeline encodes them);
+ * params: as for nrf_pack_raynet (the ORIGINAL fp32 nn.Linear tensors are read in place); out: [B, n_ext, 256]
+ * with n_ext = nrf_raynet_ext_slots(d).  One launch; must run on the same stream before nrf_render. */
+int nrf_raynet_ext_slots(const NrfRayNetDesc* d);
+int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, int n_params, const float* feats, int64_t B,
+                 float* out, void* stream);
 
 /* The fused forward of the three pipelines for B rays.  packed_warp/warp may be NULL unless
  * kind == NRF_KIND_SMPL.  n_sms <= 0 means "all SMs of the current device". */

@@ -221,11 +221,13 @@ def nerf_forward(coarse: RayNet, fine: RayNet, pos_enc: Encoder, dir_enc: Encode
 
 
 def append_to_nerf_forward(coarse: RayNet, fine: RayNet, pos_enc: Encoder, dir_enc: Encoder,
-                           pose_enc: Encoder, args, data, noise_coarse=None, noise_fine=None):
-    """models/append_to_nerf_pipeline.py:14-90 (pose features FIRST in the MLP input)."""
+                           pose_enc: Encoder, args, data, noise_coarse=None, noise_fine=None, full_pose=False):
+    """models/append_to_nerf_pipeline.py:14-90 (pose features FIRST in the MLP input).
+    ``full_pose``: models/append_smpl_params_pipeline.py:14-91 -- the same forward with all 69 pose
+    parameters (encoded: 69 * 2L = 1380 features) instead of the two arm angles."""
     samples, origin, direction, z, goal_pose = data[0], data[1], data[2], data[3], data[4]
     B, n = samples.shape[0], samples.shape[1]
-    pose = _pose2(goal_pose)
+    pose = goal_pose if full_pose else _pose2(goal_pose)
     pose_feat = pose_enc.encode(pose) if args.human_pose_encoding else pose
     enc_x = pos_enc.encode(samples)
     dirs = direction[..., None, :].expand(B, n, 3)
@@ -240,7 +242,7 @@ def append_to_nerf_forward(coarse: RayNet, fine: RayNet, pos_enc: Encoder, dir_e
 
     raw = run(coarse, enc_x, n)
     rgb, w, alpha = composite(raw, z, dirs, white_background=args.white_background, noise=noise_coarse)
-    out = dict(rgb=rgb, raw_coarse=raw, weights_coarse=w, alpha_coarse=alpha, kind='append')
+    out = dict(rgb=rgb, raw_coarse=raw, weights_coarse=w, alpha_coarse=alpha, kind='append_full' if full_pose else 'append')
     if not args.run_fine:
         out.update(rgb_fine=rgb, samples_out=samples, alpha_out=alpha)
         return out
@@ -252,6 +254,12 @@ def append_to_nerf_forward(coarse: RayNet, fine: RayNet, pos_enc: Encoder, dir_e
     out.update(rgb_fine=rgb_f, samples_out=pts, alpha_out=alpha_f, z_new=z_new, z_all=z_all,
                raw_fine=raw_f, weights_fine=w_f)
     return out
+
+
+def append_smpl_params_forward(coarse, fine, pos_enc, dir_enc, pose_enc, args, data, noise_coarse=None, noise_fine=None):
+    """models/append_smpl_params_pipeline.py:14-91."""
+    return append_to_nerf_forward(coarse, fine, pos_enc, dir_enc, pose_enc, args, data, noise_coarse, noise_fine,
+                                  full_pose=True)
 
 
 def smpl_nerf_forward(coarse: RayNet, fine: RayNet, warp: WarpNet, pos_enc: Encoder, dir_enc: Encoder,
@@ -331,6 +339,8 @@ def build_nets(kind: str, seed: int, variant: str = 'default', *, n_layers=8, wi
     A = 0
     if kind == 'append':
         A = 2 * pose_enc.output_dim if pose_encoded else 2
+    if kind == 'append_full':
+        A = 69 * pose_enc.output_dim if pose_encoded else 69
     coarse = net_cls(n_layers, width, P, D, A, list(skips))
     fine = net_cls(n_layers, width, P, D, A, list(skips))
     warp = None

@@ -87,13 +87,14 @@ def load(use_compiled_searchsorted: bool = False):
     from models.nerf_pipeline import NerfPipeline                        # noqa: E402
     from models.smpl_nerf_pipeline import SmplNerfPipeline               # noqa: E402
     from models.append_to_nerf_pipeline import AppendToNerfPipeline      # noqa: E402
+    from models.append_smpl_params_pipeline import AppendSmplParamsPipeline  # noqa: E402
 
     ns = types.SimpleNamespace(
         utils=ref_utils, PositionalEncoder=ref_utils.PositionalEncoder,
         raw2outputs=ref_utils.raw2outputs, sample_pdf=ref_utils.sample_pdf,
         fine_sampling=ref_utils.fine_sampling, RenderRayNet=RenderRayNet, WarpFieldNet=WarpFieldNet,
         NerfPipeline=NerfPipeline, SmplNerfPipeline=SmplNerfPipeline,
-        AppendToNerfPipeline=AppendToNerfPipeline)
+        AppendToNerfPipeline=AppendToNerfPipeline, AppendSmplParamsPipeline=AppendSmplParamsPipeline)
     if not use_compiled_searchsorted:
         _cached = ns
     return ns
@@ -105,6 +106,8 @@ def build_pipeline(kind: str, coarse, fine, warp, pos_enc, dir_enc, pose_enc, ar
         return ref.NerfPipeline(coarse, fine, args, pos_enc, dir_enc)
     if kind == 'append':
         return ref.AppendToNerfPipeline(coarse, fine, args, pos_enc, dir_enc, pose_enc)
+    if kind == 'append_full':
+        return ref.AppendSmplParamsPipeline(coarse, fine, args, pos_enc, dir_enc, pose_enc)
     if kind == 'smpl':
         return ref.SmplNerfPipeline(coarse, fine, warp, args, pos_enc, dir_enc, pose_enc)
     raise ValueError(kind)

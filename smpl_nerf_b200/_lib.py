@@ -21,7 +21,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC', '-shared']
 
 NRF_MAX_SKIPS = 4
-KIND = {'nerf': 0, 'smpl': 1, 'append': 2}
+KIND = {'nerf': 0, 'smpl': 1, 'append': 2, 'append_full': 2}   # append_full = append + externally hoisted 69-parameter pose
 
 
 class RayNetDesc(C.Structure):
@@ -29,7 +29,8 @@ class RayNetDesc(C.Structure):
                 ('directions_dim', C.c_int32), ('additional_input_dim', C.c_int32),
                 ('use_directional_input', C.c_int32), ('n_skips', C.c_int32),
                 ('skips', C.c_int32 * NRF_MAX_SKIPS), ('pos_freqs', C.c_int32), ('pos_identity', C.c_int32),
-                ('dir_freqs', C.c_int32), ('dir_identity', C.c_int32), ('per_sample_dirs', C.c_int32)]
+                ('dir_freqs', C.c_int32), ('dir_identity', C.c_int32), ('per_sample_dirs', C.c_int32),
+                ('ext_pose_bias', C.c_int32)]
 
 
 class WarpNetDesc(C.Structure):
@@ -45,7 +46,7 @@ class PipelineDesc(C.Structure):
 
 
 _IO_IN = ['ray_samples', 'ray_origin', 'ray_dir', 'z_vals', 'goal_pose', 'u_fine', 'noise_coarse', 'noise_fine',
-          'z_all_in']
+          'z_all_in', 'ray_bias_coarse', 'ray_bias_fine']
 _IO_OUT = ['rgb', 'rgb_fine', 'samples_out', 'alpha_out', 'warp_out', 'warped_out', 'raw_coarse', 'raw_fine',
            'weights_coarse', 'z_new', 'z_all', 'status', 'trace']
 
@@ -56,6 +57,7 @@ class RenderIO(C.Structure):
 
 EXPORTS = ['nrf_last_error', 'nrf_abi_version', 'nrf_device_supported', 'nrf_raynet_packed_bytes',
            'nrf_warpnet_packed_bytes', 'nrf_pack_raynet', 'nrf_pack_warpnet', 'nrf_render', 'nrf_render_launches',
+           'nrf_raynet_ext_slots', 'nrf_ray_bias',
            'nrf_positional_encoding', 'nrf_raw2outputs', 'nrf_sample_pdf', 'nrf_fine_sampling', 'nrf_searchsorted',
            'nrf_selftest_umma', 'nrf_selftest_umma2', 'nrf_bench_umma', 'nrf_bench_umma2']
 
@@ -109,6 +111,8 @@ def lib() -> C.CDLL:
     L.nrf_render.argtypes = [C.POINTER(PipelineDesc), C.POINTER(RayNetDesc), C.c_void_p, C.POINTER(RayNetDesc),
                              C.c_void_p, C.POINTER(WarpNetDesc), C.c_void_p, C.POINTER(RenderIO), C.c_int64, C.c_int,
                              C.c_void_p]
+    L.nrf_raynet_ext_slots.argtypes = [C.POINTER(RayNetDesc)]
+    L.nrf_ray_bias.argtypes = [C.POINTER(RayNetDesc), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.nrf_positional_encoding.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.nrf_raw2outputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -122,7 +126,7 @@ def lib() -> C.CDLL:
     L.nrf_bench_umma2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     L.nrf_selftest_umma2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nrf_bench_umma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
-    if L.nrf_abi_version() != 1:
+    if L.nrf_abi_version() != 2:
         raise RuntimeError('libnrf_b200.so ABI version mismatch; rebuild')
     _lib = L
     return L

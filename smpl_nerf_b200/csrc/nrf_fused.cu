@@ -574,6 +574,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
         for (int l = 0; l < net.n_layers; ++l) {
           const Layer& L = net.layers[l];
           if (L.ray_slot < 0) continue;
+          if (L.ray_src == RAY_POSE_EXT) {      // computed per ray by nrf_ray_bias (bias included)
+            const float* src = pass == 0 ? P.io.ray_bias_coarse : P.io.ray_bias_fine;
+            for (int i = c.tid; i < G * kWidth; i += kEpiThreads) {
+              const int g = i >> 8, col = i & 255;
+              const int64_t ri = ray0 + g;
+              rb[(static_cast<int>(L.ray_slot) * G + g) * kWidth + col] =
+                  ri < P.n_rays ? __ldg(src + (ri * net.n_ext_slots + L.ext_idx) * kWidth + col) : 0.f;
+            }
+            continue;
+          }
           for (int i = c.tid; i < G * L.n_out; i += kEpiThreads) {
             const int g = i / L.n_out, col = i % L.n_out;
             float acc = f32[L.bias_ofs + col];
@@ -797,7 +807,12 @@ extern "C" int nrf_render(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coar
   P.pose_freqs = pipe->pose_freqs; P.pose_identity = pipe->pose_identity; P.pose_encoded = pipe->pose_encoded ? 1 : 0;
   P.pose_stride = pipe->pose_stride; P.pose_col0 = pipe->pose_col0; P.pose_col1 = pipe->pose_col1;
   P.pose_dim = 0;
-  if (pipe->kind != NRF_KIND_NERF) {
+  const bool ext_pose = pipe->kind == NRF_KIND_APPEND && P.net[0].n_ext_slots > 0;
+  if (ext_pose) {
+    if (pipe->run_fine && P.net[1].n_ext_slots != P.net[0].n_ext_slots) { set_error("coarse/fine nets disagree on ext_pose_bias"); return NRF_E_INVALID; }
+    if ((rc = check_ptr(io->ray_bias_coarse, "ray_bias_coarse")) != NRF_OK) return rc;
+    if (pipe->run_fine && (rc = check_ptr(io->ray_bias_fine, "ray_bias_fine")) != NRF_OK) return rc;
+  } else if (pipe->kind != NRF_KIND_NERF) {
     P.pose_dim = pipe->pose_encoded ? 2 * (2 * pipe->pose_freqs + (pipe->pose_identity ? 1 : 0)) : 2;
     const int want = smpl ? warp->pose_dim : coarse->additional_input_dim;
     if (P.pose_dim != want) { set_error("pose feature count %d does not match the net's pose input dim %d", P.pose_dim, want); return NRF_E_INVALID; }

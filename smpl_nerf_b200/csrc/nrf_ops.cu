@@ -245,6 +245,68 @@ static int grid_for(int64_t total, int block) {
   return static_cast<int>(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
 }
 
+
+// ------------------------------------------------------------------------------ per-ray pose bias (SGEMM)
+// out[b, e, n] = bias_e[n] + sum_k W_e[n, col0_e + k] * feats[b, k]      b < B, n < 256, k < A
+// for the n_ext layers of a RenderRayNet that read the A additional inputs (models/render_ray_net.py:43-49 with
+// the input built by models/append_smpl_params_pipeline.py:46-48: pose features FIRST).  The pose is constant
+// along a ray, so this replaces A of the K columns of two layers for every SAMPLE by one small GEMM per RAY.
+// Classic fp32 register-tiled SGEMM: 128 rays x 64 outputs per CTA, K in steps of 16 through shared memory.
+struct RayBiasJob { const float* w; const float* bias; int32_t ld, col0; };
+struct RayBiasTable { int32_t n; RayBiasJob j[NRF_MAX_SKIPS + 1]; };
+
+constexpr int kRbM = 128, kRbN = 64, kRbK = 16;
+
+__global__ void __launch_bounds__(256) ray_bias_kernel(const __grid_constant__ RayBiasTable t, const float* __restrict__ feats, int64_t B,
+                                                       int A, float* __restrict__ out) {
+  __shared__ __align__(16) float As[kRbK][kRbM + 4];
+  __shared__ __align__(16) float Bs[kRbK][kRbN + 4];
+  const RayBiasJob& job = t.j[blockIdx.z];
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kRbM;
+  const int n0 = blockIdx.y * kRbN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < A; k0 += kRbK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {               // 128 x 16 feature tile, 16 consecutive threads read 16 consecutive floats
+      const int idx = threadIdx.x + 256 * i, r = idx >> 4, k = idx & 15;
+      const int64_t b = b0 + r;
+      As[k][r] = (b < B && k0 + k < A) ? feats[b * A + k0 + k] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {               // 64 x 16 weight tile
+      const int idx = threadIdx.x + 256 * i, n = idx >> 4, k = idx & 15;
+      Bs[k][n] = (k0 + k < A) ? job.w[static_cast<size_t>(n0 + n) * job.ld + job.col0 + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kRbK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][8 * ty]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][8 * ty + 4]);
+      const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][4 * tx]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float4 bias = *reinterpret_cast<const float4*>(job.bias + n0 + 4 * tx);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t b = b0 + 8 * ty + i;
+    if (b >= B) continue;
+    float4 o = make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w);
+    *reinterpret_cast<float4*>(out + (b * t.n + blockIdx.z) * kWidth + n0 + 4 * tx) = o;
+  }
+}
+
 }  // namespace nrf
 
 using namespace nrf;
@@ -335,4 +397,42 @@ extern "C" int nrf_selftest_umma(const float* a, const float* b, float* d, void*
   selftest_umma_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(a, b, d);
   e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "selftest_umma_kernel launch");
+}
+
+extern "C" int nrf_raynet_ext_slots(const NrfRayNetDesc* d) {
+  NetPlan p;
+  return plan_raynet(d, &p) == NRF_OK ? p.n_ext_slots : -1;
+}
+
+extern "C" int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, int n_params, const float* feats, int64_t B,
+                            float* out, void* stream) {
+  static thread_local NetPlan plan;
+  int rc = plan_raynet(d, &plan);
+  if (rc != NRF_OK) return rc;
+  if (plan.n_ext_slots < 1) { set_error("ray_bias: the net has no external pose-bias layers (ext_pose_bias = 0 or additional_input_dim = 0)"); return NRF_E_INVALID; }
+  const int nl = d->n_layers, A = d->additional_input_dim, P = d->positions_dim;
+  if (!params || n_params != 2 * (nl + 5)) { set_error("ray_bias: RenderRayNet expects %d parameter tensors, got %d", 2 * (nl + 5), n_params); return NRF_E_INVALID; }
+  if (!feats || !out) { set_error("ray_bias: NULL argument"); return NRF_E_INVALID; }
+  if (B < 0) { set_error("ray_bias: B < 0"); return NRF_E_INVALID; }
+  if (B == 0) return NRF_OK;
+  if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) { set_error("ray_bias: out must be 16-byte aligned"); return NRF_E_INVALID; }
+  RayBiasTable t;
+  t.n = plan.n_ext_slots;
+  for (int li = 0; li < plan.n_layers; ++li) {
+    const Layer& L = plan.layers[li];
+    if (L.ray_src != RAY_POSE_EXT) continue;
+    RayBiasJob& j = t.j[L.ext_idx];
+    // layer 0 = positions_pose_input: columns [pose(A) | xyz(P)]; layer li >= 1 = positional_net[li-1] with a skip:
+    // columns [activations(256) | pose(A) | xyz(P)]   (models/render_ray_net.py:22-31,43-49)
+    const int pidx = li == 0 ? 0 : 2 * li;
+    if (!params[pidx] || !params[pidx + 1]) { set_error("ray_bias: parameter %d is NULL", pidx); return NRF_E_INVALID; }
+    if ((reinterpret_cast<uintptr_t>(params[pidx + 1]) & 15u) != 0) { set_error("ray_bias: bias tensors must be 16-byte aligned"); return NRF_E_INVALID; }
+    j.w = params[pidx]; j.bias = params[pidx + 1];
+    j.ld = li == 0 ? A + P : kWidth + A + P;
+    j.col0 = li == 0 ? 0 : kWidth;
+  }
+  const dim3 grid(static_cast<unsigned>((B + kRbM - 1) / kRbM), kWidth / kRbN, static_cast<unsigned>(t.n));
+  ray_bias_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, feats, B, A, out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "ray_bias_kernel launch");
 }

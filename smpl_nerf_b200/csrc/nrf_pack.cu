@@ -51,7 +51,8 @@ int plan_raynet(const NrfRayNetDesc* d, NetPlan* p) {
   if (d->width != kWidth) { set_error("RenderRayNet width %d unsupported (this build: %d)", d->width, kWidth); return NRF_E_INVALID; }
   if (d->positions_dim != P || P > kChunkK || P <= 0) { set_error("positions_dim %d does not match encoder (3*(id+2L)=%d, max %d)", d->positions_dim, P, kChunkK); return NRF_E_INVALID; }
   if (d->use_directional_input && (d->directions_dim != D || D > kChunkK || D <= 0)) { set_error("directions_dim %d does not match encoder (%d, max %d)", d->directions_dim, D, kChunkK); return NRF_E_INVALID; }
-  if (A < 0 || A > kMaxRayFeat) { set_error("additional_input_dim %d unsupported (max %d)", A, kMaxRayFeat); return NRF_E_INVALID; }
+  const bool ext = d->ext_pose_bias != 0 && A > 0;
+  if (A < 0 || (!ext && A > kMaxRayFeat) || A > 65535) { set_error("additional_input_dim %d unsupported (max %d in-kernel; set ext_pose_bias for more)", A, kMaxRayFeat); return NRF_E_INVALID; }
   if (d->n_layers < 2 || d->n_layers + 3 > kMaxLayers) { set_error("n_layers %d unsupported (2..%d)", d->n_layers, kMaxLayers - 3); return NRF_E_INVALID; }
   if (d->n_skips < 0 || d->n_skips > NRF_MAX_SKIPS) { set_error("n_skips %d unsupported", d->n_skips); return NRF_E_INVALID; }
   if (d->per_sample_dirs && A > 0) { set_error("per-sample directions with additional inputs is not a reference pipeline"); return NRF_E_INVALID; }
@@ -60,7 +61,7 @@ int plan_raynet(const NrfRayNetDesc* d, NetPlan* p) {
   p->in_freqs = d->pos_freqs; p->in_identity = d->pos_identity;
   p->dir_freqs = d->dir_freqs; p->dir_identity = d->dir_identity;
   uint32_t f = 0;   // float cursor in the fp32 section
-  int slots = 0, n = 0;
+  int slots = 0, n = 0, n_ext = 0;
   auto add = [&](int n_out, int epi, int flags) -> Layer& {
     Layer& L = p->layers[n++];
     L.n_out = static_cast<uint16_t>(n_out); L.epi = static_cast<uint8_t>(epi); L.flags = static_cast<uint8_t>(flags);
@@ -69,7 +70,9 @@ int plan_raynet(const NrfRayNetDesc* d, NetPlan* p) {
     return L;
   };
   auto add_ray = [&](Layer& L, int src, int k) {
-    L.ray_src = static_cast<uint8_t>(src); L.ray_k = static_cast<uint16_t>(k); L.ray_slot = static_cast<int8_t>(slots++);
+    L.ray_slot = static_cast<int8_t>(slots++);
+    if (src == RAY_POSE && ext) { L.ray_src = RAY_POSE_EXT; L.ray_k = 0; L.ext_idx = static_cast<uint8_t>(n_ext++); return; }
+    L.ray_src = static_cast<uint8_t>(src); L.ray_k = static_cast<uint16_t>(k);
     L.rayw_ofs = f; f = align4(f + k * L.n_out);
   };
   // first layer: xyz encoding from aux (+ pose features as a per-ray bias)
@@ -87,7 +90,7 @@ int plan_raynet(const NrfRayNetDesc* d, NetPlan* p) {
     else if (d->use_directional_input) add_ray(L, RAY_DIR, D); }
   { Layer& L = add(kWidth / 2, EPI_RGB, 0); L.ksrc[L.nk++] = 0; L.ksrc[L.nk++] = 1; }
   if (slots > kMaxRaySlots) { set_error("too many per-ray bias layers (%d > %d): at most one skip layer when additional_input_dim > 0", slots, kMaxRaySlots); return NRF_E_INVALID; }
-  p->n_layers = n; p->n_ray_slots = slots;
+  p->n_layers = n; p->n_ray_slots = slots; p->n_ext_slots = n_ext;
   p->sigma_ofs = f; f = align4(f + kWidth + 1);
   p->head_ofs = f;  f = align4(f + 3 * (kWidth / 2) + 3);
   finish_plan(p, f);
@@ -231,7 +234,7 @@ extern "C" int nrf_pack_raynet(const NrfRayNetDesc* d, const float* const* param
       else { c.aux = 0; c.col0 = act0 + kChunkK * L.ksrc[kc]; c.freqs = 0; c.identity = 0; }
     }
     copy(b, 1, L.n_out, L.n_out, 0, 0, L.bias_ofs);
-    if (L.ray_src != RAY_NONE) copy(W, L.n_out, L.ray_k, ld, ray0, 1, L.rayw_ofs);
+    if (L.ray_src == RAY_POSE || L.ray_src == RAY_DIR) copy(W, L.n_out, L.ray_k, ld, ray0, 1, L.rayw_ofs);
   }
   copy(params[2 * nl + 2], 1, kWidth, kWidth, 0, 0, plan.sigma_ofs);
   copy(params[2 * nl + 3], 1, 1, 1, 0, 0, plan.sigma_ofs + kWidth);

@@ -45,7 +45,7 @@ enum LayerFlags : uint8_t {
   LF_WRITE_DIRPE = 2,  // epilogue also writes the per-sample direction encoding into aux
   LF_AUX_WAIT = 4,     // the MMA issuer must wait for fresh aux contents before this layer
 };
-enum RaySrc : uint8_t { RAY_NONE = 0, RAY_POSE = 1, RAY_DIR = 2 };
+enum RaySrc : uint8_t { RAY_NONE = 0, RAY_POSE = 1, RAY_DIR = 2, RAY_POSE_EXT = 3 };   // EXT: bias vector precomputed by nrf_ray_bias
 
 struct Layer {
   uint32_t stream_ofs;  // byte offset of the layer's first stage inside the weight stream
@@ -59,12 +59,13 @@ struct Layer {
   uint8_t ksrc[kMaxK];  // 0..3 activation chunk, kSrcAux
   uint8_t epi;          // EpiKind
   uint8_t flags;        // LayerFlags
-  uint8_t pad_;
+  uint8_t ext_idx;      // RAY_POSE_EXT: index of this layer's vector inside a ray's [n_ext][256] block
 };
 
 struct NetPlan {
   int32_t n_layers;
   int32_t n_ray_slots;
+  int32_t n_ext_slots;    // number of RAY_POSE_EXT layers
   uint32_t stream_bytes;  // weight stream size (all hi+lo stages)
   uint32_t f32_ofs;       // byte offset of the fp32 section in the blob
   uint32_t total_bytes;

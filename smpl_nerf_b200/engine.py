@@ -26,7 +26,7 @@ def _enc_cfg(enc):
     return int(enc.number_frequencies), 1 if enc.include_identity else 0
 
 
-def raynet_desc(net, pos_enc, dir_enc, per_sample_dirs: bool) -> RayNetDesc:
+def raynet_desc(net, pos_enc, dir_enc, per_sample_dirs: bool, ext_pose_bias: bool = False) -> RayNetDesc:
     """Read the RenderRayNet hyper-parameters off the module (attribute names: render_ray_net.py:11-17)."""
     d = RayNetDesc()
     d.n_layers, d.width = int(net.n_layers), int(net.width)
@@ -43,6 +43,7 @@ def raynet_desc(net, pos_enc, dir_enc, per_sample_dirs: bool) -> RayNetDesc:
     d.pos_freqs, d.pos_identity = _enc_cfg(pos_enc)
     d.dir_freqs, d.dir_identity = _enc_cfg(dir_enc)
     d.per_sample_dirs = 1 if per_sample_dirs else 0
+    d.ext_pose_bias = 1 if ext_pose_bias else 0
     return d
 
 
@@ -151,14 +152,15 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
         goal = _f32(data[4], 'goal_pose', device)
         if goal.dim() != 2 or goal.shape[0] != B or goal.shape[1] <= max(POSE_COLS):
             raise ValueError(f'goal_pose must be [B, >= {max(POSE_COLS) + 1}], got {tuple(goal.shape)}')
+    full_pose = kind == 'append_full'     # AppendSmplParamsPipeline: all pose parameters, hoisted per ray by nrf_ray_bias
 
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
-        dc = raynet_desc(model_coarse, pos_enc, dir_enc, smpl)
+        dc = raynet_desc(model_coarse, pos_enc, dir_enc, smpl, full_pose)
         pc = packed(model_coarse, dc, device, stream)
         df, pf = None, None
         if run_fine:
-            df = raynet_desc(model_fine, pos_enc, dir_enc, smpl)
+            df = raynet_desc(model_fine, pos_enc, dir_enc, smpl, full_pose)
             pf = packed(model_fine, df, device, stream)
         pipe = PipelineDesc()
         pipe.kind = KIND[kind]
@@ -166,7 +168,31 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
         pipe.white_background = 1 if args.white_background else 0
         pipe.precision = int(precision)
         dw, pw = None, None
-        if kind != 'nerf':
+        ray_bias = []
+        if full_pose:
+            # pose features exactly as models/append_smpl_params_pipeline.py:30-37 builds them, then one SGEMM per net
+            encoded = bool(args.human_pose_encoding)
+            A = int(goal.shape[1]) * (pose_enc.output_dim if encoded else 1)
+            if A != dc.additional_input_dim:
+                raise ValueError(f'pose feature count {A} does not match the net\'s additional_input_dim {dc.additional_input_dim}')
+            feats = goal
+            if encoded:
+                feats = torch.empty(B, A, dtype=torch.float32, device=device)
+                check(L.nrf_positional_encoding(goal.data_ptr(), B, int(goal.shape[1]), *_enc_cfg(pose_enc), feats.data_ptr(),
+                                                stream), 'nrf_positional_encoding(goal_pose)')
+            for net, desc in ((model_coarse, dc),) + (((model_fine, df),) if run_fine else ()):
+                n_ext = L.nrf_raynet_ext_slots(C.byref(desc))
+                if n_ext < 1:
+                    check(-1, 'plan net')
+                rb = torch.empty(B, n_ext, 256, dtype=torch.float32, device=device)
+                ps = _params(net, device)
+                arr = (C.c_void_p * len(ps))(*[p.data_ptr() for p in ps])
+                if B > 0:
+                    check(L.nrf_ray_bias(C.byref(desc), arr, len(ps), feats.data_ptr(), B, rb.data_ptr(), stream), 'nrf_ray_bias')
+                ray_bias.append(rb)
+                ray_bias.append(ps)          # keep (possibly re-laid-out) parameter tensors alive until the launch
+            ray_bias.append(feats)
+        elif kind != 'nerf':
             pipe.pose_freqs, pipe.pose_identity = _enc_cfg(pose_enc)
             pipe.pose_encoded = 1 if args.human_pose_encoding else 0
             pipe.pose_stride, pipe.pose_col0, pipe.pose_col1 = int(goal.shape[1]), POSE_COLS[0], POSE_COLS[1]
@@ -189,6 +215,11 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
         if goal is not None:
             io.goal_pose = goal.data_ptr()
         keep = [samples, origin, direction, z, goal]
+        if full_pose:
+            io.ray_bias_coarse = ray_bias[0].data_ptr()
+            if run_fine:
+                io.ray_bias_fine = ray_bias[2].data_ptr()
+            keep += [t for t in ray_bias if isinstance(t, torch.Tensor)]
         if run_fine:
             u = _u_fine(nf, device)
             io.u_fine = u.data_ptr()
@@ -247,5 +278,9 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
     return out
 
 
-def launches_per_render() -> int:
-    return int(_lib.lib().nrf_render_launches())
+def launches_per_render(kind: str = 'nerf', run_fine: bool = True, pose_encoded: bool = True) -> int:
+    """Kernels of this library launched by one render() call with warm weight caches."""
+    n = int(_lib.lib().nrf_render_launches())
+    if kind == 'append_full':      # pose encoding + one per-ray bias SGEMM per net
+        n += (1 if pose_encoded else 0) + (2 if run_fine else 1)
+    return n

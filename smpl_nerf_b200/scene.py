@@ -146,7 +146,7 @@ def make_rays(h: int, w: int, n_coarse: int = 64, *, phi: float = 10.0, theta: f
 def data_list(rays: Dict[str, torch.Tensor], kind: str, sel=slice(None), device=None):
     """Order the tensors like the reference datasets' ``__getitem__`` tuples do."""
     keys = ['ray_samples', 'ray_translation', 'ray_direction', 'z_vals']
-    if kind in ('smpl', 'append'):
+    if kind in ('smpl', 'append', 'append_full'):
         keys.append('goal_pose')
     keys.append('rgb')
     out = [rays[k][sel].contiguous() for k in keys]

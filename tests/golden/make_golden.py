@@ -34,6 +34,9 @@ CASES = [
     ('smpl_default', 'smpl', 'default', 106, 12, {}),
     ('nerf_cfg1', 'nerf', 'dense', 107, 20, dict(n_layers=4, skips=(), n_coarse=32, run_fine=0)),
     ('smpl_coarse_rawpose', 'smpl', 'dense', 108, 12, dict(pose_encoded=False, run_fine=0)),
+    # AppendSmplParamsPipeline: all 69 pose parameters, per-ray random poses
+    ('append_full_dense', 'append_full', 'dense', 109, 12, {}),
+    ('append_full_rawpose', 'append_full', 'dense', 110, 12, dict(pose_encoded=False)),
 ]
 
 
@@ -43,12 +46,17 @@ def run_oracle(kind, nets, args, data):
         return O.nerf_forward(c, f, pe, de, args, data)
     if kind == 'append':
         return O.append_to_nerf_forward(c, f, pe, de, he, args, data)
+    if kind == 'append_full':
+        return O.append_smpl_params_forward(c, f, pe, de, he, args, data)
     return O.smpl_nerf_forward(c, f, w, pe, de, he, args, data)
 
 
 def main():
     ref = R.load()
+    only = set(sys.argv[1:])
     for name, kind, variant, seed, B, kw in CASES:
+        if only and name not in only:
+            continue
         kw = dict(kw)
         n_coarse = kw.pop('n_coarse', 64)
         run_fine = kw.pop('run_fine', 1)
@@ -58,6 +66,9 @@ def main():
         # spread the B rays over the image so that they hit different depths/directions
         sel = torch.linspace(0, 24 * 24 - 1, B).long()
         data = scene.data_list(rays, kind, sel)
+        if kind == 'append_full':      # every ray gets its own full 69-parameter pose (|angle| < 1 rad)
+            g = torch.Generator().manual_seed(seed)
+            data[4] = (torch.rand(data[4].shape, generator=g) * 2 - 1).float()
         args = O.make_args(run_fine=run_fine, human_pose_encoding=1 if pose_encoded else 0)
         theirs = O.build_nets(kind, seed, variant, net_cls=ref.RenderRayNet, warp_cls=ref.WarpFieldNet,
                               enc_cls=ref.PositionalEncoder, **build)

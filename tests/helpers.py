@@ -41,6 +41,8 @@ def run_oracle(kind, nets, args, data, **kw):
         return O.nerf_forward(c, f, pe, de, args, data, **kw)
     if kind == 'append':
         return O.append_to_nerf_forward(c, f, pe, de, he, args, data, **kw)
+    if kind == 'append_full':
+        return O.append_smpl_params_forward(c, f, pe, de, he, args, data, **kw)
     return O.smpl_nerf_forward(c, f, w, pe, de, he, args, data, **kw)
 
 

@@ -9,9 +9,9 @@ from tests import helpers as H
 
 def test_fixtures_present():
     names = H.fixtures()
-    assert len(names) >= 8
+    assert len(names) >= 10
     kinds = {H.load_fixture(n)['kind'] for n in names}
-    assert kinds == {'nerf', 'append', 'smpl'}
+    assert kinds == {'nerf', 'append', 'append_full', 'smpl'}
 
 
 @pytest.mark.parametrize('name', H.fixtures())

@@ -14,7 +14,7 @@ import torch
 
 from oracle import nerf_oracle as O
 from smpl_nerf_b200 import _lib, engine, scene
-from smpl_nerf_b200.models import AppendToNerfPipeline, NerfPipeline, SmplNerfPipeline
+from smpl_nerf_b200.models import AppendSmplParamsPipeline, AppendToNerfPipeline, NerfPipeline, SmplNerfPipeline
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -27,6 +27,8 @@ def make_pipeline(kind, nets, args):
         return NerfPipeline(c, f, args, pe, de)
     if kind == 'append':
         return AppendToNerfPipeline(c, f, args, pe, de, he)
+    if kind == 'append_full':
+        return AppendSmplParamsPipeline(c, f, args, pe, de, he)
     return SmplNerfPipeline(c, f, w, args, pe, de, he)
 
 
@@ -115,7 +117,7 @@ def test_fixture_stagewise(name):
     assert torch.equal(za, both)
 
 
-@pytest.mark.parametrize('kind', ['nerf', 'append', 'smpl'])
+@pytest.mark.parametrize('kind', ['nerf', 'append', 'append_full', 'smpl'])
 def test_pipeline_api_tuple(kind):
     """The drop-in classes return the reference's tuple (order, shapes, device, dtype)."""
     nets = O.build_nets(kind, 5, 'dense')

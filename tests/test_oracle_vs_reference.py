@@ -10,7 +10,7 @@ from oracle import nerf_oracle as O
 from oracle import ref_import as R
 from smpl_nerf_b200 import scene
 
-KINDS = ['nerf', 'append', 'smpl']
+KINDS = ['nerf', 'append', 'append_full', 'smpl']
 
 
 def _run_oracle(kind, nets, args, data, **kw):
@@ -19,6 +19,8 @@ def _run_oracle(kind, nets, args, data, **kw):
         return O.nerf_forward(c, f, pe, de, args, data, **kw)
     if kind == 'append':
         return O.append_to_nerf_forward(c, f, pe, de, he, args, data, **kw)
+    if kind == 'append_full':
+        return O.append_smpl_params_forward(c, f, pe, de, he, args, data, **kw)
     return O.smpl_nerf_forward(c, f, w, pe, de, he, args, data, **kw)
 
 
@@ -41,7 +43,7 @@ def test_pipeline_bit_exact(reference, kind, variant):
             assert a.shape == b.shape and torch.equal(a, b)
 
 
-@pytest.mark.parametrize('kind', ['append', 'smpl'])
+@pytest.mark.parametrize('kind', ['append', 'append_full', 'smpl'])
 def test_raw_pose_variant_bit_exact(reference, kind):
     """human_pose_encoding=0 (raw 2-dim pose); for smpl only run_fine=0 is well-formed in the reference."""
     rays = scene.make_rays(8, 8, 64, seed=5)
