@@ -11,6 +11,7 @@
  *   utils.py:134-191  raw2outputs                      -> nrf_raw2outputs()
  *   utils.py:194-228  sample_pdf                       -> nrf_sample_pdf()
  *   utils.py:231-264  fine_sampling                    -> nrf_fine_sampling()
+ *   utils.py:26-54 get_rays + datasets/transforms.py:82-89 CoarseSampling -> nrf_generate_rays()
  *   torchsearchsorted/src/cuda/searchsorted_cuda_wrapper.cpp:18-20
  *       searchsorted_cuda_wrapper(a, v, res, side_left) -> nrf_searchsorted()
  *
@@ -172,6 +173,15 @@ int nrf_sample_pdf(const float* bins, const float* weights, const float* u, int6
 /* utils.py:231-264: origin[B,3], dir[B,3], z[B,nc], weights[B,nc], u[n_fine] -> z_all[B,nc+nf], pts[B,nc+nf,3] */
 int nrf_fine_sampling(const float* origin, const float* dir, const float* z, const float* weights, const float* u,
                       int64_t B, int32_t n_coarse, int32_t n_fine, float* z_all, float* pts, void* stream);
+/* utils.py:26-54 get_rays + datasets/transforms.py:82-89 CoarseSampling + :13-19 ToTensor for one H x W view, on the
+ * device: float64 arithmetic in numpy's operation order, rounded once to fp32.  camera_transform_host: HOST 4x4
+ * row-major camera-to-world matrix; lower/span: DEVICE [n_coarse] float64 bin tables (lower edge, upper - lower;
+ * built once on the host from near/far exactly like transforms.py:82-86); jitter: DEVICE [H*W] float64, the one
+ * np.random.rand() scalar per ray (drawn by the caller so the host RNG stream is the reference's).
+ * Outputs (fp32): ray_samples[H*W, n_coarse, 3], ray_origin[H*W, 3], ray_dir[H*W, 3], z_vals[H*W, n_coarse]. */
+int nrf_generate_rays(int32_t H, int32_t W, double focal, const double* camera_transform_host, const double* lower,
+                      const double* span, const double* jitter, int32_t n_coarse, float* ray_samples, float* ray_origin,
+                      float* ray_dir, float* z_vals, void* stream);
 /* torchsearchsorted: a[rows_a, na], v[rows_v, nv] (rows broadcast when one side has 1 row) -> res int64 */
 int nrf_searchsorted(const float* a, int64_t rows_a, int64_t na, const float* v, int64_t rows_v, int64_t nv,
                      int64_t* res, int32_t side_left, void* stream);

@@ -307,6 +307,46 @@ __global__ void __launch_bounds__(256) ray_bias_kernel(const __grid_constant__ R
   }
 }
 
+
+// ------------------------------------------------------------------------------ ray generation + coarse sampling
+// utils.py:26-54 get_rays + datasets/transforms.py:82-89 CoarseSampling + :13-19 ToTensor, for one view:
+//   local = ((i - W/2) / focal, -(j - H/2) / focal, -1)       i, j float32 pixel indices, the rest float64
+//   dir   = sum_c local[c] * R[k][c]   (products, then (p0 + p1) + p2: numpy's elementwise form, no FMA)
+//   z     = lower + (upper - lower) * jitter[ray]               one jitter scalar per ray
+//   pts   = origin + dir * z                                     float64, rounded ONCE to fp32 on store
+// One thread per (ray, sample); HBM-bound (12 B/sample written).
+struct CamParams { double r[9]; double t[3]; double focal; int32_t H, W, n; };
+
+__global__ void generate_rays_kernel(const __grid_constant__ CamParams cam, const double* __restrict__ lower, const double* __restrict__ span,
+                                     const double* __restrict__ jitter, float* __restrict__ samples, float* __restrict__ origin,
+                                     float* __restrict__ dir, float* __restrict__ z_vals) {
+  const int64_t total = static_cast<int64_t>(cam.H) * cam.W * cam.n;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t ray = idx / cam.n;
+    const int s = static_cast<int>(idx - ray * cam.n);
+    const int j = static_cast<int>(ray / cam.W), i = static_cast<int>(ray - static_cast<int64_t>(j) * cam.W);
+    const float fi = __fsub_rn(static_cast<float>(i), static_cast<float>(cam.W * .5));
+    const float fj = __fsub_rn(static_cast<float>(j), static_cast<float>(cam.H * .5));
+    const double l0 = __ddiv_rn(static_cast<double>(fi), cam.focal);
+    const double l1 = __ddiv_rn(static_cast<double>(-fj), cam.focal);
+    const double l2 = -1.0;
+    double d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      d[k] = __dadd_rn(__dadd_rn(__dmul_rn(l0, cam.r[3 * k]), __dmul_rn(l1, cam.r[3 * k + 1])), __dmul_rn(l2, cam.r[3 * k + 2]));
+    const double z = __dadd_rn(lower[s], __dmul_rn(span[s], jitter[ray]));
+    float* p = samples + idx * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = static_cast<float>(__dadd_rn(cam.t[k], __dmul_rn(d[k], z)));
+    z_vals[idx] = static_cast<float>(z);
+    if (s == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { origin[ray * 3 + k] = static_cast<float>(cam.t[k]); dir[ray * 3 + k] = static_cast<float>(d[k]); }
+    }
+  }
+}
+
 }  // namespace nrf
 
 using namespace nrf;
@@ -435,4 +475,22 @@ extern "C" int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, 
   ray_bias_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, feats, B, A, out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "ray_bias_kernel launch");
+}
+
+extern "C" int nrf_generate_rays(int32_t H, int32_t W, double focal, const double* camera_transform_host, const double* lower,
+                                 const double* span, const double* jitter, int32_t n_coarse, float* ray_samples, float* ray_origin,
+                                 float* ray_dir, float* z_vals, void* stream) {
+  if (!camera_transform_host || !lower || !span || !jitter || !ray_samples || !ray_origin || !ray_dir || !z_vals) { set_error("generate_rays: NULL argument"); return NRF_E_INVALID; }
+  if (H < 1 || W < 1 || n_coarse < 1 || !(focal > 0.0)) { set_error("generate_rays: bad shape H=%d W=%d n_coarse=%d focal=%g", H, W, n_coarse, focal); return NRF_E_INVALID; }
+  CamParams cam;
+  for (int k = 0; k < 3; ++k) {
+    for (int c = 0; c < 3; ++c) cam.r[3 * k + c] = camera_transform_host[4 * k + c];
+    cam.t[k] = camera_transform_host[4 * k + 3];
+  }
+  cam.focal = focal; cam.H = H; cam.W = W; cam.n = n_coarse;
+  const int64_t total = static_cast<int64_t>(H) * W * n_coarse;
+  generate_rays_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cam, lower, span, jitter, ray_samples, ray_origin,
+                                                                                           ray_dir, z_vals);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "generate_rays_kernel launch");
 }

@@ -50,21 +50,28 @@ def camera_rays(h: int, w: int, pose: np.ndarray, camera_angle_x: float = CAMERA
     focal = .5 * w / np.tan(.5 * camera_angle_x)
     i, j = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32), indexing='xy')
     local = np.stack([(i - w * .5) / focal, -(j - h * .5) / focal, -np.ones_like(i)], -1)
-    direction = local.reshape(-1, 3).astype(np.float64) @ pose[:3, :3].T
+    direction = np.sum(local.reshape(-1, 3)[..., np.newaxis, :] * pose[:3, :3], -1)     # utils.py:52 (elementwise products, then the sum)
     origin = np.broadcast_to(pose[:3, 3], direction.shape)
     return origin, direction
 
 
-def coarse_depths(n_rays: int, n_samples: int, rng: np.random.RandomState,
-                  near: float = NEAR, far: float = FAR) -> np.ndarray:
-    """[n_rays, n_samples] stratified depths, linear in disparity, one jitter scalar per ray."""
+def coarse_bins(n_samples: int, near: float = NEAR, far: float = FAR):
+    """(lower, upper) edges of the stratified bins, linear in disparity (datasets/transforms.py:82-86)."""
     t = np.linspace(0., 1., n_samples)
     z = 1. / (1. / near * (1. - t) + 1. / far * t)
     mids = .5 * (z[1:] + z[:-1])
     upper = np.concatenate([mids, z[-1:]])
     lower = np.concatenate([z[:1], mids])
-    jitter = rng.rand(n_rays)[:, None]
-    return lower[None, :] + (upper - lower)[None, :] * jitter
+    return lower, upper
+
+
+def coarse_depths(n_rays: int, n_samples: int, rng: np.random.RandomState,
+                  near: float = NEAR, far: float = FAR, jitter: Optional[np.ndarray] = None) -> np.ndarray:
+    """[n_rays, n_samples] stratified depths, linear in disparity, one jitter scalar per ray."""
+    lower, upper = coarse_bins(n_samples, near, far)
+    if jitter is None:
+        jitter = rng.rand(n_rays)
+    return lower[None, :] + (upper - lower)[None, :] * jitter[:, None]
 
 
 def _capsule_hit(o, d, a, b, radius):

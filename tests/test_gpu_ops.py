@@ -89,3 +89,46 @@ def test_searchsorted_ties_and_out_argument():
         ops.searchsorted(a, v, out=torch.empty(1, 6, dtype=torch.int32, device=DEV))
     with pytest.raises(AssertionError):
         ops.searchsorted(a[0], v)
+
+
+@pytest.mark.parametrize('hw,nc', [((32, 32), 64), ((17, 23), 32)])
+def test_generate_rays_is_bit_identical_to_the_host_builder(hw, nc):
+    """nrf_generate_rays (float64 on the device) against scene.make_rays (numpy float64, pinned to the reference's
+    get_rays / CoarseSampling by tests/test_scene_vs_reference.py): every output bit-equal."""
+    import numpy as np
+    from smpl_nerf_b200 import rays, scene
+    h, w = hw
+    want = scene.make_rays(h, w, nc, phi=7.0, theta=123.0, seed=11)
+    jitter = np.random.RandomState(11).rand(h * w)
+    got = rays.generate_view(h, w, scene.sphere_pose(7.0, 123.0), n_coarse=nc, jitter=jitter)
+    torch.cuda.synchronize()
+    for g, k in zip(got, ['ray_samples', 'ray_translation', 'ray_direction', 'z_vals']):
+        assert g.dtype == torch.float32 and g.shape == want[k].shape
+        assert torch.equal(g.cpu(), want[k]), k
+
+
+def test_render_driver_matches_batched_pipeline_calls():
+    """render.render_frames (device ray generation, one call per frame) == the pipeline fed host-built rays."""
+    import numpy as np
+    from oracle import nerf_oracle as O
+    from smpl_nerf_b200 import render, scene
+    from smpl_nerf_b200.models import SmplNerfPipeline
+    from tests import helpers as H
+    nets = O.build_nets('smpl', 3, 'dense')
+    args = O.make_args()
+    (c, f, wn, pe, de, he), _ = H.to_cuda(nets, [])
+    pipe = SmplNerfPipeline(c, f, wn, args, pe, de, he)
+    h = w = 12
+    cams = [scene.sphere_pose(10.0, 30.0), scene.sphere_pose(-5.0, 200.0)]
+    goal = np.zeros(69, np.float32); goal[38] = goal[41] = np.deg2rad(25.0)
+    frames = render.render_frames(pipe, cams, [goal, goal], h, w, seed=5)
+    assert frames.shape == (2, h, w, 3)
+    rng = np.random.RandomState(5)
+    for k, (phi, theta) in enumerate([(10.0, 30.0), (-5.0, 200.0)]):
+        rays_h = scene.make_rays(h, w, 64, phi=phi, theta=theta, arm_angle_deg=25.0, rng=rng)
+        data = [t.cuda() for t in scene.data_list(rays_h, 'smpl')]
+        with torch.no_grad():
+            want = pipe(data)[1]
+        assert torch.equal(frames[k].reshape(-1, 3), want)
+    psnr = render.psnr_per_frame(frames, frames.clone() + 0.1)
+    assert all(abs(p - 20.0) < 1e-3 for p in psnr)
