@@ -60,3 +60,17 @@ def alpha_mask_well_conditioned(sigma_ref, thresh=1e-3):
     m = torch.ones_like(sigma_ref, dtype=torch.bool)
     m[..., -1] = sigma_ref[..., -1].abs() > thresh
     return m
+
+
+def load_trained():
+    """The briefly trained vanilla-NeRF checkpoint + held-out view minted by tests/golden/make_trained.py."""
+    ck = torch.load(os.path.join(GOLDEN_DIR, 'trained_nerf_d4.ckpt'), weights_only=False)
+    c, f, _, pe, de, he = O.build_nets('nerf', 0, 'default', n_layers=ck['n_layers'], skips=tuple(ck['skips']))
+    c.load_state_dict({k: v.float() for k, v in ck['coarse'].items()})
+    f.load_state_dict({k: v.float() for k, v in ck['fine'].items()})
+    args = O.make_args(number_fine_samples=ck['n_fine'])
+    return ck, (c, f, None, pe, de, he), args
+
+
+def psnr(img, ref):
+    return float(-10.0 * torch.log10(torch.mean((img.double().cpu() - ref.double().cpu()) ** 2)))

@@ -60,3 +60,13 @@ def test_analytic_kats():
     zs = O.inverse_cdf(bins, torch.ones(B, n - 2), 128)
     u = torch.linspace(0, 1, 128)
     assert torch.allclose(zs, (bins[:, :1] + u * (bins[:, -1:] - bins[:, :1])), atol=2e-6)
+
+
+def test_oracle_reproduces_the_trained_checkpoint_render():
+    """Held-out view of the briefly trained checkpoint: the oracle equals the reference render bit for bit."""
+    ck, nets, args = H.load_trained()
+    with torch.no_grad():
+        out = H.run_oracle('nerf', nets, args, ck['data'])
+    assert torch.equal(out['rgb'], ck['reference_rgb']) and torch.equal(out['rgb_fine'], ck['reference_rgb_fine'])
+    assert torch.equal(out['alpha_out'], ck['reference_alpha'])
+    assert abs(H.psnr(out['rgb_fine'], ck['data'][-1]) - ck['reference_psnr']) < 1e-9

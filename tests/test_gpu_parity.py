@@ -316,3 +316,23 @@ def test_rejects_bad_inputs():
     wide = O.RayNet(8, 128, 60, 24, 0, [4]).to(DEV)
     with pytest.raises(ValueError, match='width'):
         NerfPipeline(wide, wide, O.make_args(), nets[3], nets[4])(gdata)
+
+
+def test_trained_checkpoint_psnr():
+    """north_star: "PSNR within 0.1 dB of reference on held-out views" -- a briefly trained vanilla NeRF
+    (tests/golden/make_trained.py), held-out 32x32 view, against the reference's own render of it."""
+    ck, nets, args = H.load_trained()
+    gnets, gdata = H.to_cuda(nets, ck['data'])
+    c, f, _, pe, de, he = gnets
+    pipe = NerfPipeline(c, f, args, pe, de)
+    with torch.no_grad():
+        rgb, rgb_fine, pts, alpha = pipe(gdata)
+    torch.cuda.synchronize()
+    gt = ck['data'][-1]
+    assert maxdiff(rgb, ck['reference_rgb']) <= H.TOL_RGB
+    assert maxdiff(rgb_fine, ck['reference_rgb_fine']) <= H.TOL_RGB
+    ours, theirs = H.psnr(rgb_fine, gt), ck['reference_psnr']
+    assert abs(ours - theirs) <= 0.1, (ours, theirs)
+    assert H.psnr(rgb_fine, ck['reference_rgb_fine']) >= 60.0        # render-vs-render
+    err = (alpha.cpu() - ck['reference_alpha']).abs()
+    assert float(torch.quantile(err.flatten(), 0.99)) <= H.TOL_ALPHA
