@@ -43,8 +43,9 @@ WORKLOADS = {
                  text='nerf_pipeline, 128x128, netdepth=8, 64+128'),
     'cfg1': dict(kind='nerf', side=128, n_coarse=32, n_fine=0, run_fine=0, n_layers=4, skips=[],
                  text='vanilla nerf_pipeline, 128x128, netdepth=4, 32 coarse, run_fine=0 (BASELINE configs[0])'),
-    'cfg5': dict(kind='smpl', side=512, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4],
-                 text='smpl_nerf_pipeline, 512x512 frame (BASELINE configs[4])'),
+    # configs[4]: ONE 512x512 frame per step, its rays sharded over the ranks (strong scaling), one all-gather of the tiles
+    'cfg5': dict(kind='smpl', side=512, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4], strong=True,
+                 text='smpl_nerf_pipeline, 512x512 full-frame render, rays sharded over the GPUs (BASELINE configs[4])'),
 }
 N_VIEWS = 8          # rotating distinct input views so that consecutive steps never reuse inputs
 
@@ -82,13 +83,21 @@ def flops_per_ray(w, coarse, fine, warp):
     return 2.0 * total
 
 
-def make_views(w, rank, n_views):
+def make_views(w, rank, n_views, world=1):
+    """Weak-scaling workloads: every rank gets its own views.  Strong-scaling ones (w['strong']): every rank builds
+    the SAME views and keeps its contiguous shard of the rays (smpl_nerf_b200.dist.shard_data)."""
+    from smpl_nerf_b200 import dist as nd
     from smpl_nerf_b200 import scene
+    strong = bool(w.get('strong'))
+    vrank = 0 if strong else rank
     views = []
     for v in range(n_views):
-        rays = scene.make_rays(w['side'], w['side'], w['n_coarse'], phi=5.0 + 3 * v, theta=(37.0 * (v + 1) + 11 * rank) % 360,
-                               arm_angle_deg=(60.0 / 9) * ((v + rank) % 10), seed=1000 * rank + v)
-        views.append(scene.data_list(rays, w['kind']))
+        rays = scene.make_rays(w['side'], w['side'], w['n_coarse'], phi=5.0 + 3 * v, theta=(37.0 * (v + 1) + 11 * vrank) % 360,
+                               arm_angle_deg=(60.0 / 9) * ((v + vrank) % 10), seed=1000 * vrank + v)
+        data = scene.data_list(rays, w['kind'])
+        if strong:
+            data = [t.contiguous() for t in nd.shard_data(data, rank, world)]
+        views.append(data)
     return views
 
 
@@ -223,10 +232,12 @@ def run_ours(a, w, rank, world, local_rank):
         pipe = AppendSmplParamsPipeline(coarse, fine, pargs, pe, de, he)
     else:
         pipe = NerfPipeline(coarse, fine, pargs, pe, de)
-    views_host = [[t.pin_memory() for t in v] for v in make_views(w, rank, N_VIEWS)]
+    strong = bool(w.get('strong'))
+    views_host = [[t.pin_memory() for t in v] for v in make_views(w, rank, N_VIEWS if not strong else 4, world)]
     views = [[t.to(dev) for t in v] for v in views_host]
     rays = int(views[0][0].shape[0])
-    n_total = rays * world
+    n_total = w['side'] * w['side'] if strong else rays * world
+    n_views = len(views)
     stream = torch.cuda.current_stream(dev)
     precision = 1 if a.precision == 'fast' else 0
 
@@ -244,7 +255,7 @@ def run_ours(a, w, rank, world, local_rank):
 
     with torch.no_grad():
         for i in range(a.warmup):
-            step(i, views[i % N_VIEWS])
+            step(i, views[i % n_views])
         # ---------------- device-resident throughput: exactly K steps
         barrier()
         sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -253,7 +264,7 @@ def run_ours(a, w, rank, world, local_rank):
         e0.record(stream)
         for i in range(a.steps):
             ev[i][0].record(stream)
-            img = step(i, views[(a.warmup + i) % N_VIEWS])
+            img = step(i, views[(a.warmup + i) % n_views])
             ev[i][1].record(stream)
         e1.record(stream)
         barrier()
@@ -263,13 +274,13 @@ def run_ours(a, w, rank, world, local_rank):
         # ---------------- end to end through the public API: host inputs, H2D + D2H inside the timed region
         host_img = torch.empty(n_total if world > 1 else rays, 3).pin_memory()
         for i in range(min(2, a.warmup)):
-            data = [t.to(dev, non_blocking=True) for t in views_host[i % N_VIEWS]]
+            data = [t.to(dev, non_blocking=True) for t in views_host[i % n_views]]
             host_img.copy_(step(i, data), non_blocking=True)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
         for i in range(a.steps):
-            data = [t.to(dev, non_blocking=True) for t in views_host[(a.warmup + i) % N_VIEWS]]
+            data = [t.to(dev, non_blocking=True) for t in views_host[(a.warmup + i) % n_views]]
             host_img.copy_(step(i, data), non_blocking=True)
         f1.record(stream)
         barrier()
@@ -301,12 +312,12 @@ def run_ours(a, w, rank, world, local_rank):
         pass
     line = {
         'metric': 'rays/sec', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
-        'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
         'dtype': 'f16x3-split (fp32-equivalent), fp32 accumulate' if not precision else 'f16 (1 pass), fp32 accumulate',
         'data': 'synthetic',
         'config': {'workload': w['text'], 'rays_per_step_per_gpu': rays, 'precision_mode': a.precision,
                    'weights': 'random init (seed 0, sigma head x20, bias +1)', 'algebraic_fold': False,
-                   'l2_policy': f'rotating over {N_VIEWS} distinct views; each step reads {h2d / 1e6:.1f} MB of inputs and '
+                   'l2_policy': f'rotating over {n_views} distinct views; each step reads {h2d / 1e6:.1f} MB of inputs and '
                                 f'writes >120 MB of outputs (> 126 MB L2 together)',
                    'parallelism': f'rays sharded over {world} GPU(s), weights replicated, one all-gather of rgb_fine per step'},
         'clocks': clocks,
