@@ -133,7 +133,7 @@ struct CopyJob { const float* src; int32_t rows, cols, ld, col0, transpose; uint
 struct CopyTable { int32_t n; CopyJob j[4 * kMaxLayers + 8]; };
 
 __device__ __forceinline__ int dev_enc_ref_col(int f, int freqs, int identity) {
-  if (f < 6 * freqs) { int p = f >> 1, s = f & 1, k = p / 3, comp = p % 3; return (identity ? 3 : 0) + k * 6 + s * 3 + comp; }
+  if (f < 6 * freqs) { int p = f >> 1, s = f & 1, comp = p / freqs, k = p % freqs; return (identity ? 3 : 0) + k * 6 + s * 3 + comp; }
   int c = f - 6 * freqs;
   return (identity && c < 3) ? c : -1;
 }

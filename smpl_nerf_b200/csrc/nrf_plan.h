@@ -84,13 +84,14 @@ void set_error(const char* fmt, ...);
 int cuda_fail(int err, const char* what);
 
 // Number of aux features (<= 64) an encoder produces for a 3-vector, and the reference column of
-// aux feature f (or -1 for padding).  Engine order: [sin,cos] pairs interleaved per (freq, comp),
-// then the identity components; reference order (utils.py:119-131): identity first, then for each
-// frequency sin(x,y,z) followed by cos(x,y,z).
+// aux feature f (or -1 for padding).  Engine order: [sin,cos] pairs, COMPONENT-major (pair p = comp * L + k, so
+// that a thread's 8 consecutive pairs are runs of consecutive frequencies of one component and can use the
+// double-angle recurrence), then the identity components; reference order (utils.py:119-131): identity first,
+// then for each frequency sin(x,y,z) followed by cos(x,y,z).
 __host__ __device__ inline int enc_dim(int freqs, int identity) { return 3 * (2 * freqs + (identity ? 1 : 0)); }
 __host__ __device__ inline int enc_ref_col(int f, int freqs, int identity) {
   if (f < 6 * freqs) {
-    int p = f >> 1, s = f & 1, k = p / 3, comp = p % 3;
+    int p = f >> 1, s = f & 1, comp = p / freqs, k = p % freqs;
     return (identity ? 3 : 0) + k * 6 + s * 3 + comp;
   }
   int c = f - 6 * freqs;
