@@ -29,6 +29,7 @@
 // Two 256-column TMEM accumulators ping-pong between consecutive layers, and activations are handed
 // to the MMA issuer per 64-feature K-chunk, so layer l+1's MMAs start while layer l's epilogue is
 // still draining.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -61,6 +62,7 @@ constexpr uint32_t kBarBytes = 256;                // barriers + TMEM base slot
 static_assert(8 * BAR_COUNT + 8 <= kBarBytes, "barrier area too small");
 
 struct RenderParams {
+  CUtensorMap tmap[3];   // weight streams of blob[0..2] as [rows, 128 B] uint8 tensors, box = 64 rows (8 KB)
   NetPlan net[2];
   NetPlan warp;
   const uint8_t* blob[3];
@@ -191,32 +193,22 @@ __device__ __forceinline__ void trace_ev(const RenderParams& P, int ev, uint32_t
 // ---------------------------------------------------------------------------------- roles
 struct RingState { uint32_t stage = 0, phase = 0; __device__ void advance(uint32_t n) { if (++stage == n) { stage = 0; phase ^= 1; } } };
 
-__device__ __forceinline__ void producer_layer(const Smem& sm, const uint8_t* blob, const Layer& L, RingState& rs, bool fast) {
+__device__ __forceinline__ void producer_layer(const Smem& sm, const CUtensorMap* tmap, const Layer& L, RingState& rs, bool fast) {
   const uint32_t half_bytes = L.n_out * 64u;       // this CTA's [n_out/2 x 64] fp16 half of a stage
-  const uint8_t* src = blob + L.stream_ofs + sm.rank * half_bytes;
+  const int half_rows = L.n_out >> 1;              // 128-byte rows of that half
+  int row = static_cast<int>(L.stream_ofs >> 7) + static_cast<int>(sm.rank) * half_rows;
   for (int kc = 0; kc < L.nk; ++kc) {
-    for (int is_lo = 0; is_lo < 2; ++is_lo, src += 2u * half_bytes) {
+    for (int is_lo = 0; is_lo < 2; ++is_lo, row += 2 * half_rows) {
       if (fast && is_lo) continue;                 // lo stages are not streamed in fast mode
       mbar_wait(sm.bar(BAR_EMPTY + rs.stage), rs.phase ^ 1);
-      mbar_arrive_expect_tx(sm.bar(BAR_FULL + rs.stage), half_bytes);
-      bulk_g2s(smem_u32(sm.base + kOffRing) + rs.stage * kSlotBytes, src, half_bytes, sm.bar(BAR_FULL + rs.stage));
+      // both CTAs' halves are credited to the ISSUER's full barrier (its own producer announces the total)
+      const uint32_t full0 = mapa_shared(sm.bar(BAR_FULL + rs.stage), 0);
+      if (sm.rank == 0) mbar_arrive_expect_tx(sm.bar(BAR_FULL + rs.stage), 2u * half_bytes);
+      const uint32_t dst = smem_u32(sm.base + kOffRing) + rs.stage * kSlotBytes;
+      for (int r0 = 0; r0 < half_rows; r0 += 64) tma2_load_2d(dst + static_cast<uint32_t>(r0) * 128u, tmap, 0, row + r0, full0);
       rs.advance(sm.n_stages);
     }
   }
-}
-
-// Odd CTA: once this CTA's half of a stage has landed, arrive on the issuer's full barrier (which
-// also counts the issuer's own producer + its bytes), so the issuer waits on ONE barrier per stage.
-// (A cp.async.bulk naming the peer's mbarrier directly hangs; a release.cluster arrive costs ~1000
-// cycles per stage -- both measured with nrf_bench_umma2.)
-__device__ __forceinline__ void relay_layer(const Smem& sm, const Layer& L, RingState& rs, bool fast) {
-  for (int kc = 0; kc < L.nk; ++kc)
-    for (int is_lo = 0; is_lo < 2; ++is_lo) {
-      if (fast && is_lo) continue;
-      mbar_wait(sm.bar(BAR_FULL + rs.stage), rs.phase);
-      mbar_arrive_cluster_relaxed_warp(sm.bar(BAR_FULL + rs.stage), 0);
-      rs.advance(sm.n_stages);
-    }
 }
 
 struct MmaState { RingState rs; uint32_t a_phase = 0; uint32_t layer_ctr = 0; };
@@ -428,7 +420,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
   if (threadIdx.x == 0) {
     *reinterpret_cast<uint32_t*>(smem_raw + P.off_misc + kTraceCtrOfs) = 0u;
     // issuer CTA: a stage is full when its own producer (arrive + bytes) and the peer's relay have arrived
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(sm.bar(BAR_FULL + s), sm.rank == 0 ? 2 : 1); mbar_init(sm.bar(BAR_EMPTY + s), 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(sm.bar(BAR_FULL + s), 1); mbar_init(sm.bar(BAR_EMPTY + s), 1); }
     mbar_init(sm.bar(BAR_ACC + 0), 1); mbar_init(sm.bar(BAR_ACC + 1), 1);
     for (int j = 0; j < 5; ++j) mbar_init(sm.bar(BAR_AREADY + j), 2);   // one arrival per CTA of the pair
     fence_mbar_init();
@@ -449,8 +441,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
         for (int pass = 0; pass < n_pass; ++pass) {
           const int tiles = pass == 0 ? 1 : P.tiles_f;
           for (int t = 0; t < tiles; ++t) {
-            if (smpl) producer_layer(sm, P.blob[2], P.warp.layers[0], rs, fast);
-            for (int l = 0; l < P.net[pass].n_layers; ++l) producer_layer(sm, P.blob[pass], P.net[pass].layers[l], rs, fast);
+            if (smpl) producer_layer(sm, &P.tmap[2], P.warp.layers[0], rs, fast);
+            for (int l = 0; l < P.net[pass].n_layers; ++l) producer_layer(sm, &P.tmap[pass], P.net[pass].layers[l], rs, fast);
           }
         }
     }
@@ -466,9 +458,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
             if (sm.rank == 0) {
               if (smpl) mma_layer(sm, P, tmem_base, P.warp.layers[0], st, fast);
               for (int l = 0; l < P.net[pass].n_layers; ++l) mma_layer(sm, P, tmem_base, P.net[pass].layers[l], st, fast);
-            } else {
-              if (smpl) relay_layer(sm, P.warp.layers[0], st.rs, fast);
-              for (int l = 0; l < P.net[pass].n_layers; ++l) relay_layer(sm, P.net[pass].layers[l], st.rs, fast);
             }
           }
         }
@@ -761,6 +750,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
 }
 
 // ---------------------------------------------------------------------------------- host launcher
+// The weight stream of a packed net as a 2-D uint8 tensor [rows, 128 B] (rows = 128-byte swizzle rows of the
+// pre-swizzled stages), box = 64 rows x 128 B, no swizzle/interleave: a plain strided copy of 8 KB per request.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_stream_map(CUtensorMap* map, const void* blob, uint32_t stream_bytes) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return NRF_E_CUDA; }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  const cuuint64_t dims[2] = {128, stream_bytes / 128u};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {128, 64};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(blob), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return NRF_E_CUDA; }
+  return NRF_OK;
+}
+
 static int check_ptr(const void* p, const char* name) {
   if (!p) { set_error("%s is NULL", name); return NRF_E_INVALID; }
   return NRF_OK;
@@ -801,6 +814,11 @@ extern "C" int nrf_render(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coar
     if (pipe->run_fine && !pipe->pose_encoded) { set_error("smpl pipeline with run_fine=1 requires human_pose_encoding=1 (the reference feeds the warp net encoded inputs in the fine pass, smpl_nerf_pipeline.py:71-77)"); return NRF_E_INVALID; }
   } else if (coarse->per_sample_dirs) { set_error("per_sample_dirs=1 is only valid for the smpl pipeline"); return NRF_E_INVALID; }
   for (int i = 0; i < 3; ++i) if (P.blob[i] && (reinterpret_cast<uintptr_t>(P.blob[i]) & 1023u)) { set_error("packed buffers must be 1024-byte aligned"); return NRF_E_INVALID; }
+  for (int i = 0; i < 3; ++i) {
+    if (!P.blob[i]) continue;
+    const NetPlan& np = i < 2 ? P.net[i] : P.warp;
+    if ((rc = encode_stream_map(&P.tmap[i], P.blob[i], np.stream_bytes)) != NRF_OK) return rc;
+  }
 
   const int nc = pipe->n_coarse, nf = pipe->run_fine ? pipe->n_fine : 0;
   if (nc < 16 || nc > kTileRows) { set_error("n_coarse %d unsupported (16..%d)", nc, kTileRows); return NRF_E_INVALID; }

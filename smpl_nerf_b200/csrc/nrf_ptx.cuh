@@ -180,6 +180,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// 2-D tensor TMA issued by either CTA of a pair: the tile lands in the ISSUING CTA's shared memory, its bytes are
+// credited to the mbarrier at cluster address `bar_cluster` -- with .cta_group::2 that may be the peer CTA's
+// barrier, so both halves of a weight stage complete ONE barrier in the MMA-issuing CTA without a relay hop.
+// (The 1-D cp.async.bulk has no such form: naming the peer's mbarrier there hangs.)  SASS: UTMALDG.
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst_smem, const void* tmap, int32_t c0, int32_t c1, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar_cluster)
+               : "memory");
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem) {  // one whole warp in EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(kCols) : "memory");
