@@ -17,11 +17,11 @@
 //
 // CTA = 18 warps, warp-specialised:
 //   warp 0      weight producer: streams this CTA's half of the pre-swizzled fp16 hi/lo weight stages
-//               L2 -> SMEM ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx)
+//               L2 -> SMEM ring with 2-D tensor TMA (cp.async.bulk.tensor.2d.cta_group::2); both CTAs' halves
+//               credit their bytes to the ONE full-barrier of the issuing CTA (no relay hop)
 //   warp 1      even CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 (M=256, N=n_out,
 //               fp16 x fp16 -> fp32 in both CTAs' TMEM); fp32-level accuracy comes from the split
-//               x*w ~= xh*wh + xl*wh + xh*wl (3 passes).  odd CTA: relay -- forwards "my half of the
-//               stage has landed" to the issuer's full barrier
+//               x*w ~= xh*wh + xl*wh + xh*wl (3 passes).  odd CTA: idle
 //   warps 2..17 "epilogue" warps (thread = one sample row x 16 columns of every 64-feature chunk):
 //               positional encoding -> SMEM operand tiles, TMEM -> bias/ReLU/hi-lo split -> next
 //               layer's A operand (in place), sigma / rgb / warp heads as fp32 dot products, then per
