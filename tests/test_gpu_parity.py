@@ -336,3 +336,62 @@ def test_trained_checkpoint_psnr():
     assert H.psnr(rgb_fine, ck['reference_rgb_fine']) >= 60.0        # render-vs-render
     err = (alpha.cpu() - ck['reference_alpha']).abs()
     assert float(torch.quantile(err.flatten(), 0.99)) <= H.TOL_ALPHA
+
+
+SWEEP = [
+    # kind, n_layers, skips, L_pos, id_pos, L_dir, id_dir, use_dir, n_coarse, n_fine
+    ('nerf', 8, (), 10, False, 4, False, 1, 64, 128),            # args default skips=[] (config_parser.py:21)
+    ('nerf', 6, (1, 3), 10, False, 4, False, 1, 64, 128),        # two skip connections
+    ('nerf', 8, (4,), 10, False, 4, False, 0, 64, 128),          # use_directional_input = 0
+    ('nerf', 5, (2,), 6, True, 2, True, 1, 64, 64),              # identity encodings (39 / 15 features)
+    ('nerf', 8, (4,), 10, False, 4, False, 1, 128, 64),          # one ray per tile
+    ('nerf', 4, (), 10, False, 4, False, 1, 16, 16),             # eight rays per tile
+    ('append', 8, (4,), 10, False, 4, False, 1, 48, 80),         # 2 rays per tile, 32 idle rows
+    ('smpl', 8, (4,), 10, False, 4, False, 1, 32, 32),
+    ('smpl', 3, (0,), 10, False, 4, False, 1, 64, 128),          # skip right after the first layer
+]
+
+
+@pytest.mark.parametrize('cfg', SWEEP, ids=lambda c: '-'.join(str(x) for x in c))
+def test_architecture_and_sample_count_sweep(cfg):
+    """Net shapes / encoders / sample counts beyond the shipped configs, stage-wise against the oracle."""
+    kind, n_layers, skips, L_pos, id_pos, L_dir, id_dir, use_dir, nc, nf = cfg
+    torch.manual_seed(1234 + n_layers + nc)
+    pe, de, he = O.Encoder(L_pos, id_pos), O.Encoder(L_dir, id_dir), O.Encoder(10, False)
+    P, D = 3 * pe.output_dim, 3 * de.output_dim
+    A = 2 * he.output_dim if kind == 'append' else 0
+    c = O.RayNet(n_layers, 256, P, D, A, list(skips), use_dir)
+    f = O.RayNet(n_layers, 256, P, D, A, list(skips), use_dir)
+    w = O.WarpNet(8, 256, P, 2 * he.output_dim) if kind == 'smpl' else None
+    with torch.no_grad():
+        for net in (c, f):
+            net.sigma_out_layer.weight.mul_(20.)
+            net.sigma_out_layer.bias.add_(1.)
+    for net in (c, f, w):
+        if net is not None:
+            net.eval()
+    nets = (c, f, w, pe, de, he)
+    args = O.make_args(number_fine_samples=nf)
+    rays = scene.make_rays(7, 9, nc, seed=20 + nc)
+    data = scene.data_list(rays, kind)
+    with torch.no_grad():
+        want = H.run_oracle(kind, nets, args, data)
+    gnets, gdata = H.to_cuda(nets, data)
+    gc, gf, gw = gnets[:3]
+    got = engine.render(kind, gc, gf, gw, args, pe, de, he, gdata, taps=True, z_all_in=want['z_all'].to(DEV))
+    torch.cuda.synchronize()
+    assert int(got['status'].item()) == 0
+    assert maxdiff(got['raw_coarse'][..., 3], want['raw_coarse'][..., 3]) <= H.TOL_SIGMA
+    assert maxdiff(got['raw_coarse'][..., :3], want['raw_coarse'][..., :3]) <= H.TOL_RGB
+    assert maxdiff(got['rgb'], want['rgb']) <= H.TOL_RGB
+    assert maxdiff(got['raw_fine'][..., 3], want['raw_fine'][..., 3]) <= H.TOL_SIGMA
+    assert maxdiff(got['rgb_fine'], want['rgb_fine']) <= H.TOL_RGB
+    assert torch.equal(got['samples_out'].cpu(), want['samples_out'])
+    # and the in-kernel sampler end to end
+    free = engine.render(kind, gc, gf, gw, args, pe, de, he, gdata, taps=True)
+    assert float(torch.quantile((free['z_new'].cpu() - want['z_new']).abs(), 0.99)) <= 1e-4
+    # free-running, one flipped `denom < 1e-5` decision (utils.py:224) moves a fine sample and with it a colour by
+    # more than the stage-wise tolerance -- the reference's own fp32-vs-fp64 runs differ the same way (SURVEY 7.2) --
+    # so: all but one ray within the RGB bar, the outlier within 10x of it
+    err = (free['rgb_fine'].cpu() - want['rgb_fine']).abs().max(-1).values
+    assert int((err > H.TOL_RGB).sum()) <= 1 and float(err.max()) <= 10 * H.TOL_RGB
