@@ -106,10 +106,10 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& h, uint32_t
 // into an operand tile pair (hi tile at `tile`, lo tile at `tile + kChunkBytes`).  amax2 accumulates
 // max |hi| (packed halves) for the fp16-range status flag.
 __device__ __forceinline__ void store_feat16(uint32_t tile, int row, int cc0, const float (&x)[16], bool fast, __half2& amax2) {
-  uint32_t h[8], l[8];
+  uint32_t h[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    split2(x[2 * i], x[2 * i + 1], h[i], l[i]);
+    h[i] = cvt_f16x2_sat(x[2 * i], x[2 * i + 1]);
     amax2 = __hmax2(amax2, __habs2(*reinterpret_cast<const __half2*>(&h[i])));
   }
   const uint32_t rofs = static_cast<uint32_t>(row) * 128u;
@@ -117,7 +117,13 @@ __device__ __forceinline__ void store_feat16(uint32_t tile, int row, int cc0, co
   const uint32_t o1 = rofs + (static_cast<uint32_t>(((cc0 + 1) ^ row) & 7) << 4);
   st_shared_v4(tile + o0, h[0], h[1], h[2], h[3]);
   st_shared_v4(tile + o1, h[4], h[5], h[6], h[7]);
-  if (!fast) {
+  if (!fast) {      // residuals only in parity mode (the fast mode is epilogue-bound: skipping them there is worth ~35% of it)
+    uint32_t l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+      l[i] = cvt_f16x2_sat(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+    }
     st_shared_v4(tile + kChunkBytes + o0, l[0], l[1], l[2], l[3]);
     st_shared_v4(tile + kChunkBytes + o1, l[4], l[5], l[6], l[7]);
   }
