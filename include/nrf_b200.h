@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NRF_ABI_VERSION 2
+#define NRF_ABI_VERSION 3
 
 enum {
   NRF_OK = 0,
@@ -105,6 +105,8 @@ typedef struct NrfRenderIO {
                                 sampling (stage-wise parity tests, "teacher forcing")        */
   const float* ray_bias_coarse; /* [B, nrf_raynet_ext_slots, 256] from nrf_ray_bias (ext_pose_bias nets)   */
   const float* ray_bias_fine;   /* same for the fine net                                                    */
+  const int32_t* ray_bias_nonuniform; /* optional [1] written by nrf_ray_bias: 0 = every ray has the pose of ray 0
+                                   (a rendered frame), so only row 0 of ray_bias_* was computed and is read      */
   /* outputs (fp32) */
   float* rgb;         /* [B,3] coarse colour                                                 */
   float* rgb_fine;    /* [B,3] (run_fine=0: may be NULL; the pipelines return rgb twice)     */
@@ -146,10 +148,13 @@ int nrf_pack_warpnet(const NrfWarpNetDesc* d, const float* const* params, int n_
  *   out[b, e, :] = bias_e + W_e[:, pose columns] * feats[b, :]        (fp32 FMA, CUDA cores)
  * feats: [B, A] (pose parameters, positionally encoded by the caller when the pipeline encodes them);
  * params: as for nrf_pack_raynet (the ORIGINAL fp32 nn.Linear tensors are read in place); out: [B, n_ext, 256]
- * with n_ext = nrf_raynet_ext_slots(d).  One launch; must run on the same stream before nrf_render. */
+ * with n_ext = nrf_raynet_ext_slots(d).  Must run on the same stream before nrf_render.
+ * nonuniform (optional, DEVICE int32[1]): set to 0 when all B feature rows are bit-identical (every ray of a rendered
+ * frame carries the same pose) -- then only row 0 is computed -- else to 1; hand it to nrf_render through
+ * NrfRenderIO.ray_bias_nonuniform.  Decided on the device, no host synchronisation. */
 int nrf_raynet_ext_slots(const NrfRayNetDesc* d);
 int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, int n_params, const float* feats, int64_t B,
-                 float* out, void* stream);
+                 float* out, int32_t* nonuniform, void* stream);
 
 /* The fused forward of the three pipelines for B rays.  packed_warp/warp may be NULL unless
  * kind == NRF_KIND_SMPL.  n_sms <= 0 means "all SMs of the current device". */

@@ -46,7 +46,7 @@ class PipelineDesc(C.Structure):
 
 
 _IO_IN = ['ray_samples', 'ray_origin', 'ray_dir', 'z_vals', 'goal_pose', 'u_fine', 'noise_coarse', 'noise_fine',
-          'z_all_in', 'ray_bias_coarse', 'ray_bias_fine']
+          'z_all_in', 'ray_bias_coarse', 'ray_bias_fine', 'ray_bias_nonuniform']
 _IO_OUT = ['rgb', 'rgb_fine', 'samples_out', 'alpha_out', 'warp_out', 'warped_out', 'raw_coarse', 'raw_fine',
            'weights_coarse', 'z_new', 'z_all', 'status', 'trace']
 
@@ -112,7 +112,8 @@ def lib() -> C.CDLL:
                              C.c_void_p, C.POINTER(WarpNetDesc), C.c_void_p, C.POINTER(RenderIO), C.c_int64, C.c_int,
                              C.c_void_p]
     L.nrf_raynet_ext_slots.argtypes = [C.POINTER(RayNetDesc)]
-    L.nrf_ray_bias.argtypes = [C.POINTER(RayNetDesc), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.nrf_ray_bias.argtypes = [C.POINTER(RayNetDesc), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                               C.c_void_p]
     L.nrf_generate_rays.argtypes = [C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nrf_positional_encoding.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
@@ -128,7 +129,7 @@ def lib() -> C.CDLL:
     L.nrf_bench_umma2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     L.nrf_selftest_umma2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nrf_bench_umma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
-    if L.nrf_abi_version() != 2:
+    if L.nrf_abi_version() != 3:
         raise RuntimeError('libnrf_b200.so ABI version mismatch; rebuild')
     _lib = L
     return L

@@ -579,11 +579,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           if (L.ray_slot < 0) continue;
           if (L.ray_src == RAY_POSE_EXT) {      // computed per ray by nrf_ray_bias (bias included)
             const float* src = pass == 0 ? P.io.ray_bias_coarse : P.io.ray_bias_fine;
+            const bool shared_pose = P.io.ray_bias_nonuniform && __ldg(P.io.ray_bias_nonuniform) == 0;   // then only row 0 exists
             for (int i = c.tid; i < G * kWidth; i += kEpiThreads) {
               const int g = i >> 8, col = i & 255;
               const int64_t ri = ray0 + g;
               rb[(static_cast<int>(L.ray_slot) * G + g) * kWidth + col] =
-                  ri < P.n_rays ? __ldg(src + (ri * net.n_ext_slots + L.ext_idx) * kWidth + col) : 0.f;
+                  ri < P.n_rays ? __ldg(src + ((shared_pose ? 0 : ri) * net.n_ext_slots + L.ext_idx) * kWidth + col) : 0.f;
             }
             continue;
           }

@@ -257,10 +257,21 @@ struct RayBiasTable { int32_t n; RayBiasJob j[NRF_MAX_SKIPS + 1]; };
 
 constexpr int kRbM = 128, kRbN = 64, kRbK = 16;
 
+// flag <- 1 if any feature row differs (bitwise) from row 0
+__global__ void rows_differ_kernel(const float* __restrict__ feats, int64_t B, int A, int32_t* __restrict__ flag) {
+  const int64_t total = B * A;
+  bool differ = false;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    differ |= __float_as_uint(feats[idx]) != __float_as_uint(__ldg(feats + idx % A));
+  if (__any_sync(0xffffffffu, differ) && (threadIdx.x & 31) == 0) atomicExch(flag, 1);
+}
+
 __global__ void __launch_bounds__(256) ray_bias_kernel(const __grid_constant__ RayBiasTable t, const float* __restrict__ feats, int64_t B,
-                                                       int A, float* __restrict__ out) {
+                                                       int A, float* __restrict__ out, const int32_t* __restrict__ nonuniform) {
   __shared__ __align__(16) float As[kRbK][kRbM + 4];
   __shared__ __align__(16) float Bs[kRbK][kRbN + 4];
+  if (nonuniform && *nonuniform == 0 && blockIdx.x > 0) return;      // one pose for the whole batch: row 0 is all that is read
   const RayBiasJob& job = t.j[blockIdx.z];
   const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kRbM;
   const int n0 = blockIdx.y * kRbN;
@@ -445,7 +456,7 @@ extern "C" int nrf_raynet_ext_slots(const NrfRayNetDesc* d) {
 }
 
 extern "C" int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, int n_params, const float* feats, int64_t B,
-                            float* out, void* stream) {
+                            float* out, int32_t* nonuniform, void* stream) {
   static thread_local NetPlan plan;
   int rc = plan_raynet(d, &plan);
   if (rc != NRF_OK) return rc;
@@ -471,8 +482,13 @@ extern "C" int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, 
     j.ld = li == 0 ? A + P : kWidth + A + P;
     j.col0 = li == 0 ? 0 : kWidth;
   }
+  if (nonuniform) {
+    cudaError_t e0 = cudaMemsetAsync(nonuniform, 0, sizeof(int32_t), static_cast<cudaStream_t>(stream));
+    if (e0 != cudaSuccess) return cuda_fail(e0, "cudaMemsetAsync(nonuniform)");
+    rows_differ_kernel<<<grid_for(B * A, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(feats, B, A, nonuniform);
+  }
   const dim3 grid(static_cast<unsigned>((B + kRbM - 1) / kRbM), kWidth / kRbN, static_cast<unsigned>(t.n));
-  ray_bias_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, feats, B, A, out);
+  ray_bias_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, feats, B, A, out, nonuniform);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "ray_bias_kernel launch");
 }

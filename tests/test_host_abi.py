@@ -30,7 +30,7 @@ def test_header_symbols_exported(L):
     for n in names:
         assert hasattr(L, n), f'{n} declared in include/nrf_b200.h but not exported'
     assert set(_lib.exported_symbols()) == names
-    assert L.nrf_abi_version() == 2
+    assert L.nrf_abi_version() == 3
 
 
 def test_struct_sizes_match_header(L):
@@ -38,7 +38,7 @@ def test_struct_sizes_match_header(L):
     assert C.sizeof(_lib.RayNetDesc) == 4 * (7 + 4 + 6)
     assert C.sizeof(_lib.WarpNetDesc) == 4 * 5
     assert C.sizeof(_lib.PipelineDesc) == 4 * 12
-    assert C.sizeof(_lib.RenderIO) == 8 * 24
+    assert C.sizeof(_lib.RenderIO) == 8 * 25
 
 
 def test_planner_sizes_and_rejections(L):
