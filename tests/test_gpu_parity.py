@@ -395,3 +395,26 @@ def test_architecture_and_sample_count_sweep(cfg):
     # so: all but one ray within the RGB bar, the outlier within 10x of it
     err = (free['rgb_fine'].cpu() - want['rgb_fine']).abs().max(-1).values
     assert int((err > H.TOL_RGB).sum()) <= 1 and float(err.max()) <= 10 * H.TOL_RGB
+
+
+def test_inference_loop_like_the_reference():
+    """The call sequence of inference.py:247-256 -- DataLoader batches of --inf_batchsize = 800 rays (the last one
+    short), per-tensor .to(device), out = pipeline(data), out[1].detach().cpu(), cat, reshape to the image -- with the
+    drop-in pipeline on the trained checkpoint's held-out view."""
+    ck, nets, args = H.load_trained()
+    gnets, _ = H.to_cuda(nets, [])
+    c, f, _, pe, de, he = gnets
+    pipe = NerfPipeline(c, f, args, pe, de)
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(*ck['data']), batch_size=800, shuffle=False, num_workers=0)
+    rgb_images = []
+    for data in loader:
+        data = list(data)
+        for j, element in enumerate(data):
+            data[j] = element.to(DEV)
+        out = pipe(data)
+        rgb_images.append(out[1].detach().cpu())
+    side = ck['side']
+    img = torch.cat(rgb_images).reshape(1, side, side, 3)
+    ref = ck['reference_rgb_fine'].reshape(1, side, side, 3)
+    assert float((img - ref).abs().max()) <= H.TOL_RGB
+    assert abs(H.psnr(img, ck['data'][-1].reshape(1, side, side, 3)) - ck['reference_psnr']) <= 0.1
