@@ -35,6 +35,9 @@ WORKLOADS = {
     # name: kind, image side, n_coarse, n_fine, run_fine, netdepth, skips
     'cfg2': dict(kind='smpl', side=128, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4],
                  text='smpl_nerf_pipeline, 128x128, netdepth=8, 64 coarse + 128 fine (BASELINE configs[1])'),
+    # configs[2]: 10 human poses at 256x256 -- one step = one 256x256 view, the 10 poses (arm angle 0..60 deg) rotate over the steps
+    'cfg3': dict(kind='smpl', side=256, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4], n_views=10,
+                 text='smpl_nerf_pipeline, 256x256, 10 human poses, 64 coarse + 128 fine (BASELINE configs[2])'),
     'cfg4': dict(kind='append', side=128, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4],
                  text='append_to_nerf_pipeline, 128x128, netdepth=8, 64+128 (BASELINE configs[3])'),
     'paper': dict(kind='append_full', side=128, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4],
@@ -233,7 +236,7 @@ def run_ours(a, w, rank, world, local_rank):
     else:
         pipe = NerfPipeline(coarse, fine, pargs, pe, de)
     strong = bool(w.get('strong'))
-    views_host = [[t.pin_memory() for t in v] for v in make_views(w, rank, N_VIEWS if not strong else 4, world)]
+    views_host = [[t.pin_memory() for t in v] for v in make_views(w, rank, w.get('n_views', N_VIEWS if not strong else 4), world)]
     views = [[t.to(dev) for t in v] for v in views_host]
     rays = int(views[0][0].shape[0])
     n_total = w['side'] * w['side'] if strong else rays * world
