@@ -17,10 +17,25 @@ class NerfPipeline(SmplPipeline):
         super().__init__(model_coarse, args, position_encoder, direction_encoder)
         self.model_fine = model_fine
 
+    #: set to True to read the kernel's range flag after every call (costs one device synchronisation per call)
+    strict_range = False
+
     def _render(self, data, **kw):
-        return engine.render(self.kind, self.model_coarse, self.model_fine, getattr(self, 'model_warp_field', None),
-                             self.args, self.position_encoder, self.direction_encoder,
-                             getattr(self, 'human_pose_encoder', None), data, **kw)
+        out = engine.render(self.kind, self.model_coarse, self.model_fine, getattr(self, 'model_warp_field', None),
+                            self.args, self.position_encoder, self.direction_encoder,
+                            getattr(self, 'human_pose_encoder', None), data, **kw)
+        self._status = out['status']
+        if self.strict_range:
+            self.check_range()
+        return out
+
+    def check_range(self):
+        """Raise if an activation of the LAST call left the fp16 range (|x| > 65504): the fp16 hi/lo operand split
+        saturates there, so the result would silently deviate from the fp32 reference.  Synchronises the device."""
+        st = getattr(self, '_status', None)
+        if st is not None and int(st.item()) & 1:
+            raise FloatingPointError('smpl_nerf_b200: a hidden activation exceeded the fp16 range (65504); the fused '
+                                     'engine cannot represent it -- rescale the offending layer or use the reference path')
 
     def forward(self, data):
         if len(data) < 5:

@@ -418,3 +418,22 @@ def test_inference_loop_like_the_reference():
     ref = ck['reference_rgb_fine'].reshape(1, side, side, 3)
     assert float((img - ref).abs().max()) <= H.TOL_RGB
     assert abs(H.psnr(img, ck['data'][-1].reshape(1, side, side, 3)) - ck['reference_psnr']) <= 0.1
+
+
+def test_range_flag_is_reported():
+    """Activations beyond the fp16 range: the kernel saturates and raises its status bit; check_range() surfaces it."""
+    nets = O.build_nets('nerf', 17, 'default')
+    rays = scene.make_rays(4, 4, 64, seed=14)
+    data = scene.data_list(rays, 'nerf')
+    gnets, gdata = H.to_cuda(nets, data)
+    pipe = make_pipeline('nerf', gnets, O.make_args())
+    pipe(gdata)
+    pipe.check_range()                                   # a sane net: no flag
+    with torch.no_grad():
+        gnets[0].positions_pose_input.bias.add_(1e5)     # hidden activations ~1e5 > 65504
+    pipe(gdata)
+    with pytest.raises(FloatingPointError):
+        pipe.check_range()
+    pipe.strict_range = True
+    with pytest.raises(FloatingPointError):
+        pipe(gdata)
