@@ -437,3 +437,42 @@ def test_range_flag_is_reported():
     pipe.strict_range = True
     with pytest.raises(FloatingPointError):
         pipe(gdata)
+
+
+@pytest.mark.parametrize('kind', ['nerf', 'append', 'append_full'])
+def test_full_size_properties_other_pipelines(kind):
+    """BASELINE configs[3]-sized inputs (128x128 rays, 64+128) for the other pipelines: finiteness, ranges, sortedness,
+    determinism, independence of rays (split / permuted batches give the same bits), and a seeded subset vs the oracle."""
+    nets = O.build_nets(kind, 23, 'dense')
+    args = O.make_args()
+    rays = scene.make_rays(128, 128, 64, seed=17)
+    data = scene.data_list(rays, kind)
+    gnets, gdata = H.to_cuda(nets, data)
+    c, f, w, pe, de, he = gnets
+    out = engine.render(kind, c, f, w, args, pe, de, he, gdata, taps=True)
+    torch.cuda.synchronize()
+    B = 128 * 128
+    assert int(out['status'].item()) == 0
+    for k in ('rgb', 'rgb_fine', 'alpha_out', 'samples_out', 'z_all'):
+        assert torch.isfinite(out[k]).all(), k
+    assert float(out['rgb_fine'].min()) >= -1e-5 and float(out['rgb_fine'].max()) <= 1 + 1e-5
+    assert float(out['alpha_out'].min()) >= 0 and float(out['alpha_out'].max()) <= 1
+    za = out['z_all']
+    assert bool((za[:, 1:] >= za[:, :-1]).all())
+    assert torch.equal(za, torch.sort(torch.cat([gdata[3], out['z_new']], -1), -1)[0])
+    again = engine.render(kind, c, f, w, args, pe, de, he, gdata)
+    assert torch.equal(again['rgb_fine'], out['rgb_fine']) and torch.equal(again['alpha_out'], out['alpha_out'])
+    perm = torch.randperm(B, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    shuf = engine.render(kind, c, f, w, args, pe, de, he, [t[perm] for t in gdata])
+    assert torch.equal(shuf['rgb_fine'], out['rgb_fine'][perm])
+    assert torch.equal(shuf['samples_out'], out['samples_out'][perm])
+    third = [t[B // 3:B // 3 + 4097] for t in gdata]
+    part = engine.render(kind, c, f, w, args, pe, de, he, third)
+    assert torch.equal(part['rgb_fine'], out['rgb_fine'][B // 3:B // 3 + 4097])
+    idx = torch.linspace(0, B - 1, 64).long()
+    with torch.no_grad():
+        want = H.run_oracle(kind, nets, args, [t[idx] for t in data])
+    assert maxdiff(out['rgb'][idx.to(DEV)], want['rgb']) <= H.TOL_RGB
+    assert maxdiff(out['raw_coarse'][idx.to(DEV)][..., 3], want['raw_coarse'][..., 3]) <= H.TOL_SIGMA
+    err = (out['rgb_fine'][idx.to(DEV)].cpu() - want['rgb_fine']).abs().max(-1).values
+    assert int((err > H.TOL_RGB).sum()) <= 1 and float(err.max()) <= 10 * H.TOL_RGB
