@@ -82,11 +82,12 @@ def _aligned_u8(nbytes: int, device) -> (torch.Tensor, torch.Tensor):
 def packed(net, desc, device, stream) -> torch.Tensor:
     """Device buffer holding ``net`` in the engine's layout; re-packed iff a parameter changed."""
     L = _lib.lib()
-    ps = _params(net, device)
-    key = (bytes(desc), str(device)) + tuple((p.data_ptr(), p._version) for p in net.parameters())
+    # the hit path runs on every pipeline call: keep it to one walk over the parameters (~40 us for a RenderRayNet)
+    key = (bytes(desc), device) + tuple([(p.data_ptr(), p._version) for p in net.parameters()])
     ent = _cache.get(net)
     if ent is not None and ent.key == key:
         return ent.buf
+    ps = _params(net, device)
     is_warp = isinstance(desc, WarpNetDesc)
     nbytes = (L.nrf_warpnet_packed_bytes if is_warp else L.nrf_raynet_packed_bytes)(C.byref(desc))
     if nbytes == 0:
