@@ -177,6 +177,36 @@ def cpu_reference_rays_per_s(w, state, n_batches, batch, warmup=1, seed=0):
     return batch / statistics.median(times), times
 
 
+def heldout_psnr(dev, precision):
+    """PSNR half of the BASELINE metric: the briefly trained vanilla-NeRF checkpoint of tests/golden/ (trained and
+    rendered with the REFERENCE classes by tests/golden/make_trained.py) re-rendered by the engine on its held-out
+    32x32 view -- against the analytic ground truth and against the reference's stored render."""
+    import math
+    from types import SimpleNamespace
+    from smpl_nerf_b200.models import NerfPipeline, RenderRayNet
+    from smpl_nerf_b200.ops import PositionalEncoder
+    path = os.path.join(ROOT, 'tests', 'golden', 'trained_nerf_d4.ckpt')
+    if not os.path.isfile(path):
+        return None
+    ck = torch.load(path, weights_only=False)
+    pe, de = PositionalEncoder(10, False), PositionalEncoder(4, False)
+    nets = []
+    for key in ('coarse', 'fine'):
+        net = RenderRayNet(ck['n_layers'], 256, 3 * pe.output_dim, 3 * de.output_dim, 0, list(ck['skips']))
+        net.load_state_dict({k: v.float() for k, v in ck[key].items()})
+        nets.append(net.to(dev))
+    args = SimpleNamespace(default_device=None, sigma_noise_std=0., white_background=1, run_fine=1,
+                           number_fine_samples=ck['n_fine'], human_pose_encoding=1)
+    from smpl_nerf_b200 import engine
+    data = [t.to(dev) for t in ck['data']]
+    with torch.no_grad():
+        img = engine.render('nerf', nets[0], nets[1], None, args, pe, de, None, data, precision=precision)['rgb_fine'].double().cpu()
+    db = lambda a, b: -10.0 * math.log10(max(float(torch.mean((a - b.double()) ** 2)), 1e-30))
+    return {'engine_vs_gt_db': db(img, ck['data'][-1]), 'reference_vs_gt_db': float(ck['reference_psnr']),
+            'engine_vs_reference_render_db': db(img, ck['reference_rgb_fine']),
+            'view': 'held-out 32x32 view, vanilla NeRF depth 4 (32+64 samples) trained for 1200 steps with the reference classes'}
+
+
 def cpu_model():
     try:
         for line in open('/proc/cpuinfo'):
@@ -332,6 +362,8 @@ def run_ours(a, w, rank, world, local_rank):
                      'note': 'algorithmic FLOPs = 2 x MACs of the reference nn.Linear layers; the parity mode executes 3 fp16 '
                              'MMA passes per algorithmic MAC, so the tensor pipe does 3x this work'},
     }
+    if world == 1:
+        line['psnr'] = heldout_psnr(dev, precision)
     if world == 1 and not a.no_cpu_baseline:
         batch = 256 if a.workload == 'cfg1' else 1024
         rps, times = cpu_reference_rays_per_s(w, state, 3, batch, warmup=1)
