@@ -53,7 +53,7 @@ constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kRayVec = 8 + kMaxRayFeat + 32;      // unit direction[3], raw pose pair[2]
 constexpr int kRayFloats = kRayVec + 8;
 constexpr int kRayScratchFloats = 2 * kMaxFineRows + (kTileRows + 16) + kTileRows + kMaxFineRows + kTeamScratch;   // tf, tt, cdf, pdf, z_samples, team partials of one ray
-static_assert((kTileRows / 16) * kRayScratchFloats * 4 <= 3 * 2 * 16384, "per-ray scratch must fit below the exchange slots in the A region");            // o[3] d[3] |d| valid | pose feats[64] | dir feats[32] | unit d, pose
+static_assert((kTileRows / 16) * kRayScratchFloats * 4 <= 2 * 2 * 16384, "per-ray scratch must stay inside activation chunks 0 and 1 (chunk 2 stages the warp encoding, chunk 3 the exchange slots)");            // o[3] d[3] |d| valid | pose feats[64] | dir feats[32] | unit d, pose
 
 // barrier slots inside the misc area (8 bytes each)
 enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC = 2 * kMaxStages, BAR_AREADY = 2 * kMaxStages + 2,
@@ -598,6 +598,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
         }
         named_bar_sync(1, kEpiThreads);
 
+        // sample point of this thread's row in tile t (coarse: as given; fine: o + d * z with separate mul / add)
+        auto tile_point = [&](int t, bool store, float& x, float& y, float& z) {
+          const int R = t * kTileRows + c.row;
+          const bool in_rows = R < G * n;
+          const int g = in_rows ? R / n : 0;
+          const int s = in_rows ? R - g * n : 0;
+          const int64_t ri = ray0 + g;
+          x = y = z = 0.f;
+          if (!(in_rows && ri < P.n_rays)) return;
+          if (pass == 0) {
+            const float* ps = P.io.ray_samples + (ri * nc + s) * 3;
+            x = __ldcs(ps); y = __ldcs(ps + 1); z = __ldcs(ps + 2);
+          } else {
+            const float* r = ray + g * kRayFloats;
+            const float zz = zf[g * na + s];
+            x = __fadd_rn(r[0], __fmul_rn(r[3], zz)); y = __fadd_rn(r[1], __fmul_rn(r[4], zz)); z = __fadd_rn(r[2], __fmul_rn(r[5], zz));
+            if (store && c.cg == 0 && P.io.samples_out) { float* po = P.io.samples_out + (ri * na + s) * 3; __stcs(po, x); __stcs(po + 1, y); __stcs(po + 2, z); }
+          }
+        };
+        // smpl: the warp net's input encoding of tile t is written one step EARLY -- for tile 0 here, for tile t + 1
+        // between the last two layers of tile t -- into activation chunk 2 (dead from the dir layer's MMAs on), so the
+        // warp MMA of the next tile runs under the rgb head of this one instead of after it
+        const uint32_t wpe_tile = smem_u32(sm.base) + kOffA + 2u * 2u * kChunkBytes;
+        auto warp_encode = [&](int t) {
+          float x, y, z;
+          if (c.tid == 0) trace_ev(P, 31, c.layer_ctr);
+          tile_point(t, true, x, y, z);
+          write_encoding(wpe_tile, c.row, c.cg, x, y, z, P.warp.in_freqs, P.warp.in_identity, fast);
+          if (c.tid == 0) trace_ev(P, 32, c.layer_ctr);
+          epi_publish(sm, c, 2);
+          if (c.tid == 0) trace_ev(P, 33, c.layer_ctr);
+        };
+        if (smpl) warp_encode(0);
+
         for (int t = 0; t < tiles; ++t) {
           const int R = t * kTileRows + c.row;
           const bool in_rows = R < G * n;
@@ -606,28 +640,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           const int64_t ri = ray0 + g;
           const bool valid = in_rows && ri < P.n_rays;
           const float* r = ray + g * kRayFloats;
-          float x = 0.f, y = 0.f, z = 0.f;
+          float x, y, z;
           if (c.tid == 0) trace_ev(P, 30, c.layer_ctr);
-          if (valid) {
-            if (pass == 0) {
-              const float* ps = P.io.ray_samples + (ri * nc + s) * 3;
-              x = __ldcs(ps); y = __ldcs(ps + 1); z = __ldcs(ps + 2);
-            } else {
-              const float zz = zf[g * na + s];
-              x = __fadd_rn(r[0], __fmul_rn(r[3], zz)); y = __fadd_rn(r[1], __fmul_rn(r[4], zz)); z = __fadd_rn(r[2], __fmul_rn(r[5], zz));
-              if (c.cg == 0 && P.io.samples_out) { float* po = P.io.samples_out + (ri * na + s) * 3; __stcs(po, x); __stcs(po + 1, y); __stcs(po + 2, z); }
-            }
-          }
+          tile_point(t, !smpl, x, y, z);
           float ux = 0.f, uy = 0.f, uz = 1.f;   // unit view direction of this sample (smpl)
           float dnorm_s = r[6];                 // |direction| that scales this sample's delta (utils.py:165-167)
           HeadOut ho = {0.f, 0.f, 0.f, 0.f};
           if (smpl) {
-            // ---- warp field: x -> x + W2 relu(W1 [enc(x), pose] + b1) + b2
-            if (c.tid == 0) trace_ev(P, 31, c.layer_ctr);
-            write_encoding(aux_tile, c.row, c.cg, x, y, z, P.warp.in_freqs, P.warp.in_identity, fast);
-            if (c.tid == 0) trace_ev(P, 32, c.layer_ctr);
-            epi_publish(sm, c, kSrcAux);
-            if (c.tid == 0) trace_ev(P, 33, c.layer_ctr);
+            // ---- warp field: x -> x + W2 relu(W1 [enc(x), pose] + b1) + b2   (its input was encoded one step earlier)
             const float* wf32 = reinterpret_cast<const float*>(P.blob[2] + P.warp.f32_ofs);
             c.head_s = hw_s;
             epilogue_layer<true, false, true, false>(sm, P, P.warp, wf32, rbw, P.warp.layers[0], c, g, ho);
@@ -669,6 +689,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           for (int l = 0; l < net.n_layers; ++l) {
             const Layer& L = net.layers[l];
             HeadOut hl = {0.f, 0.f, 0.f, 0.f};
+            if (smpl && l == net.n_layers - 1 && t + 1 < tiles) warp_encode(t + 1);   // chunks 2, 3 are dead: the rgb layer reads 0 and 1
             epilogue_dispatch(sm, P, net, f32, rb, L, c, g, hl);
             if (L.flags & LF_SIGMA_HEAD) sigma_part = hl.sig;
             if (L.epi == EPI_RGB) ho = hl;

@@ -107,7 +107,8 @@ int plan_warpnet(const NrfWarpNetDesc* d, NetPlan* p) {
   p->in_freqs = d->in_freqs; p->in_identity = d->in_identity;
   uint32_t f = 0;
   Layer& L = p->layers[0];
-  L.n_out = kWidth; L.epi = EPI_WARP; L.flags = LF_AUX_WAIT; L.nk = 1; L.ksrc[0] = kSrcAux;
+  // its one K-chunk (the xyz encoding) is staged in activation chunk 2, not in the aux tile: see warp_encode in nrf_fused.cu
+  L.n_out = kWidth; L.epi = EPI_WARP; L.flags = 0; L.nk = 1; L.ksrc[0] = 2;
   L.bias_ofs = f; f = align4(f + kWidth);
   L.ray_slot = -1;
   if (d->pose_dim > 0) { L.ray_src = RAY_POSE; L.ray_k = static_cast<uint16_t>(d->pose_dim); L.ray_slot = 0; L.rayw_ofs = f; f = align4(f + d->pose_dim * kWidth); }
