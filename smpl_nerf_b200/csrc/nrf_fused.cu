@@ -621,10 +621,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
         // between the last two layers of tile t -- into activation chunk 2 (dead from the dir layer's MMAs on), so the
         // warp MMA of the next tile runs under the rgb head of this one instead of after it
         const uint32_t wpe_tile = smem_u32(sm.base) + kOffA + 2u * 2u * kChunkBytes;
+        float px = 0.f, py = 0.f, pz = 0.f;     // this row's point in the tile whose warp input was encoded last
         auto warp_encode = [&](int t) {
           float x, y, z;
           if (c.tid == 0) trace_ev(P, 31, c.layer_ctr);
           tile_point(t, true, x, y, z);
+          px = x; py = y; pz = z;
           write_encoding(wpe_tile, c.row, c.cg, x, y, z, P.warp.in_freqs, P.warp.in_identity, fast);
           if (c.tid == 0) trace_ev(P, 32, c.layer_ctr);
           epi_publish(sm, c, 2);
@@ -642,7 +644,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           const float* r = ray + g * kRayFloats;
           float x, y, z;
           if (c.tid == 0) trace_ev(P, 30, c.layer_ctr);
-          tile_point(t, !smpl, x, y, z);
+          if (smpl) { x = px; y = py; z = pz; }      // computed by warp_encode(t) one step earlier
+          else tile_point(t, true, x, y, z);
           float ux = 0.f, uy = 0.f, uz = 1.f;   // unit view direction of this sample (smpl)
           float dnorm_s = r[6];                 // |direction| that scales this sample's delta (utils.py:165-167)
           HeadOut ho = {0.f, 0.f, 0.f, 0.f};
