@@ -632,7 +632,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           epi_publish(sm, c, 2);
           if (c.tid == 0) trace_ev(P, 33, c.layer_ctr);
         };
+        // nerf / append kinds: the same one step early for the xyz encoding that feeds the first layer (the aux tile's
+        // last reader, a skip layer, is long done by then)
+        auto pos_encode = [&](int t) {
+          float x, y, z;
+          if (c.tid == 0) trace_ev(P, 36, c.layer_ctr);
+          tile_point(t, true, x, y, z);
+          write_encoding(aux_tile, c.row, c.cg, x, y, z, net.in_freqs, net.in_identity, fast);
+          if (c.tid == 0) trace_ev(P, 37, c.layer_ctr);
+          epi_publish(sm, c, kSrcAux);
+          if (c.tid == 0) trace_ev(P, 38, c.layer_ctr);
+        };
         if (smpl) warp_encode(0);
+        else pos_encode(0);
 
         for (int t = 0; t < tiles; ++t) {
           const int R = t * kTileRows + c.row;
@@ -644,8 +656,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           const float* r = ray + g * kRayFloats;
           float x, y, z;
           if (c.tid == 0) trace_ev(P, 30, c.layer_ctr);
-          if (smpl) { x = px; y = py; z = pz; }      // computed by warp_encode(t) one step earlier
-          else tile_point(t, true, x, y, z);
+          x = px; y = py; z = pz;                    // smpl: computed by warp_encode(t) one step earlier (else unused)
           float ux = 0.f, uy = 0.f, uz = 1.f;   // unit view direction of this sample (smpl)
           float dnorm_s = r[6];                 // |direction| that scales this sample's delta (utils.py:165-167)
           HeadOut ho = {0.f, 0.f, 0.f, 0.f};
@@ -679,12 +690,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
             // (no barrier needed before the exchange slots are reused: every later writer of A chunk 3
             //  sits behind an mbarrier that all 16 warps arrive on only after these reads)
           }
-          // ---- encoded position -> aux (first layer and skip layer read it)
-          if (c.tid == 0) trace_ev(P, 36, c.layer_ctr);
-          write_encoding(aux_tile, c.row, c.cg, x, y, z, net.in_freqs, net.in_identity, fast);
-          if (c.tid == 0) trace_ev(P, 37, c.layer_ctr);
-          epi_publish(sm, c, kSrcAux);
-          if (c.tid == 0) trace_ev(P, 38, c.layer_ctr);
+          if (smpl) {
+            // ---- encoded (warped) position -> aux (first layer and skip layer read it)
+            if (c.tid == 0) trace_ev(P, 36, c.layer_ctr);
+            write_encoding(aux_tile, c.row, c.cg, x, y, z, net.in_freqs, net.in_identity, fast);
+            if (c.tid == 0) trace_ev(P, 37, c.layer_ctr);
+            epi_publish(sm, c, kSrcAux);
+            if (c.tid == 0) trace_ev(P, 38, c.layer_ctr);
+          }
 
           ho = {0.f, 0.f, 0.f, 0.f};
           float sigma_part = 0.f;
@@ -692,7 +705,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
           for (int l = 0; l < net.n_layers; ++l) {
             const Layer& L = net.layers[l];
             HeadOut hl = {0.f, 0.f, 0.f, 0.f};
-            if (smpl && l == net.n_layers - 1 && t + 1 < tiles) warp_encode(t + 1);   // chunks 2, 3 are dead: the rgb layer reads 0 and 1
+            if (l == net.n_layers - 1 && t + 1 < tiles) {
+              if (smpl) warp_encode(t + 1);      // chunks 2, 3 are dead: the rgb layer reads 0 and 1
+              else pos_encode(t + 1);
+            }
             epilogue_dispatch(sm, P, net, f32, rb, L, c, g, hl);
             if (L.flags & LF_SIGMA_HEAD) sigma_part = hl.sig;
             if (L.epi == EPI_RGB) ho = hl;
