@@ -425,7 +425,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
 
   if (threadIdx.x == 0) {
     *reinterpret_cast<uint32_t*>(smem_raw + P.off_misc + kTraceCtrOfs) = 0u;
-    // issuer CTA: a stage is full when its own producer (arrive + bytes) and the peer's relay have arrived
+    // a stage is full when the issuer CTA's producer has arrived (announcing the bytes of BOTH halves) and both CTAs' TMA bytes have landed
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(sm.bar(BAR_FULL + s), 1); mbar_init(sm.bar(BAR_EMPTY + s), 1); }
     mbar_init(sm.bar(BAR_ACC + 0), 1); mbar_init(sm.bar(BAR_ACC + 1), 1);
     for (int j = 0; j < 5; ++j) mbar_init(sm.bar(BAR_AREADY + j), 2);   // one arrival per CTA of the pair
@@ -453,7 +453,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
         }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (even CTA) / stage relay (odd CTA) ===========================
+    // =========================== MMA issuer (even CTA; this warp idles in the odd CTA) ===========================
     // the whole warp runs these loops convergently; one elected lane issues each instruction
     {
       MmaState st;
@@ -486,7 +486,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
     float* hw_s = sm.misc + P.o_hw;          // warp net head weights [3][256] (smpl)
     float* hr_s = sm.misc + P.o_hr;          // rgb head weights [3][128] of the current net
     float* hs_s = sm.misc + P.o_hs;          // sigma head weights [256] of the current net
-    // head-partial exchange: 8 float4 slots per row inside A chunk 3 (dead whenever it is used)
+    // head-partial exchange: a [column group][row] float4 table inside A chunk 3 (dead whenever it is used)
     float4* xchg = reinterpret_cast<float4*>(sm.base + kOffXchg) + c.row;   // slot of column group k: xchg[kTileRows * k] (lanes contiguous: no bank conflicts)
     const uint32_t aux_tile = smem_u32(sm.base) + kOffAux;
     const int G = P.G, nc = P.n_coarse, nf = P.n_fine, na = P.n_all;
