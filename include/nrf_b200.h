@@ -172,6 +172,12 @@ int nrf_positional_encoding(const float* x, int64_t n, int32_t c, int32_t freqs,
 /* utils.py:134-191: raw[B,n,4], z[B,n], dirs[B,n,3], optional noise[B,n] -> rgb[B,3], weights[B,n], alpha[B,n] */
 int nrf_raw2outputs(const float* raw, const float* z, const float* dirs, const float* noise, int64_t B, int32_t n,
                     int32_t white_background, float* rgb, float* weights, float* alpha, void* stream);
+/* Backward of raw2outputs (what loss.backward() in solver/nerf_solver.py:85 needs from this stage): d(loss)/d(raw)[B,n,4]
+ * from d(loss)/d(rgb)[B,3] and the optional d(loss)/d(weights)[B,n], d(loss)/d(alpha)[B,n] (NULL = zero).  The forward
+ * quantities are recomputed; `noise` must be the draw the forward used. */
+int nrf_raw2outputs_backward(const float* raw, const float* z, const float* dirs, const float* noise, int64_t B, int32_t n,
+                             int32_t white_background, const float* grad_rgb, const float* grad_weights,
+                             const float* grad_alpha, float* grad_raw, void* stream);
 /* utils.py:194-228: bins[B,m], weights[B,m-1], u[n_fine] -> samples[B,n_fine] */
 int nrf_sample_pdf(const float* bins, const float* weights, const float* u, int64_t B, int32_t m, int32_t n_fine,
                    float* samples, void* stream);

@@ -63,6 +63,70 @@ __global__ void raw2outputs_kernel(const float* __restrict__ raw, const float* _
   }
 }
 
+// ------------------------------------------------------------------------------ raw2outputs backward
+// d(loss)/d(raw) of utils.py:134-191 given d(loss)/d(rgb) [B,3] and, optionally, d(loss)/d(weights) [B,n] and
+// d(loss)/d(alpha) [B,n] (the reference's GMM density loss reads the densities).  With c = sigmoid(rgb_raw),
+// a = 1 - exp(-relu(s) delta), keep = 1 - a + 1e-10, T_i = prod_{j<i} keep_j, w = a T:
+//   gw_i = g_rgb . c_i  - [white] sum(g_rgb) + g_weights_i
+//   d/dc_i = w_i g_rgb                          d/da_i = gw_i T_i - (sum_{k>i} gw_k w_k) / keep_i + g_alpha_i
+//   d/ds_i = d/da_i * delta_i (1 - a_i) [s_i > 0]          d/drgb_raw = d/dc * c (1 - c)
+// One warp per ray; the forward quantities are recomputed (nothing is saved by the forward), the transmittance with
+// the same sequential product as the forward, the suffix sum sequentially from the far end.
+__global__ void raw2outputs_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ dirs,
+                                       const float* __restrict__ noise, int64_t B, int n, int white, const float* __restrict__ g_rgb,
+                                       const float* __restrict__ g_w, const float* __restrict__ g_a, float* __restrict__ g_raw) {
+  extern __shared__ __align__(16) float smem[];
+  const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n4 = (n + 3) & ~3;
+  float4* act4 = reinterpret_cast<float4*>(smem) + static_cast<size_t>(w) * n;
+  float* base = smem + static_cast<size_t>(wpb) * n * 4 + static_cast<size_t>(w) * 5 * n4;
+  float* keep = base; float* T = keep + n4; float* gw = T + n4; float* suf = gw + n4; float* dsig = suf + n4;
+  for (int64_t ray = blockIdx.x * static_cast<int64_t>(wpb) + w; ray < B; ray += static_cast<int64_t>(gridDim.x) * wpb) {
+    const float gr = g_rgb[ray * 3], gg = g_rgb[ray * 3 + 1], gb = g_rgb[ray * 3 + 2];
+    for (int i = lane; i < n; i += 32) {
+      const float4 r = *reinterpret_cast<const float4*>(raw + (ray * n + i) * 4);
+      const float* d = dirs + (ray * n + i) * 3;
+      const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+      const float dz = (i < n - 1) ? __fsub_rn(z[ray * n + i + 1], z[ray * n + i]) : 1e10f;
+      const float delta = __fmul_rn(dz, nrm);
+      const float s = noise ? __fadd_rn(r.w, noise[ray * n + i]) : r.w;
+      const float e = expf(-__fmul_rn(fmaxf(s, 0.f), delta));          // = 1 - alpha
+      const float a = __fsub_rn(1.f, e);
+      act4[i] = make_float4(sigmoidf_ref(r.x), sigmoidf_ref(r.y), sigmoidf_ref(r.z), a);
+      keep[i] = __fadd_rn(__fsub_rn(1.f, a), 1e-10f);
+      dsig[i] = s > 0.f ? delta * e : 0.f;
+    }
+    __syncwarp();
+    if (lane == 0) serial_scan<true>(keep, T, n);
+    __syncwarp();
+    const float bg = white ? (gr + gg + gb) : 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const float4 c = act4[i];
+      const float g = gr * c.x + gg * c.y + gb * c.z - bg + (g_w ? g_w[ray * n + i] : 0.f);
+      gw[i] = g;
+      suf[i] = g * (c.w * T[i]);
+    }
+    __syncwarp();
+    if (lane == 0) {          // exclusive suffix sum, from the far end
+      float run = 0.f;
+      for (int i = n - 1; i >= 0; --i) { const float v = suf[i]; suf[i] = run; run += v; }
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const float4 c = act4[i];
+      const float wi = c.w * T[i];
+      const float ga = gw[i] * T[i] - suf[i] / keep[i] + (g_a ? g_a[ray * n + i] : 0.f);
+      float4 o;
+      o.x = wi * gr * c.x * (1.f - c.x);
+      o.y = wi * gg * c.y * (1.f - c.y);
+      o.z = wi * gb * c.z * (1.f - c.z);
+      o.w = ga * dsig[i];
+      *reinterpret_cast<float4*>(g_raw + (ray * n + i) * 4) = o;
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------ sample_pdf
 // one warp per ray: pdf -> sequential cdf -> right-sided bisection -> guarded lerp
 __global__ void sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, const float* __restrict__ u,
@@ -509,4 +573,21 @@ extern "C" int nrf_generate_rays(int32_t H, int32_t W, double focal, const doubl
                                                                                            ray_dir, z_vals);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "generate_rays_kernel launch");
+}
+
+extern "C" int nrf_raw2outputs_backward(const float* raw, const float* z, const float* dirs, const float* noise, int64_t B, int32_t n,
+                                        int32_t white_background, const float* grad_rgb, const float* grad_weights,
+                                        const float* grad_alpha, float* grad_raw, void* stream) {
+  if (!raw || !z || !dirs || !grad_rgb || !grad_raw) { set_error("raw2outputs_backward: NULL argument"); return NRF_E_INVALID; }
+  if (B < 0 || n < 2 || n > 1024) { set_error("raw2outputs_backward: unsupported shape B=%lld n=%d (n in 2..1024)", (long long)B, n); return NRF_E_INVALID; }
+  if (B == 0) return NRF_OK;
+  const int wpb = 4;
+  const size_t smem = static_cast<size_t>(wpb) * (4 * n + 5 * ((n + 3) & ~3)) * sizeof(float);
+  const int grid = static_cast<int>(B / wpb + 1 > 148 * 8 ? 148 * 8 : B / wpb + 1);
+  cudaError_t e = cudaFuncSetAttribute(raw2outputs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  raw2outputs_bwd_kernel<<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(raw, z, dirs, noise, B, n, white_background, grad_rgb,
+                                                                                    grad_weights, grad_alpha, grad_raw);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "raw2outputs_bwd_kernel launch");
 }

@@ -51,27 +51,67 @@ class PositionalEncoder:
         return out
 
 
-def raw2outputs(raw: torch.Tensor, z_vals: torch.Tensor, samples_directions: torch.Tensor, args
-                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """-> (rgb[B,3], weights[B,n], density(alpha)[B,n]); noise is drawn like utils.py:172-174."""
-    _need_cuda(raw, 'raw')
+def _raw2outputs_fwd(raw, z, dirs, noise, white):
     dev = raw.device
     B, n = int(raw.shape[0]), int(raw.shape[1])
-    raw = _f32(raw, 'raw', dev, (B, n, 4))
-    z = _f32(z_vals, 'z_vals', dev, (B, n))
-    dirs = _f32(samples_directions.expand(B, n, 3), 'samples_directions', dev, (B, n, 3))
-    noise = None
-    if float(getattr(args, 'sigma_noise_std', 0.) or 0.) > 0.:
-        noise = torch.normal(0, float(args.sigma_noise_std), (B, n), device=dev)
     rgb = torch.empty(B, 3, dtype=torch.float32, device=dev)
     weights = torch.empty(B, n, dtype=torch.float32, device=dev)
     alpha = torch.empty(B, n, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(_lib.lib().nrf_raw2outputs(raw.data_ptr(), z.data_ptr(), dirs.data_ptr(),
-                                         noise.data_ptr() if noise is not None else None, B, n,
-                                         1 if args.white_background else 0, rgb.data_ptr(), weights.data_ptr(),
-                                         alpha.data_ptr(), _stream(dev)), 'nrf_raw2outputs')
+                                         noise.data_ptr() if noise is not None else None, B, n, white, rgb.data_ptr(),
+                                         weights.data_ptr(), alpha.data_ptr(), _stream(dev)), 'nrf_raw2outputs')
     return rgb, weights, alpha
+
+
+class _Raw2Outputs(torch.autograd.Function):
+    """raw2outputs with a native backward (nrf_raw2outputs_backward): gradients flow to ``raw`` only -- z_vals and the
+    directions are data in every reference pipeline."""
+
+    @staticmethod
+    def forward(ctx, raw, z, dirs, noise, white):
+        ctx.save_for_backward(raw, z, dirs, noise if noise is not None else raw.new_empty(0))
+        ctx.white = white
+        return _raw2outputs_fwd(raw, z, dirs, noise, white)
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_w, g_a):
+        raw, z, dirs, noise = ctx.saved_tensors
+        dev = raw.device
+        B, n = int(raw.shape[0]), int(raw.shape[1])
+        g_raw = torch.empty_like(raw)
+        g_rgb = torch.zeros(B, 3, dtype=torch.float32, device=dev) if g_rgb is None else g_rgb.contiguous().float()
+        g_w = None if g_w is None else g_w.contiguous().float()
+        g_a = None if g_a is None else g_a.contiguous().float()
+        ptr = lambda t: t.data_ptr() if t is not None and t.numel() > 0 else None
+        with torch.cuda.device(dev):
+            check(_lib.lib().nrf_raw2outputs_backward(raw.data_ptr(), z.data_ptr(), dirs.data_ptr(), ptr(noise), B, n, ctx.white,
+                                                      g_rgb.data_ptr(), ptr(g_w), ptr(g_a), g_raw.data_ptr(), _stream(dev)),
+                  'nrf_raw2outputs_backward')
+        return g_raw, None, None, None, None
+
+
+def raw2outputs(raw: torch.Tensor, z_vals: torch.Tensor, samples_directions: torch.Tensor, args
+                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (rgb[B,3], weights[B,n], density(alpha)[B,n]); noise is drawn like utils.py:172-174.  Differentiable with
+    respect to ``raw`` (native backward kernel) when ``raw.requires_grad``."""
+    _need_cuda(raw, 'raw')
+    dev = raw.device
+    B, n = int(raw.shape[0]), int(raw.shape[1])
+    needs_grad = torch.is_grad_enabled() and raw.requires_grad
+    raw32 = raw if (needs_grad and raw.dtype == torch.float32 and raw.is_contiguous() and tuple(raw.shape) == (B, n, 4)) \
+        else _f32(raw, 'raw', dev, (B, n, 4))
+    z = _f32(z_vals, 'z_vals', dev, (B, n))
+    dirs = _f32(samples_directions.expand(B, n, 3), 'samples_directions', dev, (B, n, 3))
+    noise = None
+    if float(getattr(args, 'sigma_noise_std', 0.) or 0.) > 0.:
+        noise = torch.normal(0, float(args.sigma_noise_std), (B, n), device=dev)
+    white = 1 if args.white_background else 0
+    if needs_grad:
+        if raw32 is not raw:
+            raise ValueError('raw must be a contiguous float32 [B, n, 4] tensor to be differentiated')
+        return _Raw2Outputs.apply(raw32, z, dirs, noise, white)
+    return _raw2outputs_fwd(raw32, z, dirs, noise, white)
 
 
 def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, args) -> torch.Tensor:
