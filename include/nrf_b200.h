@@ -169,6 +169,10 @@ int nrf_render_launches(void);
 /* utils.py:127-131: x[n, c] -> out[n, c*(identity + 2*freqs)] */
 int nrf_positional_encoding(const float* x, int64_t n, int32_t c, int32_t freqs, int32_t identity, float* out,
                             void* stream);
+/* Backward of the encoding: grad_out[n, c*(identity + 2*freqs)] -> grad_x[n, c] (needed where the encoded quantity is itself
+ * a network output: the SMPL warp field's warped samples, models/smpl_nerf_pipeline.py:49-50). */
+int nrf_positional_encoding_backward(const float* x, const float* grad_out, int64_t n, int32_t c, int32_t freqs, int32_t identity,
+                                     float* grad_x, void* stream);
 /* utils.py:134-191: raw[B,n,4], z[B,n], dirs[B,n,3], optional noise[B,n] -> rgb[B,3], weights[B,n], alpha[B,n] */
 int nrf_raw2outputs(const float* raw, const float* z, const float* dirs, const float* noise, int64_t B, int32_t n,
                     int32_t white_background, float* rgb, float* weights, float* alpha, void* stream);

@@ -58,7 +58,7 @@ class RenderIO(C.Structure):
 EXPORTS = ['nrf_last_error', 'nrf_abi_version', 'nrf_device_supported', 'nrf_raynet_packed_bytes',
            'nrf_warpnet_packed_bytes', 'nrf_pack_raynet', 'nrf_pack_warpnet', 'nrf_render', 'nrf_render_launches',
            'nrf_raynet_ext_slots', 'nrf_ray_bias', 'nrf_generate_rays',
-           'nrf_positional_encoding', 'nrf_raw2outputs', 'nrf_raw2outputs_backward', 'nrf_sample_pdf', 'nrf_fine_sampling', 'nrf_searchsorted',
+           'nrf_positional_encoding', 'nrf_positional_encoding_backward', 'nrf_raw2outputs', 'nrf_raw2outputs_backward', 'nrf_sample_pdf', 'nrf_fine_sampling', 'nrf_searchsorted',
            'nrf_selftest_umma', 'nrf_selftest_umma2', 'nrf_bench_umma', 'nrf_bench_umma2']
 
 
@@ -119,6 +119,8 @@ def lib() -> C.CDLL:
     L.nrf_positional_encoding.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.nrf_raw2outputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nrf_positional_encoding_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                                   C.c_void_p]
     L.nrf_raw2outputs_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nrf_sample_pdf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,

@@ -35,6 +35,27 @@ __global__ void pe_kernel(const float* __restrict__ x, int64_t n, int c, int fre
   }
 }
 
+// backward of the encoding: g_x[i, j] = [identity] g[i, j] + sum_k 2^k (cos(2^k x) g_sin[k] - sin(2^k x) g_cos[k])
+__global__ void pe_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, int64_t n, int c, int freqs, int identity,
+                              float* __restrict__ gx) {
+  const int width = c * (2 * freqs + (identity ? 1 : 0));
+  const int64_t total = n * c;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = idx / c;
+    const int j = static_cast<int>(idx - row * c);
+    const float v = x[idx];
+    const float* gr = g + row * width;
+    float acc = identity ? gr[j] : 0.f;
+    const int base = identity ? c : 0;
+    for (int k = 0; k < freqs; ++k) {
+      const float f = static_cast<float>(1u << k), a = v * f;
+      acc = fmaf(f, fmaf(cosf(a), gr[base + k * 2 * c + j], -sinf(a) * gr[base + k * 2 * c + c + j]), acc);
+    }
+    gx[idx] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------ raw2outputs
 // one warp per ray; raw staged in smem as float4
 __global__ void raw2outputs_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ dirs,
@@ -590,4 +611,14 @@ extern "C" int nrf_raw2outputs_backward(const float* raw, const float* z, const 
                                                                                     grad_weights, grad_alpha, grad_raw);
   e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "raw2outputs_bwd_kernel launch");
+}
+
+extern "C" int nrf_positional_encoding_backward(const float* x, const float* grad_out, int64_t n, int32_t c, int32_t freqs, int32_t identity,
+                                                float* grad_x, void* stream) {
+  if (!x || !grad_out || !grad_x) { set_error("positional_encoding_backward: NULL argument"); return NRF_E_INVALID; }
+  if (n < 0 || c < 1 || freqs < 0 || freqs > 30) { set_error("positional_encoding_backward: bad shape n=%lld c=%d freqs=%d", (long long)n, c, freqs); return NRF_E_INVALID; }
+  if (n == 0) return NRF_OK;
+  pe_bwd_kernel<<<grid_for(n * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, grad_out, n, c, freqs, identity, grad_x);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "pe_bwd_kernel launch");
 }

@@ -40,15 +40,43 @@ class PositionalEncoder:
 
     def encode(self, coordinate: torch.Tensor) -> torch.Tensor:
         _need_cuda(coordinate, 'coordinate')
-        x = _f32(coordinate, 'coordinate', coordinate.device)
-        c = int(x.shape[-1])
-        n = x.numel() // c
-        out = torch.empty(*x.shape[:-1], c * self.output_dim, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            check(_lib.lib().nrf_positional_encoding(x.data_ptr(), n, c, self.number_frequencies,
-                                                     1 if self.include_identity else 0, out.data_ptr(),
-                                                     _stream(x.device)), 'nrf_positional_encoding')
-        return out
+        if torch.is_grad_enabled() and coordinate.requires_grad:
+            return _Encode.apply(coordinate, self.number_frequencies, 1 if self.include_identity else 0)
+        return _encode_fwd(coordinate, self.number_frequencies, 1 if self.include_identity else 0)
+
+
+def _encode_fwd(coordinate, freqs, identity):
+    x = _f32(coordinate, 'coordinate', coordinate.device)
+    c = int(x.shape[-1])
+    n = x.numel() // c
+    out = torch.empty(*x.shape[:-1], c * (identity + 2 * freqs), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().nrf_positional_encoding(x.data_ptr(), n, c, freqs, identity, out.data_ptr(), _stream(x.device)),
+              'nrf_positional_encoding')
+    return out
+
+
+class _Encode(torch.autograd.Function):
+    """Positional encoding with a native backward (nrf_positional_encoding_backward)."""
+
+    @staticmethod
+    def forward(ctx, x, freqs, identity):
+        ctx.save_for_backward(x)
+        ctx.cfg = (freqs, identity)
+        return _encode_fwd(x, freqs, identity)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        freqs, identity = ctx.cfg
+        xc = x.detach().contiguous().float()
+        g = g.contiguous().float()
+        c = int(xc.shape[-1])
+        gx = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            check(_lib.lib().nrf_positional_encoding_backward(xc.data_ptr(), g.data_ptr(), xc.numel() // c, c, freqs, identity,
+                                                              gx.data_ptr(), _stream(xc.device)), 'nrf_positional_encoding_backward')
+        return gx, None, None
 
 
 def _raw2outputs_fwd(raw, z, dirs, noise, white):

@@ -165,3 +165,18 @@ def test_raw2outputs_backward_matches_autograd_of_the_oracle(white, with_noise):
     # no gradient requested -> plain forward, no graph
     out = ops.raw2outputs(raw.to(DEV), z.to(DEV), dirs.to(DEV), args)
     assert not out[0].requires_grad
+
+
+@pytest.mark.parametrize('L,ident', [(10, False), (4, True)])
+def test_positional_encoding_backward(L, ident):
+    torch.manual_seed(6)
+    x = torch.rand(50, 7, 3) * 2 - 1
+    gout = torch.randn(50, 7, 3 * ((1 if ident else 0) + 2 * L))
+    x64 = x.double().requires_grad_(True)
+    enc = O.Encoder(L, ident)
+    enc.bands = enc.bands.double()
+    (enc.encode(x64) * gout.double()).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    (ops.PositionalEncoder(L, ident).encode(xg) * gout.to(DEV)).sum().backward()
+    want = x64.grad
+    assert float((xg.grad.cpu().double() - want).abs().max()) <= 2e-6 * float(want.abs().max())
