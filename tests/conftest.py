@@ -19,3 +19,15 @@ def reference():
     if not ref_import.available():
         pytest.skip('reference tree not present on this machine')
     return ref_import.load()
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _native_library_is_built():
+    """The GPU tests call through libnrf_b200.so; it normally travels with the tree (built by __graft_entry__.build()).
+    If it is missing or older than its sources, build it once here (nvcc is on the GPU box too) -- the product itself
+    never builds implicitly and never falls back."""
+    import torch
+    if torch.cuda.is_available():
+        from smpl_nerf_b200 import _lib
+        _lib.build()
+    yield
