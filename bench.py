@@ -366,11 +366,13 @@ def run_ours(a, w, rank, world, local_rank):
         line['psnr'] = heldout_psnr(dev, precision)
     if world == 1 and not a.no_cpu_baseline:
         batch = 256 if a.workload == 'cfg1' else 1024
-        rps, times = cpu_reference_rays_per_s(w, state, 3, batch, warmup=1)
+        n_cpu = 20 if batch * 20 <= 20480 else 10       # ~10 s of CPU work at ~2,000 rays/s
+        rps, times = cpu_reference_rays_per_s(w, state, n_cpu, batch, warmup=1)
         cores = os.cpu_count() or 1
         line['cpu_baseline'] = {'value': rps, 'unit': 'rays/s', 'cores': cores, 'kind': 'port', 'cpu': cpu_model(),
-                                'sample': f'median of 3 batches of {batch} rays of the same workload after 1 warm-up batch, '
-                                          f'{cores} torch threads'}
+                                'sample': f'median of {n_cpu} batches of {batch} rays of the same workload after 1 warm-up batch '
+                                          f'({sum(times):.1f} s of CPU time), {cores} torch threads; oracle/nerf_oracle.py = '
+                                          f'bit-identical restatement of the reference\'s PyTorch pipeline'}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
