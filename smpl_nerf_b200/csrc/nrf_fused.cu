@@ -713,7 +713,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
             if (L.flags & LF_SIGMA_HEAD) sigma_part = hl.sig;
             if (L.epi == EPI_RGB) ho = hl;
             if (L.flags & LF_WRITE_DIRPE) {
-              // the skip layer's MMAs are long done: aux can now take the per-sample direction encoding
+              // this layer was the last reader of the xyz encoding and its MMAs are done: aux takes the per-sample
+              // direction encoding now (the dir layer consumes it several layers later)
               write_encoding(aux_tile, c.row, c.cg, ux, uy, uz, net.dir_freqs, net.dir_identity, fast);
               epi_publish(sm, c, kSrcAux);
             }

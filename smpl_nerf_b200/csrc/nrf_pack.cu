@@ -83,7 +83,15 @@ int plan_raynet(const NrfRayNetDesc* d, NetPlan* p) {
     for (int j = 0; j < 4; ++j) L.ksrc[L.nk++] = static_cast<uint8_t>(j);
   }
   const bool dir_aux = d->use_directional_input && d->per_sample_dirs;
-  { Layer& L = add(kWidth, EPI_LINEAR, LF_SIGMA_HEAD | (dir_aux ? LF_WRITE_DIRPE : 0)); for (int j = 0; j < 4; ++j) L.ksrc[L.nk++] = static_cast<uint8_t>(j); }
+  if (dir_aux) {
+    // the per-sample direction encoding replaces the xyz encoding in the aux tile as soon as its last reader (the
+    // last skip layer, or the first layer) has finished its MMAs: written behind THAT layer's epilogue, where the
+    // epilogue warps have slack, instead of on the critical path in front of the dir layer
+    int last_aux = 0;
+    for (int i = 0; i < d->n_layers - 1; ++i) if (is_skip(i)) last_aux = i + 1;
+    p->layers[last_aux].flags |= LF_WRITE_DIRPE;
+  }
+  { Layer& L = add(kWidth, EPI_LINEAR, LF_SIGMA_HEAD); for (int j = 0; j < 4; ++j) L.ksrc[L.nk++] = static_cast<uint8_t>(j); }
   { Layer& L = add(kWidth / 2, EPI_LINEAR, dir_aux ? LF_AUX_WAIT : 0);
     for (int j = 0; j < 4; ++j) L.ksrc[L.nk++] = static_cast<uint8_t>(j);
     if (dir_aux) L.ksrc[L.nk++] = kSrcAux;
