@@ -488,6 +488,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
     float* hs_s = sm.misc + P.o_hs;          // sigma head weights [256] of the current net
     // head-partial exchange: a [column group][row] float4 table inside A chunk 3 (dead whenever it is used)
     float4* xchg = reinterpret_cast<float4*>(sm.base + kOffXchg) + c.row;   // slot of column group k: xchg[kTileRows * k] (lanes contiguous: no bank conflicts)
+    float4* xchg_w = xchg + 4 * kTileRows;                                   // second table (same dead chunk) for the warp-net head
     const uint32_t aux_tile = smem_u32(sm.base) + kOffAux;
     const int G = P.G, nc = P.n_coarse, nf = P.n_fine, na = P.n_all;
     // head biases live in registers (a dependent global load here sits on the tile-to-tile critical path)
@@ -667,12 +668,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
             epilogue_layer<true, false, true, false>(sm, P, P.warp, wf32, rbw, P.warp.layers[0], c, g, ho);
             // all four threads of a row need the full 256-column dot products: exchange the column-group
             // partials through smem and add them in the same order -> identical bits in every thread
-            xchg[kTileRows * c.cg] = make_float4(ho.h0, ho.h1, ho.h2, 0.f);
+            // (its own table, xchg_w: since the next tile's warp input is encoded early there is no CTA-wide barrier
+            //  any more between the tile-end reads of xchg and this write)
+            xchg_w[kTileRows * c.cg] = make_float4(ho.h0, ho.h1, ho.h2, 0.f);
             named_bar_sync(1, kEpiThreads);
             if (c.tid == 0) trace_ev(P, 35, c.layer_ctr);
             float w0, w1, w2;
             {
-              const float4 p0 = xchg[0], p1 = xchg[kTileRows], p2 = xchg[2 * kTileRows], p3 = xchg[3 * kTileRows];
+              const float4 p0 = xchg_w[0], p1 = xchg_w[kTileRows], p2 = xchg_w[2 * kTileRows], p3 = xchg_w[3 * kTileRows];
               w0 = __fadd_rn(__fadd_rn(__fadd_rn(p0.x, p1.x), __fadd_rn(p2.x, p3.x)), wb0);
               w1 = __fadd_rn(__fadd_rn(__fadd_rn(p0.y, p1.y), __fadd_rn(p2.y, p3.y)), wb1);
               w2 = __fadd_rn(__fadd_rn(__fadd_rn(p0.z, p1.z), __fadd_rn(p2.z, p3.z)), wb2);
