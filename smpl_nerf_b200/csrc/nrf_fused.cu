@@ -730,8 +730,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
             // the four threads of a row split the per-sample half of raw2outputs: thread cg owns component cg of
             // (rgb_raw[3], sigma_raw) -- sums the four partials in a fixed order, adds the bias, applies the
             // sigmoid (cg < 3) or the alpha formula (cg = 3) and writes its scalar of raw4[R]
-            const float* px = reinterpret_cast<const float*>(xchg) + c.cg;
-            const float q0 = px[0], q1 = px[4 * kTileRows], q2 = px[8 * kTileRows], q3 = px[12 * kTileRows];
+            const float* qx = reinterpret_cast<const float*>(xchg) + c.cg;
+            const float q0 = qx[0], q1 = qx[4 * kTileRows], q2 = qx[8 * kTileRows], q3 = qx[12 * kTileRows];
             const float bias = c.cg == 0 ? hb0 : (c.cg == 1 ? hb1 : (c.cg == 2 ? hb2 : sb));
             const float val = __fadd_rn(__fadd_rn(__fadd_rn(q0, q1), __fadd_rn(q2, q3)), bias);
             if (valid) {
@@ -751,7 +751,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
               reinterpret_cast<float*>(raw4 + R)[c.cg] = out;
             }
           }
-          // the exchange slots are next written behind an mbarrier every warp arrives on after this point
+          // (xchg is next written at the next tile's end, or as part of activation chunk 3 by the first layer's epilogue:
+          //  both sit behind CTA-wide publish barriers that every warp reaches only after these reads)
         }
         named_bar_sync(1, kEpiThreads);   // raw4 of every tile of this pass is complete
         if (c.tid == 0) trace_ev(P, 40, c.layer_ctr);
