@@ -97,6 +97,25 @@ def test_no_cpu_fallback():
         pipe(data)
 
 
+def test_ops_and_ray_generation_refuse_cpu_tensors():
+    import numpy as np
+    from types import SimpleNamespace
+    from smpl_nerf_b200 import ops, rays, scene
+    args = SimpleNamespace(sigma_noise_std=0., white_background=1, number_fine_samples=8)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.PositionalEncoder(4, False).encode(torch.zeros(3, 3))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.raw2outputs(torch.zeros(2, 8, 4), torch.zeros(2, 8), torch.zeros(2, 8, 3), args)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.sample_pdf(torch.zeros(2, 7), torch.zeros(2, 6), args)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.searchsorted(torch.zeros(1, 4), torch.zeros(1, 2))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        rays.generate_view(4, 4, scene.sphere_pose(0., 0.), device='cpu')
+    with pytest.raises(ValueError):
+        rays.generate_view(4, 4, np.eye(3), device='cuda:0')
+
+
 def test_product_does_not_import_oracle():
     """The product package must never reach into oracle/ (only tests, smoke() and bench's CPU legs may)."""
     pkg = os.path.join(ROOT, 'smpl_nerf_b200')
