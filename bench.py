@@ -14,8 +14,12 @@ Printed JSON line (rank 0):
              inputs and D2H of rgb_fine inside the timed region
   roofline   algorithmic MLP FLOPs (2 x MACs of the reference's nn.Linear layers, un-folded,
              un-hoisted) per launch / average kernel duration, against the measured bf16 peak
-  cpu_baseline  the oracle port of the reference's PyTorch-CPU path on this box's host cores
+  cpu_baseline  the oracle port of the reference's PyTorch-CPU path on this box's host cores (~10 s sample)
+  psnr       held-out view of the briefly trained checkpoint (tests/golden/trained_nerf_d4.ckpt): engine vs ground
+             truth, the reference's own render vs ground truth, engine vs reference render
 `--impl reference` times that CPU path alone (rank 0 only), on bounded samples of the same workload.
+Other workloads (--workload): cfg1 = configs[0], cfg3 = configs[2] (256x256, 10 poses), cfg4 = configs[3] (AppendToNerf),
+cfg5 = configs[4] (ONE 512x512 frame sharded over the ranks: strong scaling), nerf, paper (AppendSmplParams).
 """
 import argparse
 import json
