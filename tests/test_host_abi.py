@@ -116,6 +116,31 @@ def test_ops_and_ray_generation_refuse_cpu_tensors():
         rays.generate_view(4, 4, np.eye(3), device='cuda:0')
 
 
+def test_render_argument_errors_are_reported_without_a_gpu(L):
+    """nrf_render validates its descriptors before it touches the device: NRF_E_INVALID (-1) + a message."""
+    c, f, w, pe, de, he = O.build_nets('smpl', 0)
+    dc = engine.raynet_desc(c, pe, de, True)
+    io = _lib.RenderIO()
+    pipe = _lib.PipelineDesc()
+    pipe.kind, pipe.n_coarse, pipe.n_fine, pipe.run_fine = 1, 64, 128, 1
+    blob = C.c_void_p(1024)            # aligned dummy address: never dereferenced on these paths
+    assert L.nrf_render(None, C.byref(dc), blob, None, None, None, None, C.byref(io), 8, 0, None) == -1
+    assert L.nrf_render(C.byref(pipe), C.byref(dc), blob, None, None, None, None, C.byref(io), -1, 0, None) == -1
+    assert b'n_rays' in L.nrf_last_error()
+    assert L.nrf_render(C.byref(pipe), C.byref(dc), blob, None, None, None, None, C.byref(io), 0, 0, None) == 0     # empty batch: nothing to do
+    assert L.nrf_render(C.byref(pipe), C.byref(dc), blob, None, None, None, None, C.byref(io), 8, 0, None) == -1
+    assert b'fine net' in L.nrf_last_error()
+    pipe.run_fine = 0
+    assert L.nrf_render(C.byref(pipe), C.byref(dc), blob, None, None, None, None, C.byref(io), 8, 0, None) == -1
+    assert b'warp net' in L.nrf_last_error()
+    pipe.kind = 7
+    assert L.nrf_render(C.byref(pipe), C.byref(dc), blob, None, None, None, None, C.byref(io), 8, 0, None) == -1
+    assert b'kind' in L.nrf_last_error()
+    assert L.nrf_ray_bias(C.byref(dc), None, 0, None, 8, None, None, None) == -1          # not an ext_pose_bias net
+    assert b'ext_pose_bias' in L.nrf_last_error()
+    assert L.nrf_generate_rays(0, 4, 1.0, None, None, None, None, 8, None, None, None, None, None) == -1
+
+
 def test_product_does_not_import_oracle():
     """The product package must never reach into oracle/ (only tests, smoke() and bench's CPU legs may)."""
     pkg = os.path.join(ROOT, 'smpl_nerf_b200')
