@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NRF_ABI_VERSION 3
+#define NRF_ABI_VERSION 4
 
 enum {
   NRF_OK = 0,
@@ -65,6 +65,10 @@ typedef struct NrfRayNetDesc {
   int32_t ext_pose_bias;         /* 1: the contribution of the A additional inputs to the first and the skip layers
                                     arrives precomputed per ray (nrf_ray_bias -> NrfRenderIO.ray_bias_*); lifts the
                                     A <= 64 limit (AppendSmplParamsPipeline: A = 69 or 1380)                       */
+  int32_t fold_linear;           /* 1: fold additional_linear_layer (models/render_ray_net.py:51, no activation behind it) into its
+                                    two consumers at pack time -- sigma_out_layer and directional_input (:52-57) -- as fp64
+                                    products rounded once to fp32: W_dir' = W_dir[:, :W] W_add, w_sigma' = w_sigma W_add (biases
+                                    alike).  Removes one 256x256 layer per sample (-10.8% MACs); fp32-level reassociation. */
 } NrfRayNetDesc;
 
 /* WarpFieldNet (models/warp_field_net.py:8-15): Linear(positions_dim + pose_dim -> width), ReLU,

@@ -126,14 +126,14 @@ def composite(raw: torch.Tensor, z: torch.Tensor, dirs: torch.Tensor, *, white_b
     it as an argument so both sides of a parity test consume the same draw.
     """
     delta = z[..., 1:] - z[..., :-1]
-    far = torch.tensor([1e10], dtype=z.dtype).expand(delta[..., :1].shape)
+    far = torch.tensor([1e10], dtype=z.dtype, device=z.device).expand(delta[..., :1].shape)
     delta = torch.cat([delta, far], -1)
     delta = delta * torch.norm(dirs, dim=-1)
     colour = torch.sigmoid(raw[..., :3])
     sig = raw[..., 3] if noise is None else raw[..., 3] + noise
     alpha = 1. - torch.exp(-torch.relu(sig) * delta)
     keep = 1. - alpha + 1e-10
-    ones = torch.ones(keep.shape[:-1], dtype=z.dtype).unsqueeze(-1)
+    ones = torch.ones(keep.shape[:-1], dtype=z.dtype, device=z.device).unsqueeze(-1)
     trans = torch.cumprod(torch.cat([ones, keep[..., :-1]], -1), -1)       # exclusive product
     weights = alpha * trans
     rgb = torch.sum(weights[..., None] * colour, -2)
@@ -152,7 +152,7 @@ def inverse_cdf(bins: torch.Tensor, weights: torch.Tensor, n_fine: int) -> torch
     pdf = w / torch.sum(w, -1, keepdim=True)
     cdf = torch.cumsum(pdf, -1)
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
-    u = torch.linspace(0., 1., steps=n_fine, dtype=torch.float32).to(cdf.dtype)
+    u = torch.linspace(0., 1., steps=n_fine, dtype=torch.float32).to(device=cdf.device, dtype=cdf.dtype)
     u = u.expand(list(cdf.shape[:-1]) + [n_fine]).contiguous()
     idx = torch.searchsorted(cdf, u, right=True)           # == torchsearchsorted side='right'
     lo = torch.clamp(idx - 1, min=0)

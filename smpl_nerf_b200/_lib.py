@@ -21,6 +21,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC', '-shared']
 
 NRF_MAX_SKIPS = 4
+ABI_VERSION = 4          # NRF_ABI_VERSION of include/nrf_b200.h this binding was written against
 KIND = {'nerf': 0, 'smpl': 1, 'append': 2, 'append_full': 2}   # append_full = append + externally hoisted 69-parameter pose
 
 
@@ -30,7 +31,7 @@ class RayNetDesc(C.Structure):
                 ('use_directional_input', C.c_int32), ('n_skips', C.c_int32),
                 ('skips', C.c_int32 * NRF_MAX_SKIPS), ('pos_freqs', C.c_int32), ('pos_identity', C.c_int32),
                 ('dir_freqs', C.c_int32), ('dir_identity', C.c_int32), ('per_sample_dirs', C.c_int32),
-                ('ext_pose_bias', C.c_int32)]
+                ('ext_pose_bias', C.c_int32), ('fold_linear', C.c_int32)]
 
 
 class WarpNetDesc(C.Structure):
@@ -133,7 +134,7 @@ def lib() -> C.CDLL:
     L.nrf_bench_umma2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     L.nrf_selftest_umma2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nrf_bench_umma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
-    if L.nrf_abi_version() != 3:
+    if L.nrf_abi_version() != ABI_VERSION:
         raise RuntimeError('libnrf_b200.so ABI version mismatch; rebuild')
     _lib = L
     return L

@@ -50,10 +50,10 @@ constexpr uint32_t kSmemLimit = 232448;            // 227 KB opt-in maximum per 
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 64 + kEpiThreads;
-constexpr int kRayVec = 8 + kMaxRayFeat + 32;      // unit direction[3], raw pose pair[2]
+constexpr int kRayVec = 8 + kMaxRayFeat + kChunkK; // offset of unit direction[3], raw pose pair[2]: behind o, d, |d|, valid (8), pose feats (<= kMaxRayFeat), dir feats (<= kChunkK, what plan_raynet admits)
 constexpr int kRayFloats = kRayVec + 8;
 constexpr int kRayScratchFloats = 2 * kMaxFineRows + (kTileRows + 16) + kTileRows + kMaxFineRows + kTeamScratch;   // tf, tt, cdf, pdf, z_samples, team partials of one ray
-static_assert((kTileRows / 16) * kRayScratchFloats * 4 <= 2 * 2 * 16384, "per-ray scratch must stay inside activation chunks 0 and 1 (chunk 2 stages the warp encoding, chunk 3 the exchange slots)");            // o[3] d[3] |d| valid | pose feats[64] | dir feats[32] | unit d, pose
+static_assert((kTileRows / 16) * kRayScratchFloats * 4 <= 2 * 2 * 16384, "per-ray scratch must stay inside activation chunks 0 and 1 (chunk 2 stages the warp encoding, chunk 3 the exchange slots)");            // o[3] d[3] |d| valid | pose feats[64] | dir feats[64] | unit d, pose
 
 // barrier slots inside the misc area (8 bytes each)
 enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC = 2 * kMaxStages, BAR_AREADY = 2 * kMaxStages + 2,
@@ -402,8 +402,10 @@ __device__ __forceinline__ void epilogue_layer(const Smem& sm, const RenderParam
 
 __device__ __forceinline__ void epilogue_dispatch(const Smem& sm, const RenderParams& P, const NetPlan& net, const float* f32,
                                                   const float* rb_base, const Layer& L, EpiCtx& c, int g, HeadOut& ho) {
-  if (L.epi == EPI_RELU) epilogue_layer<true, true, false, false>(sm, P, net, f32, rb_base, L, c, g, ho);
-  else if (L.epi == EPI_LINEAR) {
+  if (L.epi == EPI_RELU) {
+    if (L.flags & LF_SIGMA_HEAD) epilogue_layer<true, true, false, true>(sm, P, net, f32, rb_base, L, c, g, ho);   // folded additional_linear_layer
+    else epilogue_layer<true, true, false, false>(sm, P, net, f32, rb_base, L, c, g, ho);
+  } else if (L.epi == EPI_LINEAR) {
     if (L.flags & LF_SIGMA_HEAD) epilogue_layer<false, true, false, true>(sm, P, net, f32, rb_base, L, c, g, ho);
     else epilogue_layer<false, true, false, false>(sm, P, net, f32, rb_base, L, c, g, ho);
   } else epilogue_layer<true, false, true, false>(sm, P, net, f32, rb_base, L, c, g, ho);
@@ -775,8 +777,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
             composite_ray_activated(raw4 + g * n, n, P.white_bkgd, rgb_dst, w_dst, tf, tt, ts, tm);
             if (pass == 0 && P.run_fine) {
               float* zfg = zf + g * na;
-              if (P.io.z_all_in && valid) {
-                for (int i = tm.t; i < na; i += tm.T) zfg[i] = P.io.z_all_in[ri * na + i];
+              if (P.io.z_all_in) {      // teacher forcing; padding rays get a sorted ramp (nothing of theirs is stored)
+                for (int i = tm.t; i < na; i += tm.T) zfg[i] = valid ? P.io.z_all_in[ri * na + i] : static_cast<float>(i);
                 tm.sync();
               } else {
                 sample_ray(&raw4[g * nc].w, 4, zc + g * nc, nc, nf, u_s, cdfx, pd, zs, zfg,

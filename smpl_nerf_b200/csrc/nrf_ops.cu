@@ -560,7 +560,7 @@ extern "C" int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, 
     RayBiasJob& j = t.j[L.ext_idx];
     // layer 0 = positions_pose_input: columns [pose(A) | xyz(P)]; layer li >= 1 = positional_net[li-1] with a skip:
     // columns [activations(256) | pose(A) | xyz(P)]   (models/render_ray_net.py:22-31,43-49)
-    const int pidx = li == 0 ? 0 : 2 * li;
+    const int pidx = L.pidx;
     if (!params[pidx] || !params[pidx + 1]) { set_error("ray_bias: parameter %d is NULL", pidx); return NRF_E_INVALID; }
     if ((reinterpret_cast<uintptr_t>(params[pidx + 1]) & 15u) != 0) { set_error("ray_bias: bias tensors must be 16-byte aligned"); return NRF_E_INVALID; }
     j.w = params[pidx]; j.bias = params[pidx + 1];

@@ -62,9 +62,12 @@ int plan_raynet(const NrfRayNetDesc* d, NetPlan* p) {
   p->dir_freqs = d->dir_freqs; p->dir_identity = d->dir_identity;
   uint32_t f = 0;   // float cursor in the fp32 section
   int slots = 0, n = 0, n_ext = 0;
-  auto add = [&](int n_out, int epi, int flags) -> Layer& {
+  const int nl = d->n_layers;
+  const bool fold = d->fold_linear != 0;
+  auto add = [&](int n_out, int epi, int flags, int role, int pidx) -> Layer& {
     Layer& L = p->layers[n++];
     L.n_out = static_cast<uint16_t>(n_out); L.epi = static_cast<uint8_t>(epi); L.flags = static_cast<uint8_t>(flags);
+    L.role = static_cast<uint8_t>(role); L.pidx = static_cast<uint8_t>(pidx);
     L.ray_slot = -1; L.ray_src = RAY_NONE; L.ray_k = 0; L.nk = 0;
     L.bias_ofs = f; f = align4(f + n_out);
     return L;
@@ -76,9 +79,10 @@ int plan_raynet(const NrfRayNetDesc* d, NetPlan* p) {
     L.rayw_ofs = f; f = align4(f + k * L.n_out);
   };
   // first layer: xyz encoding from aux (+ pose features as a per-ray bias)
-  { Layer& L = add(kWidth, EPI_RELU, LF_AUX_WAIT); L.ksrc[L.nk++] = kSrcAux; if (A > 0) add_ray(L, RAY_POSE, A); }
+  { Layer& L = add(kWidth, EPI_RELU, LF_AUX_WAIT, ROLE_FIRST, 0); L.ksrc[L.nk++] = kSrcAux; if (A > 0) add_ray(L, RAY_POSE, A); }
   for (int i = 0; i < d->n_layers - 1; ++i) {
-    Layer& L = add(kWidth, EPI_RELU, 0);
+    // folded: the sigma head reads the last trunk layer's output directly (through w_sigma W_add)
+    Layer& L = add(kWidth, EPI_RELU, (fold && i == d->n_layers - 2) ? LF_SIGMA_HEAD : 0, ROLE_TRUNK, 2 * (i + 1));
     if (is_skip(i)) { L.ksrc[L.nk++] = kSrcAux; if (A > 0) add_ray(L, RAY_POSE, A); }
     for (int j = 0; j < 4; ++j) L.ksrc[L.nk++] = static_cast<uint8_t>(j);
   }
@@ -91,16 +95,18 @@ int plan_raynet(const NrfRayNetDesc* d, NetPlan* p) {
     for (int i = 0; i < d->n_layers - 1; ++i) if (is_skip(i)) last_aux = i + 1;
     p->layers[last_aux].flags |= LF_WRITE_DIRPE;
   }
-  { Layer& L = add(kWidth, EPI_LINEAR, LF_SIGMA_HEAD); for (int j = 0; j < 4; ++j) L.ksrc[L.nk++] = static_cast<uint8_t>(j); }
-  { Layer& L = add(kWidth / 2, EPI_LINEAR, dir_aux ? LF_AUX_WAIT : 0);
+  if (!fold) { Layer& L = add(kWidth, EPI_LINEAR, LF_SIGMA_HEAD, ROLE_LINEAR, 2 * nl); for (int j = 0; j < 4; ++j) L.ksrc[L.nk++] = static_cast<uint8_t>(j); }
+  { Layer& L = add(kWidth / 2, EPI_LINEAR, dir_aux ? LF_AUX_WAIT : 0, ROLE_DIR, 2 * nl + 4);
     for (int j = 0; j < 4; ++j) L.ksrc[L.nk++] = static_cast<uint8_t>(j);
     if (dir_aux) L.ksrc[L.nk++] = kSrcAux;
     else if (d->use_directional_input) add_ray(L, RAY_DIR, D); }
-  { Layer& L = add(kWidth / 2, EPI_RGB, 0); L.ksrc[L.nk++] = 0; L.ksrc[L.nk++] = 1; }
+  { Layer& L = add(kWidth / 2, EPI_RGB, 0, ROLE_RGB, 2 * nl + 6); L.ksrc[L.nk++] = 0; L.ksrc[L.nk++] = 1; }
   if (slots > kMaxRaySlots) { set_error("too many per-ray bias layers (%d > %d): at most one skip layer when additional_input_dim > 0", slots, kMaxRaySlots); return NRF_E_INVALID; }
   p->n_layers = n; p->n_ray_slots = slots; p->n_ext_slots = n_ext;
   p->sigma_ofs = f; f = align4(f + kWidth + 1);
   p->head_ofs = f;  f = align4(f + 3 * (kWidth / 2) + 3);
+  p->folded = fold ? 1 : 0;
+  if (fold) { p->fold_ofs = f; f = align4(f + (kWidth / 2) * (kWidth + (d->use_directional_input ? D : 0)) + kWidth / 2 + kWidth + 1); }
   finish_plan(p, f);
   return NRF_OK;
 }
@@ -116,7 +122,7 @@ int plan_warpnet(const NrfWarpNetDesc* d, NetPlan* p) {
   uint32_t f = 0;
   Layer& L = p->layers[0];
   // its one K-chunk (the xyz encoding) is staged in activation chunk 2, not in the aux tile: see warp_encode in nrf_fused.cu
-  L.n_out = kWidth; L.epi = EPI_WARP; L.flags = 0; L.nk = 1; L.ksrc[0] = 2;
+  L.n_out = kWidth; L.epi = EPI_WARP; L.flags = 0; L.nk = 1; L.ksrc[0] = 2; L.role = ROLE_WARP; L.pidx = 0;
   L.bias_ofs = f; f = align4(f + kWidth);
   L.ray_slot = -1;
   if (d->pose_dim > 0) { L.ray_src = RAY_POSE; L.ray_k = static_cast<uint16_t>(d->pose_dim); L.ray_slot = 0; L.rayw_ofs = f; f = align4(f + d->pose_dim * kWidth); }
@@ -173,9 +179,39 @@ __global__ void pack_f32_kernel(const __grid_constant__ CopyTable t, float* __re
   }
 }
 
-static int launch_pack(const NetPlan& plan, PackTable& pt, CopyTable& ct, void* packed, cudaStream_t s) {
+// additional_linear_layer folded into its two consumers (models/render_ray_net.py:51-57: no activation in between):
+//   Wdir'[n, k] = sum_j Wdir[n, j] Wadd[j, k]   (k < 256; the direction columns are copied)     bdir' = bdir + Wdir[:, :256] badd
+//   wsig'[k]    = sum_j wsig[j] Wadd[j, k]                                                       bsig' = bsig + wsig . badd
+// fp64 accumulation, rounded ONCE to fp32.  out: Wdir'[half][ld] | bdir'[half] | wsig'[256] | bsig'[1]
+__global__ void fold_linear_kernel(const float* __restrict__ w_add, const float* __restrict__ b_add, const float* __restrict__ w_sig,
+                                   const float* __restrict__ b_sig, const float* __restrict__ w_dir, const float* __restrict__ b_dir,
+                                   int ld, float* __restrict__ out) {
+  constexpr int half = kWidth / 2;
+  float* wd = out; float* bd = out + half * ld; float* ws = bd + half; float* bs = ws + kWidth;
+  const int total = (half + 1) * kWidth;              // rows 0..half-1: Wdir', row half: wsig'
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int n = idx / kWidth, k = idx - n * kWidth;
+    const float* row = n < half ? w_dir + static_cast<size_t>(n) * ld : w_sig;
+    double acc = 0.0;
+    for (int j = 0; j < kWidth; ++j) acc = fma(static_cast<double>(row[j]), static_cast<double>(w_add[j * kWidth + k]), acc);
+    if (n < half) wd[n * ld + k] = static_cast<float>(acc); else ws[k] = static_cast<float>(acc);
+  }
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < half * (ld - kWidth); idx += gridDim.x * blockDim.x) {
+    const int n = idx / (ld - kWidth), k = kWidth + idx % (ld - kWidth);
+    wd[n * ld + k] = w_dir[static_cast<size_t>(n) * ld + k];
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n <= half; n += gridDim.x * blockDim.x) {
+    const float* row = n < half ? w_dir + static_cast<size_t>(n) * ld : w_sig;
+    double acc = n < half ? static_cast<double>(b_dir[n]) : static_cast<double>(b_sig[0]);
+    for (int j = 0; j < kWidth; ++j) acc = fma(static_cast<double>(row[j]), static_cast<double>(b_add[j]), acc);
+    if (n < half) bd[n] = static_cast<float>(acc); else bs[0] = static_cast<float>(acc);
+  }
+}
+
+static int launch_pack(const NetPlan& plan, PackTable& pt, CopyTable& ct, void* packed, cudaStream_t s, bool zero = true) {
   if ((reinterpret_cast<uintptr_t>(packed) & 1023u) != 0) { set_error("packed buffer must be 1024-byte aligned"); return NRF_E_INVALID; }
-  cudaError_t e = cudaMemsetAsync(packed, 0, plan.total_bytes, s);
+  cudaError_t e = cudaSuccess;
+  if (zero) e = cudaMemsetAsync(packed, 0, plan.total_bytes, s);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(packed)");
   pack_stream_kernel<<<dim3(pt.n, 4), 256, 0, s>>>(pt, static_cast<uint8_t*>(packed));
   pack_f32_kernel<<<ct.n, 256, 0, s>>>(ct, reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + plan.f32_ofs));
@@ -222,20 +258,33 @@ extern "C" int nrf_pack_raynet(const NrfRayNetDesc* d, const float* const* param
   auto copy = [&](const float* src, int rows, int cols, int ld, int col0, int tr, uint32_t dst) {
     CopyJob& j = ct.j[ct.n++]; j.src = src; j.rows = rows; j.cols = cols; j.ld = ld; j.col0 = col0; j.transpose = tr; j.dst = dst;
   };
+  float* f32 = reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + plan.f32_ofs);
+  const int ld_dir = d->use_directional_input ? kWidth + D : kWidth;
+  const float* w_dir = params[2 * nl + 4], *b_dir = params[2 * nl + 5], *w_sig = params[2 * nl + 2], *b_sig = params[2 * nl + 3];
+  bool zeroed = false;
+  if (plan.folded) {
+    // folded tensors live in the blob's fp32 section; the pack kernels below read them from there (same stream)
+    if ((reinterpret_cast<uintptr_t>(packed) & 1023u) != 0) { set_error("packed buffer must be 1024-byte aligned"); return NRF_E_INVALID; }
+    cudaError_t e = cudaMemsetAsync(packed, 0, plan.total_bytes, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(packed)");
+    zeroed = true;
+    float* fo = f32 + plan.fold_ofs;
+    fold_linear_kernel<<<64, 256, 0, static_cast<cudaStream_t>(stream)>>>(params[2 * nl], params[2 * nl + 1], w_sig, b_sig, w_dir, b_dir, ld_dir, fo);
+    w_dir = fo; b_dir = fo + (kWidth / 2) * ld_dir; w_sig = b_dir + kWidth / 2; b_sig = w_sig + kWidth;
+  }
   for (int li = 0; li < plan.n_layers; ++li) {
     const Layer& L = plan.layers[li];
     // which nn.Linear feeds this MMA layer, and where its input column blocks start
-    int pidx, ld, act0 = 0, aux0 = 0, ray0 = 0, aux_fr = d->pos_freqs, aux_id = d->pos_identity;
-    if (li == 0) { pidx = 0; ld = A + P; ray0 = 0; aux0 = A; }
-    else if (li <= nl - 1) {
-      pidx = 2 * li;
+    int ld, act0 = 0, aux0 = 0, ray0 = 0, aux_fr = d->pos_freqs, aux_id = d->pos_identity;
+    const float* W = params[L.pidx];
+    const float* b = params[L.pidx + 1];
+    if (L.role == ROLE_FIRST) { ld = A + P; ray0 = 0; aux0 = A; }
+    else if (L.role == ROLE_TRUNK) {
       const bool skip = (L.ksrc[0] == kSrcAux);
       ld = skip ? kWidth + A + P : kWidth; ray0 = kWidth; aux0 = kWidth + A;
-    } else if (li == nl) { pidx = 2 * nl; ld = kWidth; }
-    else if (li == nl + 1) { pidx = 2 * nl + 4; ld = d->use_directional_input ? kWidth + D : kWidth; ray0 = kWidth; aux0 = kWidth; aux_fr = d->dir_freqs; aux_id = d->dir_identity; }
-    else { pidx = 2 * nl + 6; ld = kWidth / 2; }
-    const float* W = params[pidx];
-    const float* b = params[pidx + 1];
+    } else if (L.role == ROLE_LINEAR) { ld = kWidth; }
+    else if (L.role == ROLE_DIR) { W = w_dir; b = b_dir; ld = ld_dir; ray0 = kWidth; aux0 = kWidth; aux_fr = d->dir_freqs; aux_id = d->dir_identity; }
+    else { ld = kWidth / 2; }
     for (int kc = 0; kc < L.nk; ++kc) {
       PackChunk& c = pt.c[pt.n++];
       c.w = W; c.ld = ld; c.n_out = L.n_out; c.dst = L.stream_ofs + static_cast<uint32_t>(kc) * 4u * (L.n_out / 2u) * 128u;
@@ -245,11 +294,12 @@ extern "C" int nrf_pack_raynet(const NrfRayNetDesc* d, const float* const* param
     copy(b, 1, L.n_out, L.n_out, 0, 0, L.bias_ofs);
     if (L.ray_src == RAY_POSE || L.ray_src == RAY_DIR) copy(W, L.n_out, L.ray_k, ld, ray0, 1, L.rayw_ofs);
   }
-  copy(params[2 * nl + 2], 1, kWidth, kWidth, 0, 0, plan.sigma_ofs);
-  copy(params[2 * nl + 3], 1, 1, 1, 0, 0, plan.sigma_ofs + kWidth);
+  copy(w_sig, 1, kWidth, kWidth, 0, 0, plan.sigma_ofs);
+  copy(b_sig, 1, 1, 1, 0, 0, plan.sigma_ofs + kWidth);
   copy(params[2 * nl + 8], 3, kWidth / 2, kWidth / 2, 0, 0, plan.head_ofs);
   copy(params[2 * nl + 9], 1, 3, 3, 0, 0, plan.head_ofs + 3 * (kWidth / 2));
-  return launch_pack(plan, pt, ct, packed, static_cast<cudaStream_t>(stream));
+  (void)f32;
+  return launch_pack(plan, pt, ct, packed, static_cast<cudaStream_t>(stream), !zeroed);
 }
 
 extern "C" int nrf_pack_warpnet(const NrfWarpNetDesc* d, const float* const* params, int n_params, void* packed, void* stream) {

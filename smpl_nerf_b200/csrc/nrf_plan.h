@@ -60,7 +60,10 @@ struct Layer {
   uint8_t epi;          // EpiKind
   uint8_t flags;        // LayerFlags
   uint8_t ext_idx;      // RAY_POSE_EXT: index of this layer's vector inside a ray's [n_ext][256] block
+  uint8_t role;         // LayerRole: which nn.Linear of the reference net feeds this MMA layer
+  uint8_t pidx;         // index of that nn.Linear's weight in the state_dict-ordered parameter list (bias = pidx + 1)
 };
+enum LayerRole : uint8_t { ROLE_FIRST = 0, ROLE_TRUNK = 1, ROLE_LINEAR = 2, ROLE_DIR = 3, ROLE_RGB = 4, ROLE_WARP = 5 };
 
 struct NetPlan {
   int32_t n_layers;
@@ -73,6 +76,8 @@ struct NetPlan {
   uint32_t sigma_ofs;     // float offset: wsigma[256], bsigma[1]
   int32_t in_freqs, in_identity;    // encoding of xyz that feeds the aux K-chunk
   int32_t dir_freqs, dir_identity;  // encoding of the view direction
+  int32_t folded;         // 1: additional_linear_layer is folded into the sigma head and directional_input at pack time
+  uint32_t fold_ofs;      // float offset (fp32 section) of the folded tensors: Wdir'[128][256 + D], bdir'[128], wsigma'[256], bsigma'[1]
   Layer layers[kMaxLayers];
 };
 

@@ -26,7 +26,12 @@ def _enc_cfg(enc):
     return int(enc.number_frequencies), 1 if enc.include_identity else 0
 
 
-def raynet_desc(net, pos_enc, dir_enc, per_sample_dirs: bool, ext_pose_bias: bool = False) -> RayNetDesc:
+#: fold additional_linear_layer into the sigma head and directional_input at pack time (render_ray_net.py:51-57 has no
+#: activation between them): one 256x256 layer less per sample, fp32-level reassociation.  On in both precision modes.
+FOLD_LINEAR = True
+
+
+def raynet_desc(net, pos_enc, dir_enc, per_sample_dirs: bool, ext_pose_bias: bool = False, fold: Optional[bool] = None) -> RayNetDesc:
     """Read the RenderRayNet hyper-parameters off the module (attribute names: render_ray_net.py:11-17)."""
     d = RayNetDesc()
     d.n_layers, d.width = int(net.n_layers), int(net.width)
@@ -44,6 +49,7 @@ def raynet_desc(net, pos_enc, dir_enc, per_sample_dirs: bool, ext_pose_bias: boo
     d.dir_freqs, d.dir_identity = _enc_cfg(dir_enc)
     d.per_sample_dirs = 1 if per_sample_dirs else 0
     d.ext_pose_bias = 1 if ext_pose_bias else 0
+    d.fold_linear = 1 if (FOLD_LINEAR if fold is None else fold) else 0
     return d
 
 
@@ -61,6 +67,17 @@ class _Packed:
 
 
 _cache: "weakref.WeakKeyDictionary[torch.nn.Module, _Packed]" = weakref.WeakKeyDictionary()
+
+
+def invalidate(net=None) -> None:
+    """Drop the packed copy of ``net`` (or of every net).  The cache key is every parameter's (data_ptr, _version):
+    optimizer steps and load_state_dict bump the version, but in-place writes through ``p.data`` (``p.data.copy_()``, some
+    EMA code) do NOT -- call this after such an update.  The packed buffer is re-filled in place on the stream of the next
+    render call; renders of the same net from several streams at once must be ordered by the caller."""
+    if net is None:
+        _cache.clear()
+    else:
+        _cache.pop(net, None)
 
 
 def _params(net, device) -> Sequence[torch.Tensor]:
@@ -128,7 +145,7 @@ def _f32(t: torch.Tensor, name: str, device, shape=None) -> torch.Tensor:
 
 def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_enc, pose_enc, data,
            *, taps: bool = False, z_all_in: Optional[torch.Tensor] = None, noise=None, n_sms: int = 0,
-           precision: int = 0, trace_cap: int = 0) -> Dict[str, torch.Tensor]:
+           precision: int = 0, trace_cap: int = 0, fold: Optional[bool] = None) -> Dict[str, torch.Tensor]:
     """One fused forward.  ``data`` is the reference's per-batch list
     [ray_samples, ray_translation, ray_direction, z_vals, (goal_pose,) rgb]; returns a dict of
     freshly allocated fp32 CUDA tensors (see NrfRenderIO in include/nrf_b200.h)."""
@@ -157,11 +174,11 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
 
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
-        dc = raynet_desc(model_coarse, pos_enc, dir_enc, smpl, full_pose)
+        dc = raynet_desc(model_coarse, pos_enc, dir_enc, smpl, full_pose, fold)
         pc = packed(model_coarse, dc, device, stream)
         df, pf = None, None
         if run_fine:
-            df = raynet_desc(model_fine, pos_enc, dir_enc, smpl, full_pose)
+            df = raynet_desc(model_fine, pos_enc, dir_enc, smpl, full_pose, fold)
             pf = packed(model_fine, df, device, stream)
         pipe = PipelineDesc()
         pipe.kind = KIND[kind]

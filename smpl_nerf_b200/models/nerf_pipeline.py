@@ -19,8 +19,11 @@ class NerfPipeline(SmplPipeline):
 
     #: set to True to read the kernel's range flag after every call (costs one device synchronisation per call)
     strict_range = False
+    #: 0 = parity (fp16 hi/lo split, 3 MMA passes, every parity claim), 1 = fast (one fp16 pass; misses the 1e-4 alpha bar)
+    precision = 0
 
     def _render(self, data, **kw):
+        kw.setdefault('precision', self.precision)
         out = engine.render(self.kind, self.model_coarse, self.model_fine, getattr(self, 'model_warp_field', None),
                             self.args, self.position_encoder, self.direction_encoder,
                             getattr(self, 'human_pose_encoder', None), data, **kw)

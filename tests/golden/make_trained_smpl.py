@@ -1,0 +1,110 @@
+"""Mint the trained SmplNerfPipeline fixture -- build container only.
+
+    python tests/golden/make_trained_smpl.py
+
+Trains the HEADLINE architecture -- SmplNerfPipeline, two RenderRayNet 8x256 (skips=[4]) + WarpFieldNet, 64 coarse +
+128 fine samples -- for a few hundred Adam steps with the REFERENCE classes (imported from /root/reference; loss =
+MSE(rgb) + MSE(rgb_fine), solver/smpl_nerf_solver.py:35-43 without the optional GMM term) on 64x64 views of the synthetic
+capsule figure whose arms MOVE with the pose (arm angle 0..60 degrees, goal_pose columns 38 and 41), then renders a
+held-out view (unseen camera, unseen arm angle) with the reference pipeline in fp32 AND in fp64 and stores:
+
+  * the FULL fp32 weights (no rounding: the engine's fp16 hi/lo weight split is exercised, lo != 0),
+  * the held-out rays + analytic ground truth, the reference's six outputs, its raw sigma/rgb taps, its PSNR,
+  * the reference's own fp32-vs-fp64 deviation on the same inputs (the noise floor that puts parity errors in context).
+
+tests/test_gpu_parity.py::test_trained_smpl_* and bench.py's `psnr` key render the same view with the engine."""
+import copy
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import nerf_oracle as O      # noqa: E402
+from oracle import ref_import as R       # noqa: E402
+from smpl_nerf_b200 import scene         # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'trained_smpl_d8.ckpt')
+SIDE, NC, NF = 64, 64, 128
+STEPS = int(os.environ.get('NRF_TRAIN_STEPS', 700))
+BATCH = int(os.environ.get('NRF_TRAIN_BATCH', 384))
+
+
+def main():
+    ref = R.load()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    torch.set_num_threads(int(os.environ.get('NRF_TRAIN_THREADS', os.cpu_count() or 1)))
+    c, f, w, pe, de, he = O.build_nets('smpl', 41, 'default', net_cls=ref.RenderRayNet, warp_cls=ref.WarpFieldNet,
+                                       enc_cls=ref.PositionalEncoder)
+    for m in (c, f, w):
+        m.train()
+    args = O.make_args(number_fine_samples=NF)
+    pipe = ref.SmplNerfPipeline(c, f, w, args, pe, de, he)
+    views = [scene.make_rays(SIDE, SIDE, NC, phi=8.0 + 4 * (k % 3), theta=36.0 * k, arm_angle_deg=60.0 * (k % 5) / 4,
+                             seed=200 + k, with_colours=True) for k in range(10)]
+    train = {k: torch.cat([v[k] for v in views]) for k in views[0]}
+    params = [p for m in (c, f, w) for p in m.parameters()]
+    opt = torch.optim.Adam(params, lr=5e-4)
+    n = train['z_vals'].shape[0]
+    fg = torch.nonzero((train['rgb'] < 0.99).any(-1)).flatten()
+    print(f'{n} training rays, {fg.numel()} on the figure; {STEPS} steps of {BATCH} rays', flush=True)
+    t0 = time.time()
+    for step in range(STEPS):
+        sel = torch.cat([torch.randint(0, n, (BATCH // 2,)), fg[torch.randint(0, fg.numel(), (BATCH // 2,))]])
+        data = scene.data_list(train, 'smpl', sel)
+        out = pipe(data)
+        loss = torch.mean((out[0] - data[-1]) ** 2) + torch.mean((out[1] - data[-1]) ** 2)
+        opt.zero_grad(); loss.backward(); opt.step()
+        if step % 20 == 0:
+            print(f'step {step:4d} loss {float(loss):.5f}  ({time.time() - t0:.0f} s)', flush=True)
+    for m in (c, f, w):
+        m.eval()
+    held = scene.make_rays(SIDE, SIDE, NC, phi=10.0, theta=52.0, arm_angle_deg=37.0, seed=999, with_colours=True)   # == held_args below
+    data = scene.data_list(held, 'smpl')
+    taps = {}
+    hooks = [c.register_forward_hook(lambda m, i, o: taps.__setitem__('raw_coarse', o.detach().clone())),
+             f.register_forward_hook(lambda m, i, o: taps.__setitem__('raw_fine', o.detach().clone()))]
+    with torch.no_grad():
+        ref_out = [t.clone() for t in pipe(data)]
+    for h in hooks:
+        h.remove()
+    # the reference's own fp32-vs-fp64 deviation (noise floor) through the bit-identical oracle port in float64
+    c64, f64, w64 = (copy.deepcopy(m).double() for m in (c, f, w))
+    with torch.no_grad():
+        o64 = O.smpl_nerf_forward(c64, f64, w64, pe, de, he, args, [t.double() for t in data])
+    floor = dict(rgb_fine=float((ref_out[1].double() - o64['rgb_fine']).abs().max()),
+                 alpha=float((ref_out[5].double() - o64['alpha_out']).abs().max()),
+                 alpha_p999=float(torch.quantile((ref_out[5].double() - o64['alpha_out']).abs().flatten()[:4000000], 0.999)),
+                 sigma_fine=float((taps['raw_fine'].view(-1, NC + NF, 4)[..., 3].double() - o64['raw_fine'][..., 3]).abs().max()),
+                 sigma_coarse=float((taps['raw_coarse'].view(-1, NC, 4)[..., 3].double() - o64['raw_coarse'][..., 3]).abs().max()))
+    mse = float(torch.mean((ref_out[1].double() - data[-1].double()) ** 2))
+    psnr = -10.0 * np.log10(mse)
+    white = -10.0 * np.log10(float(torch.mean((1.0 - data[-1].double()) ** 2)))
+    print(f'held-out PSNR of the reference render vs ground truth: {psnr:.3f} dB (all-white image: {white:.3f} dB)')
+    print('reference fp32-vs-fp64 floor:', floor)
+    # fp32 run of the (bit-identical) port for the intermediates the reference pipeline does not return
+    with torch.no_grad():
+        o32 = O.smpl_nerf_forward(c, f, w, pe, de, he, args, data)
+    assert torch.equal(o32['rgb_fine'], ref_out[1]) and torch.equal(o32['alpha_out'], ref_out[5]), 'port != reference'
+    sub = slice(0, None, 8)          # per-sample tensors are stored for every 8th ray only (file size)
+    # the held-out rays are NOT stored (4 MB): scene.make_rays(**held_args) regenerates them bit-for-bit (numpy float64
+    # arithmetic + RandomState(seed)); `data_checksum` guards that
+    held_args = dict(h=SIDE, w=SIDE, n_coarse=NC, phi=10.0, theta=52.0, arm_angle_deg=37.0, seed=999, with_colours=True)
+    torch.save(dict(coarse=c.state_dict(), fine=f.state_dict(), warp=w.state_dict(), n_coarse=NC, n_fine=NF, side=SIDE,
+                    held_args=held_args, data_checksum=[float(t.double().sum()) for t in data],
+                    reference_rgb=ref_out[0], reference_rgb_fine=ref_out[1], sub_step=8,
+                    reference_warped=ref_out[4][sub].clone(),
+                    reference_alpha=ref_out[5][sub].clone(), reference_z_all=o32['z_all'][sub].clone(),
+                    reference_sigma_coarse=taps['raw_coarse'].view(-1, NC, 4)[sub, :, 3].clone(),
+                    reference_sigma_fine=taps['raw_fine'].view(-1, NC + NF, 4)[sub, :, 3].clone(),
+                    reference_psnr=psnr, white_psnr=white, floor=floor, steps=STEPS,
+                    batch=BATCH, torch_version=torch.__version__), OUT)
+    print(f'{OUT}: {os.path.getsize(OUT) / 1024:.0f} KB')
+
+
+if __name__ == '__main__':
+    main()

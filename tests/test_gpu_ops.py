@@ -63,6 +63,37 @@ def test_sample_pdf():
     assert float(err.max()) <= float((bins[:, 1:] - bins[:, :-1]).max()) + 1e-5
 
 
+@pytest.mark.parametrize('nc,nf', [(64, 128), (32, 64), (48, 80), (17, 5)])
+def test_fine_sampling(nc, nf):
+    """ops.fine_sampling (nrf_fine_sampling, utils.py:231-264) against the oracle: the merged depths are sorted, hold the
+    coarse depths bit-for-bit, the points are o + d * z with the reference's separate multiply and add, and the new
+    samples agree with the oracle's away from the sampler's two step-function switches (see test_sample_pdf)."""
+    torch.manual_seed(5)
+    B = 96
+    z = torch.sort(torch.rand(B, nc) * 3 + 1, -1)[0]
+    w = torch.rand(B, nc) ** 4
+    w[0] = 0
+    o, d = torch.randn(B, 3), torch.randn(B, 3)
+    args = O.make_args(number_fine_samples=nf)
+    z_want, pts_want, z_new = O.fine_samples(o, d, z, w, nf)
+    z_got, pts_got = ops.fine_sampling(o.to(DEV), d.to(DEV), z.to(DEV), w.to(DEV), args)
+    z_got, pts_got = z_got.cpu(), pts_got.cpu()
+    assert z_got.shape == (B, nc + nf) and pts_got.shape == (B, nc + nf, 3)
+    assert bool((z_got[:, 1:] >= z_got[:, :-1]).all())
+    # points are exactly o + d * z of the kernel's own depths (separate fp32 multiply and add, utils.py:262)
+    assert torch.equal(pts_got, o[:, None, :] + d[:, None, :] * z_got[:, :, None])
+    # every coarse depth is present bit-for-bit
+    for b in range(0, B, 7):
+        assert set(z[b].tolist()) <= set(z_got[b].tolist())
+    err = (z_got - z_want).abs()
+    assert float(torch.quantile(err.flatten(), 0.98)) <= 1e-5
+    assert float(err.max()) <= float((z[:, 1:] - z[:, :-1]).max()) + 1e-5
+    # rays whose new samples match the oracle's to the last bit must give the identical merge
+    same = (ops.sample_pdf((.5 * (z[:, 1:] + z[:, :-1])).to(DEV), w[:, 1:-1].contiguous().to(DEV), args).cpu() == z_new).all(-1)
+    assert int(same.sum()) > B // 2
+    assert torch.equal(z_got[same], z_want[same]) and torch.equal(pts_got[same], pts_want[same])
+
+
 @pytest.mark.parametrize('Ba,Bv', [(1, 1), (100, 100), (1, 100), (100, 1)])
 @pytest.mark.parametrize('A,V', [(1, 1), (50, 12), (500, 120), (63, 128)])
 @pytest.mark.parametrize('side', ['left', 'right'])

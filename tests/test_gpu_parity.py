@@ -365,13 +365,18 @@ SWEEP = [
     ('append', 8, (4,), 10, False, 4, False, 1, 48, 80),         # 2 rays per tile, 32 idle rows
     ('smpl', 8, (4,), 10, False, 4, False, 1, 32, 32),
     ('smpl', 3, (0,), 10, False, 4, False, 1, 64, 128),          # skip right after the first layer
+    ('nerf', 8, (4,), 10, False, 6, False, 1, 64, 128),          # 36 direction features (> 32: ADVICE r1, per-ray table overflow)
+    ('append', 8, (4,), 10, False, 10, True, 1, 64, 64),         # 63 direction features, the planner's maximum
+    ('nerf', 8, (4,), 10, False, 4, False, 1, 64, 128, False),   # additional_linear_layer NOT folded (fold=False)
+    ('smpl', 8, (4,), 10, False, 4, False, 1, 64, 128, False),
 ]
 
 
 @pytest.mark.parametrize('cfg', SWEEP, ids=lambda c: '-'.join(str(x) for x in c))
 def test_architecture_and_sample_count_sweep(cfg):
     """Net shapes / encoders / sample counts beyond the shipped configs, stage-wise against the oracle."""
-    kind, n_layers, skips, L_pos, id_pos, L_dir, id_dir, use_dir, nc, nf = cfg
+    kind, n_layers, skips, L_pos, id_pos, L_dir, id_dir, use_dir, nc, nf = cfg[:10]
+    fold = cfg[10] if len(cfg) > 10 else None           # None: the engine default (folded)
     torch.manual_seed(1234 + n_layers + nc)
     pe, de, he = O.Encoder(L_pos, id_pos), O.Encoder(L_dir, id_dir), O.Encoder(10, False)
     P, D = 3 * pe.output_dim, 3 * de.output_dim
@@ -394,7 +399,7 @@ def test_architecture_and_sample_count_sweep(cfg):
         want = H.run_oracle(kind, nets, args, data)
     gnets, gdata = H.to_cuda(nets, data)
     gc, gf, gw = gnets[:3]
-    got = engine.render(kind, gc, gf, gw, args, pe, de, he, gdata, taps=True, z_all_in=want['z_all'].to(DEV))
+    got = engine.render(kind, gc, gf, gw, args, pe, de, he, gdata, taps=True, z_all_in=want['z_all'].to(DEV), fold=fold)
     torch.cuda.synchronize()
     assert int(got['status'].item()) == 0
     assert maxdiff(got['raw_coarse'][..., 3], want['raw_coarse'][..., 3]) <= H.TOL_SIGMA
@@ -404,7 +409,7 @@ def test_architecture_and_sample_count_sweep(cfg):
     assert maxdiff(got['rgb_fine'], want['rgb_fine']) <= H.TOL_RGB
     assert torch.equal(got['samples_out'].cpu(), want['samples_out'])
     # and the in-kernel sampler end to end
-    free = engine.render(kind, gc, gf, gw, args, pe, de, he, gdata, taps=True)
+    free = engine.render(kind, gc, gf, gw, args, pe, de, he, gdata, taps=True, fold=fold)
     assert float(torch.quantile((free['z_new'].cpu() - want['z_new']).abs(), 0.99)) <= 1e-4
     # free-running, one flipped `denom < 1e-5` decision (utils.py:224) moves a fine sample and with it a colour by
     # more than the stage-wise tolerance -- the reference's own fp32-vs-fp64 runs differ the same way --

@@ -30,12 +30,12 @@ def test_header_symbols_exported(L):
     for n in names:
         assert hasattr(L, n), f'{n} declared in include/nrf_b200.h but not exported'
     assert set(_lib.exported_symbols()) == names
-    assert L.nrf_abi_version() == 3
+    assert L.nrf_abi_version() == _lib.ABI_VERSION
 
 
 def test_struct_sizes_match_header(L):
     # int32 counts in the C structs (include/nrf_b200.h)
-    assert C.sizeof(_lib.RayNetDesc) == 4 * (7 + 4 + 6)
+    assert C.sizeof(_lib.RayNetDesc) == 4 * (7 + 4 + 7)
     assert C.sizeof(_lib.WarpNetDesc) == 4 * 5
     assert C.sizeof(_lib.PipelineDesc) == 4 * 12
     assert C.sizeof(_lib.RenderIO) == 8 * 25
