@@ -92,6 +92,8 @@ typedef struct NrfPipelineDesc {
   int32_t pose_stride;      /* floats per row of goal_pose (69)                        */
   int32_t pose_col0, pose_col1; /* the two columns the pipelines read (38, 41)         */
   int32_t precision;        /* 0 = parity (fp16 hi/lo split, 3 MMA passes); 1 = fast (1 pass) */
+  int32_t pose_all;         /* training entry points only: 1 = the pipeline feeds ALL pose_stride pose parameters
+                               (AppendSmplParamsPipeline, models/append_smpl_params_pipeline.py:30-37), 0 = the two columns above */
 } NrfPipelineDesc;
 
 /* Inputs/outputs of one render call.  NULL is allowed where marked optional. */
@@ -204,6 +206,38 @@ int nrf_generate_rays(int32_t H, int32_t W, double focal, const double* camera_t
 /* torchsearchsorted: a[rows_a, na], v[rows_v, nv] (rows broadcast when one side has 1 row) -> res int64 */
 int nrf_searchsorted(const float* a, int64_t rows_a, int64_t na, const float* v, int64_t rows_v, int64_t nv,
                      int64_t* res, int32_t side_left, void* stream);
+
+/* ---- training (the callers are solver/nerf_solver.py:81-87 and solver/smpl_nerf_solver.py:74-83:
+ *      out = pipeline(data); loss = MSE(out[0], gt) + MSE(out[1], gt); loss.backward()) ----
+ * nrf_train_forward computes the same outputs as nrf_render, layer by layer (one tcgen05 GEMM per nn.Linear), and leaves in
+ * `workspace` (caller-owned device buffer of nrf_train_workspace_bytes(), 256-byte aligned) what nrf_train_backward needs.
+ * params_*: HOST arrays of DEVICE pointers to the ORIGINAL fp32 nn.Linear tensors in state_dict order (as nrf_pack_*).
+ * nrf_train_backward takes d(loss)/d(rgb) [B,3] and d(loss)/d(rgb_fine) [B,3] and ACCUMULATES d(loss)/d(parameter) into
+ * grads_* (same order and shapes as params_*; the caller zeroes them).  The other outputs (sample points, alpha, warp) are
+ * not differentiated, like the hierarchical sampler (utils.py:260 detaches it).  `io` must be the same in both calls.
+ * pipe->precision: 0 = three fp16 MMA passes in forward and backward (fp32-equivalent), 1 = one pass (mixed precision). */
+size_t nrf_train_workspace_bytes(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, const NrfRayNetDesc* fine,
+                                 const NrfWarpNetDesc* warp, int64_t B);
+int nrf_train_forward(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, const float* const* params_coarse, int n_coarse,
+                      const NrfRayNetDesc* fine, const float* const* params_fine, int n_fine, const NrfWarpNetDesc* warp,
+                      const float* const* params_warp, int n_warp, const NrfRenderIO* io, int64_t B, void* workspace,
+                      size_t workspace_bytes, int n_sms, void* stream);
+int nrf_train_backward(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, const float* const* params_coarse, int n_coarse,
+                       const NrfRayNetDesc* fine, const float* const* params_fine, int n_fine, const NrfWarpNetDesc* warp,
+                       const float* const* params_warp, int n_warp, const NrfRenderIO* io, int64_t B, void* workspace,
+                       size_t workspace_bytes, const float* grad_rgb, const float* grad_rgb_fine, float* const* grads_coarse,
+                       float* const* grads_fine, float* const* grads_warp, int n_sms, void* stream);
+/* Building blocks of the training path, exported for stage-wise tests.  "planes" = a matrix as two fp16 tensors hi, lo
+ * (x ~= hi + lo), row-major [rows, ld]; lo may be NULL with passes = 1.
+ * nrf_split_planes: fp32 [rows, cols] (row pitch ld) -> planes [rows, cols_pad] (row pitch ld_dst), zero padded.
+ * nrf_gemm_planes:  b_mn = 0: C[S,N] = A[S,K] B[N,K]^T (the forward of nn.Linear);  b_mn = 1: C[S,N] = A[S,K] B[K,N] (dX = dY W).
+ *                   out_hi != NULL: C = [relu](acc + bias) as planes (+ fp32 copy in out_f32 if given); else fp32 C in out_f32.
+ * nrf_gemm_dw:      out[M,N] += A[S,M]^T B[S,N] (dW = dY^T X), split over the SMs; partial: >= (max_split * M * N + 2) floats. */
+int nrf_split_planes(const float* src, int64_t rows, int32_t cols, int32_t ld, void* hi, void* lo, int32_t ld_dst, int32_t cols_pad, void* stream);
+int nrf_gemm_planes(int32_t b_mn, const void* a_hi, const void* a_lo, int64_t S, int32_t K, const void* b_hi, const void* b_lo, int32_t N,
+                    int32_t passes, const float* bias, int32_t relu, float* out_f32, void* out_hi, void* out_lo, void* stream);
+int nrf_gemm_dw(const void* a_hi, const void* a_lo, int32_t M, const void* b_hi, const void* b_lo, int32_t N, int64_t S, int32_t passes,
+                float* partial, int32_t max_split, float* out, void* stream);
 
 /* tcgen05 self-test: D[128,256] = A[128,64] * B[256,64]^T with fp16 operands staged through the swizzled
  * shared-memory layout / descriptors the renderer uses (SWIZZLE_128B K-major tiles, N = 256 per

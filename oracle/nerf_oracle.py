@@ -166,10 +166,14 @@ def inverse_cdf(bins: torch.Tensor, weights: torch.Tensor, n_fine: int) -> torch
 
 
 def fine_samples(origin: torch.Tensor, direction: torch.Tensor, z: torch.Tensor,
-                 weights: torch.Tensor, n_fine: int):
+                 weights: torch.Tensor, n_fine: int, z_all_in: Optional[torch.Tensor] = None):
+    """``z_all_in`` (not in the reference): use these merged depths instead of the sampler's -- "teacher forcing" for
+    stage-wise parity and gradient tests, where a flipped sampler decision would otherwise mask everything else."""
     mid = .5 * (z[..., 1:] + z[..., :-1])
     z_new = inverse_cdf(mid, weights[..., 1:-1], n_fine).detach()
     z_all, _ = torch.sort(torch.cat([z, z_new], -1), -1)
+    if z_all_in is not None:
+        z_all = z_all_in.to(z.dtype)
     pts = origin[..., None, :] + direction[..., None, :] * z_all[..., :, None]
     return z_all, pts, z_new
 
@@ -195,7 +199,7 @@ def _pose2(goal_pose: torch.Tensor) -> torch.Tensor:
 
 
 def nerf_forward(coarse: RayNet, fine: RayNet, pos_enc: Encoder, dir_enc: Encoder, args,
-                 data: Sequence[torch.Tensor], noise_coarse=None, noise_fine=None) -> Dict[str, torch.Tensor]:
+                 data: Sequence[torch.Tensor], noise_coarse=None, noise_fine=None, z_all_in=None) -> Dict[str, torch.Tensor]:
     """models/nerf_pipeline.py:14-67.  Returns a dict; ``as_tuple`` gives the reference order."""
     samples, origin, direction, z = data[0], data[1], data[2], data[3]
     B, n = samples.shape[0], samples.shape[1]
@@ -208,7 +212,7 @@ def nerf_forward(coarse: RayNet, fine: RayNet, pos_enc: Encoder, dir_enc: Encode
     if not args.run_fine:
         out.update(rgb_fine=rgb, samples_out=samples, alpha_out=alpha)
         return out
-    z_all, pts, z_new = fine_samples(origin, direction, z, w, args.number_fine_samples)
+    z_all, pts, z_new = fine_samples(origin, direction, z, w, args.number_fine_samples, z_all_in)
     m = pts.shape[1]
     enc_xf = pos_enc.encode(pts)
     enc_df = enc_d[..., :1, :].expand(B, m, enc_d.shape[-1])
@@ -221,7 +225,7 @@ def nerf_forward(coarse: RayNet, fine: RayNet, pos_enc: Encoder, dir_enc: Encode
 
 
 def append_to_nerf_forward(coarse: RayNet, fine: RayNet, pos_enc: Encoder, dir_enc: Encoder,
-                           pose_enc: Encoder, args, data, noise_coarse=None, noise_fine=None, full_pose=False):
+                           pose_enc: Encoder, args, data, noise_coarse=None, noise_fine=None, full_pose=False, z_all_in=None):
     """models/append_to_nerf_pipeline.py:14-90 (pose features FIRST in the MLP input).
     ``full_pose``: models/append_smpl_params_pipeline.py:14-91 -- the same forward with all 69 pose
     parameters (encoded: 69 * 2L = 1380 features) instead of the two arm angles."""
@@ -246,7 +250,7 @@ def append_to_nerf_forward(coarse: RayNet, fine: RayNet, pos_enc: Encoder, dir_e
     if not args.run_fine:
         out.update(rgb_fine=rgb, samples_out=samples, alpha_out=alpha)
         return out
-    z_all, pts, z_new = fine_samples(origin, direction, z, w, args.number_fine_samples)
+    z_all, pts, z_new = fine_samples(origin, direction, z, w, args.number_fine_samples, z_all_in)
     m = pts.shape[1]
     raw_f = run(fine, pos_enc.encode(pts), m)
     dirs_f = direction[..., None, :].expand(B, m, 3)
@@ -256,14 +260,14 @@ def append_to_nerf_forward(coarse: RayNet, fine: RayNet, pos_enc: Encoder, dir_e
     return out
 
 
-def append_smpl_params_forward(coarse, fine, pos_enc, dir_enc, pose_enc, args, data, noise_coarse=None, noise_fine=None):
+def append_smpl_params_forward(coarse, fine, pos_enc, dir_enc, pose_enc, args, data, noise_coarse=None, noise_fine=None, z_all_in=None):
     """models/append_smpl_params_pipeline.py:14-91."""
     return append_to_nerf_forward(coarse, fine, pos_enc, dir_enc, pose_enc, args, data, noise_coarse, noise_fine,
-                                  full_pose=True)
+                                  full_pose=True, z_all_in=z_all_in)
 
 
 def smpl_nerf_forward(coarse: RayNet, fine: RayNet, warp: WarpNet, pos_enc: Encoder, dir_enc: Encoder,
-                      pose_enc: Encoder, args, data, noise_coarse=None, noise_fine=None):
+                      pose_enc: Encoder, args, data, noise_coarse=None, noise_fine=None, z_all_in=None):
     """models/smpl_nerf_pipeline.py:16-100 (warp field, per-sample view directions)."""
     samples, origin, direction, z, goal_pose = data[0], data[1], data[2], data[3], data[4]
     B, n = samples.shape[0], samples.shape[1]
@@ -296,7 +300,7 @@ def smpl_nerf_forward(coarse: RayNet, fine: RayNet, warp: WarpNet, pos_enc: Enco
     if not args.run_fine:
         out.update(rgb_fine=rgb, warp_out=wf, samples_out=samples, warped_out=warped, alpha_out=alpha)
         return out
-    z_all, pts, z_new = fine_samples(origin, direction, z, w, args.number_fine_samples)
+    z_all, pts, z_new = fine_samples(origin, direction, z, w, args.number_fine_samples, z_all_in)
     m = pts.shape[1]
     wf_f = warp_of(pts, m, encoded=True)                    # always the encoded form (:71-77)
     warped_f = pts + wf_f

@@ -15,8 +15,8 @@ from typing import List
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.environ.get('NRF_LIB_PATH') or os.path.join(CSRC, 'libnrf_b200.so')   # NRF_LIB_PATH: A/B builds (developer)
-SOURCES = ['nrf_pack.cu', 'nrf_fused.cu', 'nrf_ops.cu', 'nrf_diag.cu']
-HEADERS = ['nrf_plan.h', 'nrf_ptx.cuh', 'nrf_stages.cuh', os.path.join('..', '..', 'include', 'nrf_b200.h')]
+SOURCES = ['nrf_pack.cu', 'nrf_fused.cu', 'nrf_ops.cu', 'nrf_diag.cu', 'nrf_gemm.cu', 'nrf_train.cu']
+HEADERS = ['nrf_plan.h', 'nrf_ptx.cuh', 'nrf_stages.cuh', 'nrf_gemm.cuh', 'nrf_train_kernels.cuh', os.path.join('..', '..', 'include', 'nrf_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -43,7 +43,7 @@ class PipelineDesc(C.Structure):
     _fields_ = [('kind', C.c_int32), ('n_coarse', C.c_int32), ('n_fine', C.c_int32), ('run_fine', C.c_int32),
                 ('white_background', C.c_int32), ('pose_freqs', C.c_int32), ('pose_identity', C.c_int32),
                 ('pose_encoded', C.c_int32), ('pose_stride', C.c_int32), ('pose_col0', C.c_int32),
-                ('pose_col1', C.c_int32), ('precision', C.c_int32)]
+                ('pose_col1', C.c_int32), ('precision', C.c_int32), ('pose_all', C.c_int32)]
 
 
 _IO_IN = ['ray_samples', 'ray_origin', 'ray_dir', 'z_vals', 'goal_pose', 'u_fine', 'noise_coarse', 'noise_fine',
@@ -60,7 +60,8 @@ EXPORTS = ['nrf_last_error', 'nrf_abi_version', 'nrf_device_supported', 'nrf_ray
            'nrf_warpnet_packed_bytes', 'nrf_pack_raynet', 'nrf_pack_warpnet', 'nrf_render', 'nrf_render_launches',
            'nrf_raynet_ext_slots', 'nrf_ray_bias', 'nrf_generate_rays',
            'nrf_positional_encoding', 'nrf_positional_encoding_backward', 'nrf_raw2outputs', 'nrf_raw2outputs_backward', 'nrf_sample_pdf', 'nrf_fine_sampling', 'nrf_searchsorted',
-           'nrf_selftest_umma', 'nrf_selftest_umma2', 'nrf_bench_umma', 'nrf_bench_umma2']
+           'nrf_selftest_umma', 'nrf_selftest_umma2', 'nrf_bench_umma', 'nrf_bench_umma2',
+           'nrf_train_workspace_bytes', 'nrf_train_forward', 'nrf_train_backward', 'nrf_split_planes', 'nrf_gemm_planes', 'nrf_gemm_dw']
 
 
 def _stale() -> bool:
@@ -134,6 +135,18 @@ def lib() -> C.CDLL:
     L.nrf_bench_umma2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     L.nrf_selftest_umma2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nrf_bench_umma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
+    PP = C.POINTER(C.c_void_p)
+    L.nrf_train_workspace_bytes.restype = C.c_size_t
+    L.nrf_train_workspace_bytes.argtypes = [C.POINTER(PipelineDesc), C.POINTER(RayNetDesc), C.POINTER(RayNetDesc), C.POINTER(WarpNetDesc), C.c_int64]
+    _net_args = [C.POINTER(PipelineDesc), C.POINTER(RayNetDesc), PP, C.c_int, C.POINTER(RayNetDesc), PP, C.c_int, C.POINTER(WarpNetDesc), PP, C.c_int,
+                 C.POINTER(RenderIO), C.c_int64, C.c_void_p, C.c_size_t]
+    L.nrf_train_forward.argtypes = _net_args + [C.c_int, C.c_void_p]
+    L.nrf_train_backward.argtypes = _net_args + [C.c_void_p, C.c_void_p, PP, PP, PP, C.c_int, C.c_void_p]
+    L.nrf_split_planes.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.nrf_gemm_planes.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nrf_gemm_dw.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                              C.c_void_p, C.c_void_p]
     if L.nrf_abi_version() != ABI_VERSION:
         raise RuntimeError('libnrf_b200.so ABI version mismatch; rebuild')
     _lib = L

@@ -1,0 +1,447 @@
+// tcgen05 GEMM kernels of the training path -- see nrf_gemm.cuh for the three products they serve.
+//
+//   tile_gemm_kernel   C[S, N] = A[S, K] . op(B): the weight operand (K <= 320, one 128- or 64-column slice) stays
+//                      RESIDENT in shared memory, the CTA streams 128-row sample tiles through a TMA ring and double-
+//                      buffers the accumulator in TMEM, so the epilogue of tile i (bias / ReLU / ReLU' mask / hi-lo split ->
+//                      planes) overlaps the MMAs of tile i + 1.  Roofline: tensor (3 x 2 S K N flop in parity mode) --
+//                      the A stream is 4 K bytes per sample per slice, ~40 B/clk/SM at the MMA rate.
+//   dw_gemm_kernel     dW[128, N] += A[s, m]^T B[s, n] over this CTA's share of the samples (split-K), both operands
+//                      MN-major straight out of the row-major planes; partial sums to HBM, reduced by dw_reduce_kernel.
+//                      Roofline: HBM (each sample row of dY and X is read once per 128-wide M half: ~3 KB per sample per
+//                      layer in parity mode against 2 x 3 x 256 x 256 flop = 131 flop/B).
+//
+// Warp roles: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (converged warp, elected lane), the rest = epilogue
+// (TMEM lane quarter = warp % 4).
+#include <cstdio>
+#include <cstring>
+
+#include "nrf_gemm.cuh"
+#include "nrf_plan.h"
+#include "nrf_ptx.cuh"
+
+namespace nrf {
+
+constexpr uint32_t kGemmSmemLimit = 232448;
+constexpr int kTileThreads = 320;     // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kDwThreads = 192;       // TMA warp, MMA warp, 4 epilogue warps
+constexpr uint32_t kATile = 16384;    // [128 x 64] fp16
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cvt_f16x2_satfinite(float x0, float x1) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
+}
+
+struct GemmBars { uint64_t b_full, a_full[4], a_empty[4], acc_full[2], acc_empty[2]; uint32_t tmem; uint32_t pad; };
+
+// ------------------------------------------------------------------------------------------------ tile GEMM
+__global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid_constant__ TileGemmParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t planes = P.passes == 3 ? 2u : 1u;
+  const int nk = P.kc[0] + (P.n_src > 1 ? P.kc[1] : 0);
+  const uint32_t b_chunk = static_cast<uint32_t>(P.n_tile) * 128u;
+  const uint32_t b_bytes = static_cast<uint32_t>(nk) * planes * b_chunk;
+  const uint32_t a_stage = planes * kATile;
+  const uint32_t smem_b = smem_u32(smem), smem_a = smem_b + b_bytes;
+  GemmBars* bars = reinterpret_cast<GemmBars*>(smem + b_bytes + static_cast<uint32_t>(P.n_stages) * a_stage);
+  const int n0 = blockIdx.y * P.n_tile;
+  const int64_t n_mt = (P.S + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars->b_full), 1);
+    for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&bars->a_full[s]), 1); mbar_init(smem_u32(&bars->a_empty[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bars->acc_full[b]), 1); mbar_init(smem_u32(&bars->acc_empty[b]), 8); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(smem_u32(&bars->tmem));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = bars->tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- resident weight slice
+      mbar_arrive_expect_tx(smem_u32(&bars->b_full), b_bytes);
+      int c = 0;
+      for (int j = 0; j < P.n_src; ++j)
+        for (int lc = 0; lc < P.kc[j]; ++lc, ++c)
+          for (uint32_t p = 0; p < planes; ++p) {
+            const CUtensorMap* map = p ? &P.b_lo[j] : &P.b_hi[j];
+            const uint32_t dst = smem_b + (static_cast<uint32_t>(c) * planes + p) * b_chunk;
+            if (!P.b_mn) tma_load_2d(dst, map, 64 * lc, n0, smem_u32(&bars->b_full));
+            else for (int g = 0; g < P.n_tile / 64; ++g) tma_load_2d(dst + g * 8192u, map, n0 + 64 * g, 64 * lc, smem_u32(&bars->b_full));
+          }
+      // ---- sample tiles
+      uint32_t stage = 0, phase = 0;
+      for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x)
+        for (int j = 0; j < P.n_src; ++j)
+          for (int lc = 0; lc < P.kc[j]; ++lc) {
+            mbar_wait(smem_u32(&bars->a_empty[stage]), phase ^ 1);
+            mbar_arrive_expect_tx(smem_u32(&bars->a_full[stage]), a_stage);
+            const uint32_t dst = smem_a + stage * a_stage;
+            tma_load_2d(dst, &P.a_hi[j], 64 * lc, static_cast<int32_t>(mt * 128), smem_u32(&bars->a_full[stage]));
+            if (planes == 2) tma_load_2d(dst + kATile, &P.a_lo[j], 64 * lc, static_cast<int32_t>(mt * 128), smem_u32(&bars->a_full[stage]));
+            if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
+          }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_f16_major(128, static_cast<uint32_t>(P.n_tile), 0u, P.b_mn ? 1u : 0u);
+    mbar_wait(smem_u32(&bars->b_full), 0);
+    tc_fence_after_sync();
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      mbar_wait(smem_u32(&bars->acc_empty[buf]), ((it >> 1) & 1u) ^ 1u);
+      tc_fence_after_sync();
+      const uint32_t acc = tmem + buf * static_cast<uint32_t>(P.n_tile);
+      uint32_t accumulate = 0;
+      for (int c = 0; c < nk; ++c) {
+        mbar_wait(smem_u32(&bars->a_full[stage]), phase);
+        tc_fence_after_sync();
+        const uint32_t a_hi = smem_a + stage * a_stage, a_lo = a_hi + kATile;
+        const uint32_t b_hi = smem_b + static_cast<uint32_t>(c) * planes * b_chunk, b_lo = b_hi + b_chunk;
+        for (uint32_t pass = 0; pass < static_cast<uint32_t>(P.passes); ++pass) {
+          const uint32_t a = pass == 1 ? a_lo : a_hi, b = pass == 2 ? b_lo : b_hi;      // hi*hi, lo*hi, hi*lo
+          const uint64_t ad = umma_desc_sw128(a);
+#pragma unroll
+          for (uint32_t ks = 0; ks < 4; ++ks) {
+            const uint64_t bd = P.b_mn ? umma_desc_mn_sw128(b + ks * 2048u, 8192u, 1024u) : umma_desc_sw128(b) + 2u * ks;
+            umma_f16_ss_warp(acc, ad + 2u * ks, bd, idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        umma_commit_warp(smem_u32(&bars->a_empty[stage]));
+        if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_warp(smem_u32(&bars->acc_full[buf]));
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int cols_w = P.n_tile / 2;
+    const float s_out = P.sc_out ? __ldg(P.sc_out) : 1.f, inv_out = P.sc_out ? __ldg(P.sc_out + 1) : 1.f;
+    const float ratio = (P.epi == GEPI_F32 ? 1.f : s_out) * (P.sc_in ? __ldg(P.sc_in + 1) : 1.f);     // stored-in -> stored-out (or real)
+    const bool rescale = P.sc_in != nullptr || P.sc_out != nullptr;
+    float l1_run = 0.f;
+    bool saturated = false;
+    uint32_t it = 0;
+    for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      const int64_t row = mt * 128 + 32 * q + lane;
+      const bool row_ok = row < P.S;
+      const float* bias_row = P.bias ? P.bias + (P.bias_ld ? (row_ok ? row / P.rows_per_ray : 0) * P.bias_ld : 0) : nullptr;
+      const float rs = (P.row_scale && row_ok) ? P.row_scale[row * P.row_scale_ld] * s_out : 0.f;
+      float l1 = 0.f;
+      mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem + buf * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(half * cols_w);
+      for (int g = 0; g < cols_w / 16; ++g) {
+        uint32_t v[16];
+        tmem_ld16(taddr + 16u * g, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const int col = n0 + half * cols_w + 16 * g;
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+        if (rescale) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] *= ratio;
+        }
+        if (bias_row) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias_row + col) + i);
+            x[4 * i] += b.x; x[4 * i + 1] += b.y; x[4 * i + 2] += b.z; x[4 * i + 3] += b.w;
+          }
+        }
+        if (P.row_scale) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = fmaf(rs, __ldg(P.col_vec + col + i), x[i]);
+        }
+        if (P.relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
+        }
+        if (P.mask_hi) {
+          const uint4* mp = reinterpret_cast<const uint4*>(P.mask_hi + row * P.mask_ld + col);
+          const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {      // post-ReLU activations are >= 0: "active" = any non-zero bit pattern
+            if ((mw[i] & 0x7FFFu) == 0u) x[2 * i] = 0.f;
+            if ((mw[i] & 0x7FFF0000u) == 0u) x[2 * i + 1] = 0.f;
+          }
+        }
+        if (P.l1max) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) l1 += fabsf(x[i]);
+        }
+        if (P.epi == GEPI_F32) {
+          float4* op = reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 o = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            if (P.accumulate) { const float4 t = op[i]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            op[i] = o;
+          }
+        } else {
+          uint32_t h[8], l[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            saturated |= fabsf(x[2 * i]) > 65504.f || fabsf(x[2 * i + 1]) > 65504.f;
+            h[i] = cvt_f16x2_satfinite(x[2 * i], x[2 * i + 1]);
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+            l[i] = cvt_f16x2_satfinite(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+          }
+          uint4* ph = reinterpret_cast<uint4*>(P.out_hi + row * P.out_ld + col);
+          ph[0] = make_uint4(h[0], h[1], h[2], h[3]); ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
+          if (P.out_lo) {
+            uint4* pl = reinterpret_cast<uint4*>(P.out_lo + row * P.out_ld + col);
+            pl[0] = make_uint4(l[0], l[1], l[2], l[3]); pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+          }
+          if (P.out_f32) {
+            float4* op = reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          }
+        }
+      }
+      l1_run = fmaxf(l1_run, l1);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
+    }
+    if (P.l1max) {
+      l1_run *= (P.epi == GEPI_F32 ? 1.f : inv_out) * static_cast<float>(gridDim.y * 2);     // real units; 2 column segments per slice
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) l1_run = fmaxf(l1_run, __shfl_xor_sync(0xffffffffu, l1_run, o));
+      if (lane == 0 && isfinite(l1_run)) atomicMax(P.l1max, __float_as_uint(l1_run));
+    }
+    if (saturated && P.status) atomicOr(P.status, 2);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------ dW GEMM (split-K over samples)
+__global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_constant__ DwGemmParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t planes = P.passes == 3 ? 2u : 1u;
+  const uint32_t a_bytes = 16384u, b_bytes = static_cast<uint32_t>(P.N) * 128u;       // one plane of one 64-sample stage
+  const uint32_t stage_bytes = planes * (a_bytes + b_bytes);
+  GemmBars* bars = reinterpret_cast<GemmBars*>(smem + static_cast<uint32_t>(P.n_stages) * stage_bytes);
+  const int64_t n_chunks = (P.S + 63) / 64;
+  const int m_tile = P.m0 + 128 * blockIdx.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&bars->a_full[s]), 1); mbar_init(smem_u32(&bars->a_empty[s]), 1); }
+    mbar_init(smem_u32(&bars->acc_full[0]), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(smem_u32(&bars->tmem));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = bars->tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t c = blockIdx.y; c < n_chunks; c += gridDim.y) {
+        mbar_wait(smem_u32(&bars->a_empty[stage]), phase ^ 1);
+        const uint32_t full = smem_u32(&bars->a_full[stage]);
+        mbar_arrive_expect_tx(full, stage_bytes);
+        const uint32_t base = smem_u32(smem) + stage * stage_bytes;
+        const int32_t s0 = static_cast<int32_t>(c * 64);
+        for (uint32_t p = 0; p < planes; ++p) {
+          const uint32_t da = base + p * a_bytes, db = base + planes * a_bytes + p * b_bytes;
+          for (int g = 0; g < 2; ++g) tma_load_2d(da + g * 8192u, p ? &P.a_lo : &P.a_hi, m_tile + 64 * g, s0, full);
+          for (int g = 0; g < P.N / 64; ++g) tma_load_2d(db + g * 8192u, p ? &P.b_lo : &P.b_hi, P.n0 + 64 * g, s0, full);
+        }
+        if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_f16_major(128, static_cast<uint32_t>(P.N), 1u, 1u);
+    uint32_t stage = 0, phase = 0, accumulate = 0;
+    for (int64_t c = blockIdx.y; c < n_chunks; c += gridDim.y) {
+      mbar_wait(smem_u32(&bars->a_full[stage]), phase);
+      tc_fence_after_sync();
+      const uint32_t base = smem_u32(smem) + stage * stage_bytes;
+      const uint32_t a_hi = base, a_lo = base + a_bytes, b_hi = base + planes * a_bytes, b_lo = b_hi + b_bytes;
+      for (uint32_t pass = 0; pass < static_cast<uint32_t>(P.passes); ++pass) {
+        const uint32_t a = pass == 1 ? a_lo : a_hi, b = pass == 2 ? b_lo : b_hi;
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) {
+          umma_f16_ss_warp(tmem, umma_desc_mn_sw128(a + ks * 2048u, 8192u, 1024u), umma_desc_mn_sw128(b + ks * 2048u, 8192u, 1024u), idesc, accumulate);
+          accumulate = 1;
+        }
+      }
+      umma_commit_warp(smem_u32(&bars->a_empty[stage]));
+      if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
+    }
+    umma_commit_warp(smem_u32(&bars->acc_full[0]));
+  } else {
+    const int q = warp & 3;
+    const bool any = static_cast<int64_t>(blockIdx.y) < n_chunks;
+    mbar_wait(smem_u32(&bars->acc_full[0]), 0);
+    tc_fence_after_sync();
+    const int m = 128 * blockIdx.x + 32 * q + lane;
+    float* dst = P.partial + (static_cast<size_t>(blockIdx.y) * P.M_total + m) * P.N;
+    for (int g = 0; g < P.N / 16; ++g) {
+      uint32_t v[16];
+      tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + 16u * g, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<float4*>(dst + 16 * g)[i] = any ? make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_planes_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows) {
+  static EncodeTiledFn2 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return NRF_E_CUDA; }
+    fn = reinterpret_cast<EncodeTiledFn2>(p);
+  }
+  if (!base || (reinterpret_cast<uintptr_t>(base) & 15u) || (ld_elems & 7u)) { set_error("plane tensors must be 16-byte aligned with a row pitch that is a multiple of 8 elements"); return NRF_E_INVALID; }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld_elems * 2u};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for a [%llu x %llu] plane", static_cast<int>(r), (unsigned long long)rows, (unsigned long long)cols); return NRF_E_CUDA; }
+  return NRF_OK;
+}
+
+static int device_sms(int n_sms, int* out) {
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  if (n_sms > 0 && n_sms < sms) sms = n_sms;
+  *out = sms;
+  return NRF_OK;
+}
+
+int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
+  static thread_local TileGemmParams P;
+  memset(&P, 0, sizeof(P));
+  if (a.n_src < 1 || a.n_src > 2) { set_error("tile_gemm: n_src %d", a.n_src); return NRF_E_INVALID; }
+  if (a.passes != 1 && a.passes != 3) { set_error("tile_gemm: passes must be 1 or 3"); return NRF_E_INVALID; }
+  if (a.N < 64 || (a.N & 63)) { set_error("tile_gemm: N = %d must be a multiple of 64", a.N); return NRF_E_INVALID; }
+  const int64_t S = a.a[0].rows;
+  if (S <= 0) return NRF_OK;
+  P.n_tile = (a.N % 128 == 0) ? 128 : 64;
+  P.n_src = a.n_src; P.b_mn = a.b_mn ? 1 : 0; P.passes = a.passes; P.S = S;
+  int nk = 0, rc;
+  for (int j = 0; j < a.n_src; ++j) {
+    const Planes& A = a.a[j]; const Planes& B = a.b[j];
+    if (A.cols < 64 || (A.cols & 63) || A.rows != S) { set_error("tile_gemm: A source %d has %d columns / %lld rows", j, A.cols, (long long)A.rows); return NRF_E_INVALID; }
+    if (a.passes == 3 && (!A.lo || !B.lo)) { set_error("tile_gemm: 3 passes need the lo planes"); return NRF_E_INVALID; }
+    P.kc[j] = A.cols / 64; nk += P.kc[j];
+    if ((rc = encode_planes_map(&P.a_hi[j], A.hi, S, A.cols, A.ld, 64, 128)) != NRF_OK) return rc;
+    if (a.passes == 3 && (rc = encode_planes_map(&P.a_lo[j], A.lo, S, A.cols, A.ld, 64, 128)) != NRF_OK) return rc;
+    if (!a.b_mn) {      // B[N, K]: rows = output features
+      if (B.rows != a.N || B.cols != A.cols) { set_error("tile_gemm: B source %d is [%lld x %d], expected [%d x %d]", j, (long long)B.rows, B.cols, a.N, A.cols); return NRF_E_INVALID; }
+      if ((rc = encode_planes_map(&P.b_hi[j], B.hi, B.rows, B.cols, B.ld, 64, P.n_tile)) != NRF_OK) return rc;
+      if (a.passes == 3 && (rc = encode_planes_map(&P.b_lo[j], B.lo, B.rows, B.cols, B.ld, 64, P.n_tile)) != NRF_OK) return rc;
+    } else {            // B[K, N]: rows = reduction index
+      if (B.rows != A.cols || B.cols != a.N) { set_error("tile_gemm: B source %d is [%lld x %d], expected [%d x %d]", j, (long long)B.rows, B.cols, A.cols, a.N); return NRF_E_INVALID; }
+      if ((rc = encode_planes_map(&P.b_hi[j], B.hi, B.rows, B.cols, B.ld, 64, 64)) != NRF_OK) return rc;
+      if (a.passes == 3 && (rc = encode_planes_map(&P.b_lo[j], B.lo, B.rows, B.cols, B.ld, 64, 64)) != NRF_OK) return rc;
+    }
+  }
+  const uint32_t planes = a.passes == 3 ? 2u : 1u;
+  const uint32_t b_bytes = static_cast<uint32_t>(nk) * planes * P.n_tile * 128u, a_stage = planes * kATile;
+  if (b_bytes + 2 * a_stage + 256 > kGemmSmemLimit) { set_error("tile_gemm: K = %d too large for a resident weight slice", 64 * nk); return NRF_E_INVALID; }
+  int stages = static_cast<int>((kGemmSmemLimit - 256 - b_bytes) / a_stage);
+  P.n_stages = stages > 4 ? 4 : stages;
+  P.epi = a.epi; P.relu = a.relu; P.bias = a.bias; P.bias_ld = a.bias_ld; P.rows_per_ray = a.rows_per_ray > 0 ? a.rows_per_ray : 1;
+  P.out_hi = a.out.hi; P.out_lo = a.out.lo; P.out_ld = a.out.ld; P.out_f32 = a.out_f32; P.out_f32_ld = a.out_f32_ld; P.accumulate = a.accumulate;
+  P.mask_hi = a.mask_hi; P.mask_ld = a.mask_ld; P.row_scale = a.row_scale; P.row_scale_ld = a.row_scale_ld; P.col_vec = a.col_vec;
+  P.sc_in = a.sc_in; P.sc_out = a.sc_out; P.l1max = a.l1max; P.status = a.status;
+  if (a.epi == GEPI_PLANES && !a.out.hi) { set_error("tile_gemm: planes epilogue without an output"); return NRF_E_INVALID; }
+  if (a.epi == GEPI_F32 && !a.out_f32) { set_error("tile_gemm: fp32 epilogue without an output"); return NRF_E_INVALID; }
+  int sms;
+  if ((rc = device_sms(n_sms, &sms)) != NRF_OK) return rc;
+  const int slices = a.N / P.n_tile;
+  const int64_t n_mt = (S + 127) / 128;
+  int gx = sms / slices; if (gx < 1) gx = 1; if (gx > n_mt) gx = static_cast<int>(n_mt);
+  const uint32_t smem_bytes = b_bytes + static_cast<uint32_t>(P.n_stages) * a_stage + 256;
+  cudaError_t e = cudaFuncSetAttribute(tile_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tile_gemm)");
+  tile_gemm_kernel<<<dim3(gx, slices), kTileThreads, smem_bytes, stream>>>(P);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "tile_gemm_kernel launch");
+}
+
+int dw_gemm_max_split(int n_sms, int M) {
+  int sms = 148;
+  if (device_sms(n_sms, &sms) != NRF_OK) sms = 148;
+  const int mt = M / 128 > 0 ? M / 128 : 1;
+  return sms / mt > 0 ? sms / mt : 1;
+}
+
+int launch_dw_gemm(const Planes& a, int m0, int M, const Planes& b, int n0, int N, int passes, float* partial, int max_split,
+                   int* n_split_out, int n_sms, cudaStream_t stream) {
+  static thread_local DwGemmParams P;
+  memset(&P, 0, sizeof(P));
+  if (passes != 1 && passes != 3) { set_error("dw_gemm: passes must be 1 or 3"); return NRF_E_INVALID; }
+  if (M < 128 || (M & 127) || N < 64 || N > 256 || (N & 63)) { set_error("dw_gemm: M = %d (multiple of 128) / N = %d (64..256, multiple of 64) unsupported", M, N); return NRF_E_INVALID; }
+  if (a.rows != b.rows || a.rows <= 0) { set_error("dw_gemm: operand row counts differ (%lld vs %lld)", (long long)a.rows, (long long)b.rows); return NRF_E_INVALID; }
+  if (m0 + M > a.cols || n0 + N > b.cols) { set_error("dw_gemm: column window outside the planes"); return NRF_E_INVALID; }
+  if (passes == 3 && (!a.lo || !b.lo)) { set_error("dw_gemm: 3 passes need the lo planes"); return NRF_E_INVALID; }
+  int rc;
+  if ((rc = encode_planes_map(&P.a_hi, a.hi, a.rows, a.cols, a.ld, 64, 64)) != NRF_OK) return rc;
+  if ((rc = encode_planes_map(&P.b_hi, b.hi, b.rows, b.cols, b.ld, 64, 64)) != NRF_OK) return rc;
+  if (passes == 3) {
+    if ((rc = encode_planes_map(&P.a_lo, a.lo, a.rows, a.cols, a.ld, 64, 64)) != NRF_OK) return rc;
+    if ((rc = encode_planes_map(&P.b_lo, b.lo, b.rows, b.cols, b.ld, 64, 64)) != NRF_OK) return rc;
+  }
+  P.m0 = m0; P.n0 = n0; P.N = N; P.passes = passes; P.S = a.rows; P.partial = partial; P.M_total = M;
+  const uint32_t planes = passes == 3 ? 2u : 1u;
+  const uint32_t stage_bytes = planes * (16384u + static_cast<uint32_t>(N) * 128u);
+  int stages = static_cast<int>((kGemmSmemLimit - 256) / stage_bytes);
+  P.n_stages = stages > 4 ? 4 : stages;
+  const int64_t n_chunks = (a.rows + 63) / 64;
+  int split = dw_gemm_max_split(n_sms, M);
+  if (split > max_split) split = max_split;
+  if (split > n_chunks) split = static_cast<int>(n_chunks);
+  if (split < 1) split = 1;
+  *n_split_out = split;
+  cudaError_t e = cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dw_gemm)");
+  dw_gemm_kernel<<<dim3(M / 128, split), kDwThreads, static_cast<uint32_t>(P.n_stages) * stage_bytes + 256, stream>>>(P);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "dw_gemm_kernel launch");
+}
+
+}  // namespace nrf

@@ -246,6 +246,49 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {
                : "memory");
 }
 
+// ------------------------------------------------------------------------------ training GEMMs (cta_group::1)
+// 2-D tensor TMA into this CTA's shared memory, completion counted on this CTA's mbarrier.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, int32_t c0, int32_t c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+// MN-major operand tile, 128-byte swizzle (PTX ISA canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), T = 8 fp16):
+// 64 consecutive M/N elements (128 B) per K row, 8 K rows per 1024-byte swizzle atom; atoms follow each other along K
+// every `sbo` bytes and along M/N every `lbo` bytes.  This is what a SWIZZLE_128B tensor-TMA box of
+// {64 elements, R rows} of a ROW-MAJOR [K, MN] matrix leaves in shared memory, so dY[S, out] / X[S, in] / W[out, in]
+// feed tcgen05.mma "transposed" without any data movement.  One K = 16 step = two atoms = 2048 bytes.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with explicit operand majors (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_major(uint32_t m, uint32_t n, uint32_t a_mn, uint32_t b_mn) {
+  return (1u << 4) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_ss_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xFFFFFFFF;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xFFFFFFFF;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------ operand layout helper
 // Byte offset of element (row, k) inside one [rows x 64] fp16 K-major SWIZZLE_128B tile whose base is
 // 1024-byte aligned: 16-byte chunk index (k/8) is XORed with (row % 8).

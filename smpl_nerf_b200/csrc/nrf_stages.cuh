@@ -8,6 +8,26 @@ namespace nrf {
 
 __device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
 
+// sin and cos of a (|a| < ~1e5) to ~1.2 ulp: 2-term Cody-Waite reduction by pi/2 (exact under FMA for
+// the encoder's arguments x * 2^k) and the Cephes sinf/cosf minimax polynomials on [-pi/4, pi/4].
+// Replaces libdevice sincosf, whose slow path (Payne-Hanek) bloats the kernel when inlined 100x.
+__device__ __forceinline__ void sincos_pe(float a, float& s_out, float& c_out) {
+  const float t = fmaf(a, 0.636619747f, 12582912.f);
+  const int qi = __float_as_int(t);
+  const float q = t - 12582912.f;
+  float r = fmaf(q, -1.57079637050628662109375f, a);
+  r = fmaf(q, 4.37113900018624283e-8f, r);
+  const float z = r * r;
+  float s = fmaf(fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f), z, -1.6666654611e-1f);
+  s = fmaf(s * z, r, r);
+  float c = fmaf(fmaf(fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z, -0.5f);
+  c = fmaf(c, z, 1.0f);
+  float ss = (qi & 1) ? c : s, cc = (qi & 1) ? s : c;
+  if (qi & 2) ss = -ss;
+  if ((qi + 1) & 2) cc = -cc;
+  s_out = ss; c_out = cc;
+}
+
 // ---------------------------------------------------------------------------------- per-sample stage
 // utils.py:161-175 for one sample: raw = (rgb_raw, sigma_raw) -> (sigmoid(rgb_raw), alpha) with
 // alpha = 1 - exp(-relu(sigma_raw [+ noise]) * dz * |dir|); dz is z[i+1] - z[i], or 1e10 for the last sample.

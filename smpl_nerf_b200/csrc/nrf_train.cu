@@ -1,0 +1,595 @@
+// Training path: the pipelines' forward computed LAYER BY LAYER with everything the backward needs kept in a caller-owned
+// workspace, and the backward of solver/nerf_solver.py:81-87 (`loss = MSE(rgb) + MSE(rgb_fine); loss.backward()`) down to
+// every nn.Linear parameter of the coarse, fine and warp-field nets.
+//
+//   forward (per pass):  encodings -> planes | per-ray inputs -> per-ray bias vectors | one tcgen05 GEMM per nn.Linear
+//                        (tile_gemm: bias / ReLU / hi-lo split fused in the epilogue) | sigma / rgb / warp heads |
+//                        compositing | inverse-CDF sampling (the sampler is detached, utils.py:260)
+//   backward (per pass): compositing backward -> d raw | heads | per layer: dW = dY^T X (dw_gemm, split-K), db, per-ray-input
+//                        columns, dX = dY W with ReLU' fused (tile_gemm, N-major weights) | SMPL: encodings' backward ->
+//                        warped points -> warp net
+// Gradients travel as fp16 hi/lo planes multiplied by ONE power-of-two scale derived on the device from max |d raw| and
+// divided out where a parameter gradient is written.  precision 0 = 3 MMA passes everywhere (fp32-equivalent), 1 = 1 pass.
+#include <cstdio>
+#include <cstring>
+
+#include "nrf_gemm.cuh"
+#include "nrf_plan.h"
+#include "nrf_ptx.cuh"
+#include "nrf_train_kernels.cuh"
+
+namespace nrf {
+
+struct TLayer {
+  int role, pidx, n_out, in_act, aux /*0 none, 1 xyz encoding, 2 direction encoding*/, aux_cols;
+  int ray_src /*0, 1 pose, 2 dir*/, ray_k, ld, col_act, col_ray, col_aux, relu;
+};
+struct TNet { int n; int nl; TLayer L[kMaxLayers]; int A, P, D; };
+
+static int plan_train_net(const NrfRayNetDesc* d, TNet* t) {
+  NetPlan tmp;
+  NrfRayNetDesc dd = *d;
+  dd.fold_linear = 0;
+  dd.ext_pose_bias = d->additional_input_dim > 0 ? 1 : 0;     // any A is fine here: pose inputs are always hoisted per ray
+  int rc = plan_raynet(&dd, &tmp);                             // shape validation (same limits as the renderer)
+  if (rc != NRF_OK) return rc;
+  memset(t, 0, sizeof(*t));
+  const int nl = d->n_layers, W = kWidth, A = d->additional_input_dim, P = d->positions_dim;
+  const int D = d->use_directional_input ? d->directions_dim : 0;
+  t->nl = nl; t->A = A; t->P = P; t->D = D;
+  auto is_skip = [&](int i) { for (int s = 0; s < d->n_skips; ++s) if (d->skips[s] == i) return true; return false; };
+  int n = 0;
+  { TLayer& L = t->L[n++]; L.role = ROLE_FIRST; L.pidx = 0; L.n_out = W; L.aux = 1; L.aux_cols = P; L.ray_src = A > 0 ? 1 : 0; L.ray_k = A;
+    L.ld = A + P; L.col_ray = 0; L.col_aux = A; L.relu = 1; }
+  for (int i = 0; i < nl - 1; ++i) {
+    TLayer& L = t->L[n++]; L.role = ROLE_TRUNK; L.pidx = 2 * (i + 1); L.n_out = W; L.in_act = W; L.relu = 1; L.ld = W;
+    if (is_skip(i)) { L.aux = 1; L.aux_cols = P; L.ray_src = A > 0 ? 1 : 0; L.ray_k = A; L.ld = W + A + P; L.col_ray = W; L.col_aux = W + A; }
+  }
+  { TLayer& L = t->L[n++]; L.role = ROLE_LINEAR; L.pidx = 2 * nl; L.n_out = W; L.in_act = W; L.ld = W; }
+  { TLayer& L = t->L[n++]; L.role = ROLE_DIR; L.pidx = 2 * nl + 4; L.n_out = W / 2; L.in_act = W; L.ld = W + D;
+    if (D > 0) { if (d->per_sample_dirs) { L.aux = 2; L.aux_cols = D; L.col_aux = W; } else { L.ray_src = 2; L.ray_k = D; L.col_ray = W; } } }
+  { TLayer& L = t->L[n++]; L.role = ROLE_RGB; L.pidx = 2 * nl + 6; L.n_out = W / 2; L.in_act = W / 2; L.ld = W / 2; L.relu = 1; }
+  t->n = n;
+  return NRF_OK;
+}
+
+// ------------------------------------------------------------------------------ workspace (bump allocator: same walk for sizing and use)
+struct Bump {
+  uint8_t* base; size_t off;
+  template <typename T> T* take(size_t count) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+  Planes planes(int64_t rows, int cols, bool lo) {
+    Planes p; p.rows = rows; p.cols = cols; p.ld = cols;
+    p.hi = take<__half>(static_cast<size_t>(rows) * cols);
+    p.lo = lo ? take<__half>(static_cast<size_t>(rows) * cols) : nullptr;
+    return p;
+  }
+};
+
+struct NetWeights { Planes act[kMaxLayers], aux[kMaxLayers]; };
+constexpr int kScaleSlots = 64, kWmaxSlots = 48;
+// wmax slots: [p * 20 + l] activation block of layer l of net p; [p * 20 + 16] rgb head, [p * 20 + 17] sigma head; [40] warp head
+static inline int wslot(int p, int l) { return p * 20 + l; }
+struct PassWs {
+  int64_t S; int n;
+  Planes encx, encd, wpe, warph, act[kMaxLayers];
+  float *a_f32, *h2_f32, *warph_f32, *raw, *dnorm, *warp_raw, *warped, *u, *rb[kMaxLayers], *rbw, *g_raw, *g_dnorm, *z;
+  const float* pts;
+};
+struct TrainWs {
+  NetWeights w[2]; Planes warp_w;
+  PassWs pass[2];
+  float *pose_feat, *dir_feat, *ray_norm, *weights_c, *alpha_c, *z_all, *pts_fine, *warp_pose_feat;
+  Planes dy[2];
+  float *dysum, *g_encx, *g_encd, *g_warp, *partial;
+  float* sc;               // [kScaleSlots][2]: {s, 1/s} of every gradient plane tensor of the backward chain
+  unsigned int* mx;        // [kScaleSlots]: row-L1 bounds (float bits); mx[0] = max |d raw| over both passes
+  unsigned int* wmax;      // [kWmaxSlots]: max |W| per (net, layer) activation block and per head (float bits; written by the forward)
+  size_t bytes;
+};
+
+struct TrainCfg {
+  int kind, nc, nf, na, run_fine, white, passes, smpl, A_pose /*per-ray pose features of the pipeline*/, n_sel;
+  int64_t B;
+};
+
+static void layout_ws(Bump& m, const TrainCfg& c, const TNet net[2], TrainWs* ws) {
+  const bool lo = c.passes == 3;
+  const int n_pass = c.run_fine ? 2 : 1;
+  for (int p = 0; p < n_pass; ++p)
+    for (int l = 0; l < net[p].n; ++l) {
+      const TLayer& L = net[p].L[l];
+      if (L.in_act) ws->w[p].act[l] = m.planes(L.n_out, L.in_act, lo);
+      if (L.aux) ws->w[p].aux[l] = m.planes(L.n_out, 64, lo);
+    }
+  if (c.smpl) ws->warp_w = m.planes(kWidth, 64, lo);
+  ws->pose_feat = m.take<float>(static_cast<size_t>(c.B) * (c.A_pose > 0 ? c.A_pose : 1));
+  ws->dir_feat = m.take<float>(static_cast<size_t>(c.B) * 64);
+  ws->ray_norm = m.take<float>(c.B);
+  ws->weights_c = m.take<float>(static_cast<size_t>(c.B) * c.nc);
+  ws->alpha_c = m.take<float>(static_cast<size_t>(c.B) * c.nc);
+  ws->z_all = m.take<float>(static_cast<size_t>(c.B) * c.na);
+  ws->pts_fine = m.take<float>(static_cast<size_t>(c.B) * c.na * 3);
+  int64_t Smax = 0;
+  for (int p = 0; p < n_pass; ++p) {
+    PassWs& w = ws->pass[p];
+    w.n = p == 0 ? c.nc : c.na;
+    w.S = c.B * w.n;
+    Smax = w.S > Smax ? w.S : Smax;
+    w.encx = m.planes(w.S, 64, lo);
+    if (c.smpl) { w.encd = m.planes(w.S, 64, lo); w.wpe = m.planes(w.S, 64, lo); w.warph = m.planes(w.S, kWidth, lo);
+                  w.warph_f32 = m.take<float>(static_cast<size_t>(w.S) * kWidth); w.warp_raw = m.take<float>(static_cast<size_t>(w.S) * 3);
+                  w.warped = m.take<float>(static_cast<size_t>(w.S) * 3); w.u = m.take<float>(static_cast<size_t>(w.S) * 3);
+                  w.rbw = m.take<float>(static_cast<size_t>(c.B) * kWidth); w.g_dnorm = m.take<float>(w.S); }
+    w.dnorm = m.take<float>(w.S);
+    for (int l = 0; l < net[p].n; ++l) {
+      const TLayer& L = net[p].L[l];
+      w.act[l] = m.planes(w.S, L.n_out, lo);
+      if (L.ray_src) w.rb[l] = m.take<float>(static_cast<size_t>(c.B) * L.n_out);
+    }
+    w.a_f32 = m.take<float>(static_cast<size_t>(w.S) * kWidth);
+    w.h2_f32 = m.take<float>(static_cast<size_t>(w.S) * (kWidth / 2));
+    w.raw = m.take<float>(static_cast<size_t>(w.S) * 4);
+    w.g_raw = m.take<float>(static_cast<size_t>(w.S) * 4);
+  }
+  ws->dy[0] = m.planes(Smax, kWidth, true);
+  ws->dy[1] = m.planes(Smax, kWidth, true);
+  ws->dysum = m.take<float>(static_cast<size_t>(c.B) * kWidth);
+  if (c.smpl) { ws->g_encx = m.take<float>(static_cast<size_t>(Smax) * 64); ws->g_encd = m.take<float>(static_cast<size_t>(Smax) * 64);
+                ws->g_warp = m.take<float>(static_cast<size_t>(Smax) * 3); }
+  ws->partial = m.take<float>(static_cast<size_t>(148) * kWidth * kWidth);
+  ws->sc = m.take<float>(2 * kScaleSlots);
+  ws->mx = reinterpret_cast<unsigned int*>(m.take<float>(kScaleSlots));
+  ws->wmax = reinterpret_cast<unsigned int*>(m.take<float>(kWmaxSlots));
+  ws->bytes = (m.off + 255) & ~static_cast<size_t>(255);
+}
+
+static int make_cfg(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, const NrfRayNetDesc* fine, const NrfWarpNetDesc* warp, int64_t B,
+                    TrainCfg* c, TNet net[2]) {
+  if (!pipe || !coarse) { set_error("train: pipe/coarse is NULL"); return NRF_E_INVALID; }
+  if (pipe->kind != NRF_KIND_NERF && pipe->kind != NRF_KIND_SMPL && pipe->kind != NRF_KIND_APPEND) { set_error("train: unknown pipeline kind %d", pipe->kind); return NRF_E_INVALID; }
+  if (B < 0) { set_error("train: B < 0"); return NRF_E_INVALID; }
+  memset(c, 0, sizeof(*c));
+  c->kind = pipe->kind; c->nc = pipe->n_coarse; c->run_fine = pipe->run_fine ? 1 : 0; c->nf = c->run_fine ? pipe->n_fine : 0;
+  c->na = c->nc + c->nf; c->white = pipe->white_background ? 1 : 0; c->passes = pipe->precision == 1 ? 1 : 3; c->B = B;
+  c->smpl = pipe->kind == NRF_KIND_SMPL;
+  if (c->nc < 2 || c->nc > 1024 || (c->run_fine && (c->nc < 3 || c->nf < 1 || c->na > 1024))) { set_error("train: unsupported sample counts %d + %d", c->nc, c->nf); return NRF_E_INVALID; }
+  int rc;
+  if ((rc = plan_train_net(coarse, &net[0])) != NRF_OK) return rc;
+  if (c->run_fine) {
+    if (!fine) { set_error("train: run_fine=1 needs the fine net"); return NRF_E_INVALID; }
+    if ((rc = plan_train_net(fine, &net[1])) != NRF_OK) return rc;
+    if (fine->additional_input_dim != coarse->additional_input_dim) { set_error("train: coarse/fine additional_input_dim differ"); return NRF_E_INVALID; }
+  }
+  if (pipe->kind != NRF_KIND_NERF) {
+    c->n_sel = pipe->pose_all ? pipe->pose_stride : 2;
+    c->A_pose = pipe->pose_encoded ? c->n_sel * (2 * pipe->pose_freqs + (pipe->pose_identity ? 1 : 0)) : c->n_sel;
+  }
+  if (c->smpl) {
+    if (!warp) { set_error("train: the smpl pipeline needs the warp net"); return NRF_E_INVALID; }
+    if (!pipe->pose_encoded) { set_error("train: the smpl pipeline is trainable with human_pose_encoding=1 only (the reference's fine pass always feeds the warp net encoded inputs, smpl_nerf_pipeline.py:71-77)"); return NRF_E_INVALID; }
+    if (warp->width != kWidth || warp->positions_dim != enc_dim(warp->in_freqs, warp->in_identity) || warp->positions_dim > 64) { set_error("train: unsupported warp net shape"); return NRF_E_INVALID; }
+    if (warp->pose_dim != c->A_pose) { set_error("train: warp net pose_dim %d != pipeline pose features %d", warp->pose_dim, c->A_pose); return NRF_E_INVALID; }
+    if (!coarse->per_sample_dirs || (c->run_fine && !fine->per_sample_dirs)) { set_error("train: smpl pipeline needs per_sample_dirs=1 nets"); return NRF_E_INVALID; }
+  } else {
+    if (coarse->per_sample_dirs) { set_error("train: per_sample_dirs=1 is only valid for the smpl pipeline"); return NRF_E_INVALID; }
+    if (coarse->additional_input_dim != c->A_pose) { set_error("train: pose feature count %d does not match the net's additional_input_dim %d", c->A_pose, coarse->additional_input_dim); return NRF_E_INVALID; }
+  }
+  return NRF_OK;
+}
+
+static int grid1(int64_t total, int block) {
+  int64_t g = (total + block - 1) / block;
+  return static_cast<int>(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g));
+}
+#define TRY(x) do { int rc__ = (x); if (rc__ != NRF_OK) return rc__; } while (0)
+#define LAUNCH_CHECK(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return cuda_fail(e__, what); } while (0)
+
+struct TrainCtx {
+  TrainCfg c; TNet net[2]; TrainWs ws;
+  const NrfPipelineDesc* pipe; const NrfRayNetDesc* nd[2]; const NrfWarpNetDesc* wd;
+  const float* const* par[3];      // coarse, fine, warp parameter tables (host arrays of device pointers)
+  NrfRenderIO io;
+  int n_sms; cudaStream_t st;
+};
+
+static int setup(TrainCtx& t, const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, const float* const* pc, int n_pc,
+                 const NrfRayNetDesc* fine, const float* const* pf, int n_pf, const NrfWarpNetDesc* warp, const float* const* pw, int n_pw,
+                 const NrfRenderIO* io, int64_t B, void* workspace, size_t ws_bytes, int n_sms, void* stream) {
+  TRY(make_cfg(pipe, coarse, fine, warp, B, &t.c, t.net));
+  if (!io) { set_error("train: io is NULL"); return NRF_E_INVALID; }
+  if (!pc || n_pc != 2 * (coarse->n_layers + 5)) { set_error("train: coarse RenderRayNet expects %d parameter tensors, got %d", 2 * (coarse->n_layers + 5), n_pc); return NRF_E_INVALID; }
+  if (t.c.run_fine && (!pf || n_pf != 2 * (fine->n_layers + 5))) { set_error("train: fine RenderRayNet expects %d parameter tensors, got %d", 2 * (fine->n_layers + 5), n_pf); return NRF_E_INVALID; }
+  if (t.c.smpl && (!pw || n_pw != 4)) { set_error("train: WarpFieldNet expects 4 parameter tensors, got %d", n_pw); return NRF_E_INVALID; }
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) { set_error("train: workspace must be a 256-byte aligned device buffer"); return NRF_E_INVALID; }
+  Bump m{static_cast<uint8_t*>(workspace), 0};
+  layout_ws(m, t.c, t.net, &t.ws);
+  if (t.ws.bytes > ws_bytes) { set_error("train: workspace too small (%zu bytes given, %zu needed)", ws_bytes, t.ws.bytes); return NRF_E_INVALID; }
+  t.pipe = pipe; t.nd[0] = coarse; t.nd[1] = fine; t.wd = warp; t.par[0] = pc; t.par[1] = pf; t.par[2] = pw;
+  t.io = *io; t.n_sms = n_sms; t.st = static_cast<cudaStream_t>(stream);
+  if (!io->ray_samples || !io->ray_origin || !io->ray_dir || !io->z_vals) { set_error("train: ray inputs are NULL"); return NRF_E_INVALID; }
+  if (t.c.kind != NRF_KIND_NERF && !io->goal_pose) { set_error("train: goal_pose is NULL"); return NRF_E_INVALID; }
+  if (t.c.run_fine && !io->u_fine) { set_error("train: u_fine is NULL"); return NRF_E_INVALID; }
+  return NRF_OK;
+}
+
+// ------------------------------------------------------------------------------ forward
+static int split_weights(TrainCtx& t) {
+  static thread_local SplitTable tab;
+  tab.n = 0;
+  auto flush = [&]() -> int {
+    if (tab.n == 0) return NRF_OK;
+    split_planes_kernel<<<dim3(8, tab.n), 256, 0, t.st>>>(tab);
+    tab.n = 0;
+    LAUNCH_CHECK("split_planes_kernel");
+    return NRF_OK;
+  };
+  cudaError_t e0 = cudaMemsetAsync(t.ws.wmax, 0, kWmaxSlots * sizeof(unsigned int), t.st);
+  if (e0 != cudaSuccess) return cuda_fail(e0, "cudaMemsetAsync(wmax)");
+  auto add = [&](const float* src, int rows, int cols, int ld, int col0, const Planes& dst, unsigned int* wmax) -> int {
+    SplitJob& j = tab.j[tab.n++];
+    j.src = src; j.rows = rows; j.cols = cols; j.ld = ld; j.col0 = col0; j.hi = dst.hi; j.lo = dst.lo; j.ld_dst = dst.ld; j.cols_pad = dst.cols;
+    j.wmax = wmax;
+    return tab.n == 40 ? flush() : NRF_OK;
+  };
+  const int n_pass = t.c.run_fine ? 2 : 1;
+  for (int p = 0; p < n_pass; ++p)
+    for (int l = 0; l < t.net[p].n; ++l) {
+      const TLayer& L = t.net[p].L[l];
+      const float* W = t.par[p][L.pidx];
+      if (!W || !t.par[p][L.pidx + 1]) { set_error("train: parameter %d of net %d is NULL", L.pidx, p); return NRF_E_INVALID; }
+      if (L.in_act) TRY(add(W, L.n_out, L.in_act, L.ld, L.col_act, t.ws.w[p].act[l], t.ws.wmax + wslot(p, l)));
+      if (L.aux) TRY(add(W, L.n_out, L.aux_cols, L.ld, L.col_aux, t.ws.w[p].aux[l], nullptr));
+    }
+  if (t.c.smpl) TRY(add(t.par[2][0], kWidth, t.wd->positions_dim, t.wd->positions_dim + t.wd->pose_dim, 0, t.ws.warp_w, nullptr));
+  TRY(flush());
+  for (int p = 0; p < n_pass; ++p) {
+    const int nl = t.net[p].nl;
+    absmax_kernel<<<1, 128, 0, t.st>>>(t.par[p][2 * nl + 8], 3 * (kWidth / 2), t.ws.wmax + wslot(p, 16));
+    absmax_kernel<<<1, 128, 0, t.st>>>(t.par[p][2 * nl + 2], kWidth, t.ws.wmax + wslot(p, 17));
+  }
+  if (t.c.smpl) absmax_kernel<<<1, 128, 0, t.st>>>(t.par[2][2], 3 * kWidth, t.ws.wmax + 40);
+  LAUNCH_CHECK("absmax_kernel");
+  return NRF_OK;
+}
+
+static int ray_bias(TrainCtx& t, const float* W, int ld, int col0, int K, const float* bias, const float* feat, int n_out, float* out) {
+  const size_t smem = static_cast<size_t>(8) * K * sizeof(float);
+  if (smem > 200 * 1024) { set_error("train: %d per-ray features do not fit the bias kernel", K); return NRF_E_INVALID; }
+  cudaError_t e = cudaFuncSetAttribute(ray_bias2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem > 48 * 1024 ? smem : 48 * 1024));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ray_bias2)");
+  ray_bias2_kernel<<<static_cast<unsigned>((t.c.B + 7) / 8), 256, smem, t.st>>>(W, ld, col0, K, bias, feat, t.c.B, n_out, out);
+  LAUNCH_CHECK("ray_bias2_kernel");
+  return NRF_OK;
+}
+
+static int heads(TrainCtx& t, const float* x, int64_t S, int K, const float* W, const float* b, int nh, float* out, int out_ld, int c0) {
+  heads_kernel<<<grid1(S, 8), 256, static_cast<size_t>(nh) * K * sizeof(float), t.st>>>(x, S, K, W, b, nh, out, out_ld, c0);
+  LAUNCH_CHECK("heads_kernel");
+  return NRF_OK;
+}
+
+static int encode(TrainCtx& t, const float* x, int64_t S, int freqs, int identity, const Planes& dst) {
+  encode_planes_kernel<<<grid1(S * 8, 256), 256, 0, t.st>>>(x, S, freqs, identity, dst.hi, dst.lo);
+  LAUNCH_CHECK("encode_planes_kernel");
+  return NRF_OK;
+}
+
+static int forward_pass(TrainCtx& t, int p) {
+  const TrainCfg& c = t.c;
+  PassWs& w = t.ws.pass[p];
+  const TNet& net = t.net[p];
+  const NrfRayNetDesc* d = t.nd[p];
+  const bool last = p == (c.run_fine ? 1 : 0);
+  const float* pts = w.pts;
+  if (c.smpl) {
+    // ---- warp field (models/smpl_nerf_pipeline.py:30-49, 71-79): x -> x + W2 relu(W1 [enc(x), enc(pose)] + b1) + b2
+    const int Pw = t.wd->positions_dim, Aw = t.wd->pose_dim;
+    TRY(encode(t, pts, w.S, t.wd->in_freqs, t.wd->in_identity, w.wpe));
+    const float* bias = t.par[2][1];
+    if (Aw > 0) { TRY(ray_bias(t, t.par[2][0], Pw + Aw, Pw, Aw, t.par[2][1], t.ws.pose_feat, kWidth, w.rbw)); bias = w.rbw; }
+    TileGemmArgs g{};
+    g.a[0] = w.wpe; g.b[0] = t.ws.warp_w; g.n_src = 1; g.N = kWidth; g.passes = c.passes; g.epi = GEPI_PLANES; g.relu = 1;
+    g.bias = bias; g.bias_ld = Aw > 0 ? kWidth : 0; g.rows_per_ray = w.n; g.out = w.warph; g.out_f32 = w.warph_f32; g.out_f32_ld = kWidth;
+    g.status = t.io.status;
+    TRY(launch_tile_gemm(g, t.n_sms, t.st));
+    TRY(heads(t, w.warph_f32, w.S, kWidth, t.par[2][2], t.par[2][3], 3, w.warp_raw, 3, 0));
+    smpl_points_kernel<<<grid1(w.S, 256), 256, 0, t.st>>>(pts, w.warp_raw, t.io.ray_origin, w.S, w.n, w.warped, w.u, w.dnorm,
+                                                           last ? t.io.warp_out : nullptr, last ? t.io.warped_out : nullptr);
+    LAUNCH_CHECK("smpl_points_kernel");
+    TRY(encode(t, w.warped, w.S, d->pos_freqs, d->pos_identity, w.encx));
+    TRY(encode(t, w.u, w.S, d->dir_freqs, d->dir_identity, w.encd));
+  } else {
+    TRY(encode(t, pts, w.S, d->pos_freqs, d->pos_identity, w.encx));
+  }
+  for (int l = 0; l < net.n; ++l) {
+    const TLayer& L = net.L[l];
+    const float* W = t.par[p][L.pidx];
+    const float* b = t.par[p][L.pidx + 1];
+    const float* bias = b;
+    if (L.ray_src) {
+      TRY(ray_bias(t, W, L.ld, L.col_ray, L.ray_k, b, L.ray_src == 1 ? t.ws.pose_feat : t.ws.dir_feat, L.n_out, w.rb[l]));
+      bias = w.rb[l];
+    }
+    TileGemmArgs g{};
+    int ns = 0;
+    if (L.in_act) { g.a[ns] = w.act[l - 1]; g.b[ns] = t.ws.w[p].act[l]; ++ns; }
+    if (L.aux) { g.a[ns] = L.aux == 1 ? w.encx : w.encd; g.b[ns] = t.ws.w[p].aux[l]; ++ns; }
+    g.n_src = ns; g.N = L.n_out; g.passes = c.passes; g.epi = GEPI_PLANES; g.relu = L.relu;
+    g.bias = bias; g.bias_ld = L.ray_src ? L.n_out : 0; g.rows_per_ray = w.n; g.out = w.act[l];
+    if (L.role == ROLE_LINEAR) { g.out_f32 = w.a_f32; g.out_f32_ld = kWidth; }
+    if (L.role == ROLE_RGB) { g.out_f32 = w.h2_f32; g.out_f32_ld = kWidth / 2; }
+    g.status = t.io.status;
+    TRY(launch_tile_gemm(g, t.n_sms, t.st));
+  }
+  const int nl = net.nl;
+  TRY(heads(t, w.h2_f32, w.S, kWidth / 2, t.par[p][2 * nl + 8], t.par[p][2 * nl + 9], 3, w.raw, 4, 0));
+  TRY(heads(t, w.a_f32, w.S, kWidth, t.par[p][2 * nl + 2], t.par[p][2 * nl + 3], 1, w.raw, 4, 3));
+  // ---- compositing: the SMPL coarse pass scales its deltas by |warped - o| per sample, every other pass by |ray_direction|
+  const bool per_sample = c.smpl && p == 0;
+  const float* dn = per_sample ? w.dnorm : t.ws.ray_norm;
+  const int wpb = 4;
+  const size_t smem = static_cast<size_t>(wpb) * (4 * w.n + 4 * ((w.n + 3) & ~3) + kTeamScratch) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem > 48 * 1024 ? smem : 48 * 1024));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(composite_fwd)");
+  float* rgb = p == 0 ? t.io.rgb : t.io.rgb_fine;
+  float* alpha = last ? t.io.alpha_out : t.ws.alpha_c;
+  if (!rgb) { set_error("train: rgb output of pass %d is NULL", p); return NRF_E_INVALID; }
+  composite_fwd_kernel<<<grid1(c.B, wpb), wpb * 32, smem, t.st>>>(w.raw, w.z, dn, per_sample ? 1 : 0, p == 0 ? t.io.noise_coarse : t.io.noise_fine, c.B, w.n,
+                                                                   c.white, rgb, p == 0 ? t.ws.weights_c : nullptr, alpha);
+  LAUNCH_CHECK("composite_fwd_kernel");
+  return NRF_OK;
+}
+
+static int forward_all(TrainCtx& t) {
+  const TrainCfg& c = t.c;
+  if (c.B == 0) return NRF_OK;
+  TRY(split_weights(t));
+  {
+    const NrfRayNetDesc* d = t.nd[0];
+    const int D = (d->use_directional_input && !c.smpl) ? d->directions_dim : 0;
+    ray_feats_kernel<<<grid1(c.B * (c.A_pose + D + 1), 256), 256, 0, t.st>>>(
+        t.io.goal_pose, t.pipe->pose_stride, c.n_sel, t.pipe->pose_col0, t.pipe->pose_col1, t.pipe->pose_all ? 1 : 0, t.pipe->pose_freqs,
+        t.pipe->pose_identity, t.pipe->pose_encoded ? 1 : 0, t.io.ray_dir, d->dir_freqs, d->dir_identity, c.B, c.A_pose, D, t.ws.pose_feat,
+        t.ws.dir_feat, t.ws.ray_norm);
+    LAUNCH_CHECK("ray_feats_kernel");
+  }
+  t.ws.pass[0].pts = t.io.ray_samples;
+  t.ws.pass[0].z = const_cast<float*>(t.io.z_vals);
+  TRY(forward_pass(t, 0));
+  if (c.run_fine) {
+    // the sampler is detached in the reference (utils.py:260): plain forward kernels, nothing saved but z_all / the points
+    float* pts = t.io.samples_out ? t.io.samples_out : t.ws.pts_fine;
+    if (t.io.z_all_in) {      // teacher-forced depths (stage-wise tests)
+      points_from_z_kernel<<<grid1(c.B * c.na, 256), 256, 0, t.st>>>(t.io.ray_origin, t.io.ray_dir, t.io.z_all_in, c.B, c.na, t.ws.z_all, pts);
+      LAUNCH_CHECK("points_from_z_kernel");
+    } else {
+      TRY(nrf_fine_sampling(t.io.ray_origin, t.io.ray_dir, t.io.z_vals, t.ws.weights_c, t.io.u_fine, c.B, c.nc, c.nf, t.ws.z_all, pts, t.st));
+    }
+    t.ws.pass[1].pts = pts;
+    t.ws.pass[1].z = t.ws.z_all;
+    TRY(forward_pass(t, 1));
+  }
+  return NRF_OK;
+}
+
+// ------------------------------------------------------------------------------ backward
+struct Grads { float* const* g[3]; };
+
+static int dw_into(TrainCtx& t, const Planes& dy, const float* sc, int M, const Planes& x, int n0, int N, int cols, float* dst, int ld, int col0) {
+  int split = 0;
+  TRY(launch_dw_gemm(dy, 0, M, x, n0, N, t.c.passes, t.ws.partial, 148, &split, t.n_sms, t.st));
+  dw_reduce_kernel<<<grid1(static_cast<int64_t>(M) * cols, 256), 256, 0, t.st>>>(t.ws.partial, split, M, N, cols, sc, dst, ld, col0);
+  LAUNCH_CHECK("dw_reduce_kernel");
+  return NRF_OK;
+}
+
+static int colsum_and_bias(TrainCtx& t, const Planes& dy, const float* sc, int F, int n, float* db) {
+  ray_colsum_kernel<<<static_cast<unsigned>(t.c.B), F, 0, t.st>>>(dy.hi, dy.lo, dy.ld, F, n, t.ws.dysum);
+  LAUNCH_CHECK("ray_colsum_kernel");
+  bias_grad_kernel<<<(F + 31) / 32, 256, 0, t.st>>>(t.ws.dysum, t.c.B, F, sc, db);
+  LAUNCH_CHECK("bias_grad_kernel");
+  return NRF_OK;
+}
+
+static int rayfeat_dw(TrainCtx& t, const float* sc, const float* feat, int n_out, int K, float* dW, int ld, int col0) {
+  rayfeat_dw_kernel<<<dim3((K + 15) / 16, (n_out + 15) / 16), 256, 0, t.st>>>(t.ws.dysum, feat, t.c.B, n_out, K, sc, dW, ld, col0);
+  LAUNCH_CHECK("rayfeat_dw_kernel");
+  return NRF_OK;
+}
+
+static int head_bwd(TrainCtx& t, const float* x, int64_t S, int K, const float* g, int g_ld, int c0, int nh, const float* W, const float* sc_out,
+                    int relu_mask, float* dW, float* db, const Planes* dy, unsigned int* l1max) {
+  const int rows = 128;
+  head_bwd_kernel<<<static_cast<unsigned>((S + rows - 1) / rows), 256, 0, t.st>>>(x, S, K, g, g_ld, c0, nh, W, sc_out, relu_mask, dW, db,
+                                                                                  dy ? dy->hi : nullptr, dy ? dy->lo : nullptr, dy ? dy->ld : 0, rows, l1max);
+  LAUNCH_CHECK("head_bwd_kernel");
+  return NRF_OK;
+}
+
+static int next_scale(TrainCtx& t, const unsigned int* lmax, float mul, const unsigned int* wmax, const unsigned int* ea, const unsigned int* eb, float* sc) {
+  scale_from_bound_kernel<<<1, 1, 0, t.st>>>(lmax, mul, wmax, ea, eb, sc);
+  LAUNCH_CHECK("scale_from_bound_kernel");
+  return NRF_OK;
+}
+
+static Planes view(const Planes& p, int cols, int64_t rows) { Planes v = p; v.cols = cols; v.rows = rows; return v; }     // same storage, narrower logical extent (ld kept)
+
+static int backward_pass(TrainCtx& t, int p, const Grads& G) {
+  const TrainCfg& c = t.c;
+  PassWs& w = t.ws.pass[p];
+  const TNet& net = t.net[p];
+  const int nl = net.nl;
+  float* const* g = G.g[p];
+  int cur = 0;
+  // scale / bound slots of this pass's chain: slot 0 is global (max |d raw|), this pass uses 1 + 24 p ...
+  int slot = 1 + 24 * p;
+  auto SC = [&](int k) { return t.ws.sc + 2 * k; };
+  auto MX = [&](int k) { return t.ws.mx + k; };
+  // ---- rgb head -> dY of the last (ReLU) layer: |dY| <= 3 max|d raw| max|W_rgb|
+  Planes dy = view(t.ws.dy[cur], kWidth / 2, w.S);
+  TRY(next_scale(t, MX(0), 3.f, t.ws.wmax + wslot(p, 16), nullptr, nullptr, SC(slot)));
+  TRY(head_bwd(t, w.h2_f32, w.S, kWidth / 2, w.g_raw, 4, 0, 3, t.par[p][2 * nl + 8], SC(slot), 1, g[2 * nl + 8], g[2 * nl + 9], &dy, MX(slot)));
+  // ---- sigma head (its contribution to d(additional_linear_layer output) is the rank-1 term of the dir layer's dX epilogue)
+  TRY(head_bwd(t, w.a_f32, w.S, kWidth, w.g_raw, 4, 3, 1, t.par[p][2 * nl + 2], nullptr, 0, g[2 * nl + 2], g[2 * nl + 3], nullptr, nullptr));
+  bool encx_written = false;
+  for (int l = net.n - 1; l >= 0; --l) {
+    const TLayer& L = net.L[l];
+    float* dW = g[L.pidx];
+    float* db = g[L.pidx + 1];
+    const float* sc = SC(slot);
+    dy = view(t.ws.dy[cur], L.n_out, w.S);
+    // parameter gradients
+    if (L.in_act) TRY(dw_into(t, dy, sc, L.n_out, w.act[l - 1], 0, L.in_act, L.in_act, dW, L.ld, L.col_act));
+    if (L.aux) TRY(dw_into(t, dy, sc, L.n_out, L.aux == 1 ? w.encx : w.encd, 0, 64, L.aux_cols, dW, L.ld, L.col_aux));
+    TRY(colsum_and_bias(t, dy, sc, L.n_out, w.n, db));
+    if (L.ray_src) TRY(rayfeat_dw(t, sc, L.ray_src == 1 ? t.ws.pose_feat : t.ws.dir_feat, L.n_out, L.ray_k, dW, L.ld, L.col_ray));
+    // gradient of the encodings (only the SMPL pipeline differentiates them: they are functions of the warp net); REAL units
+    if (c.smpl && L.aux) {
+      TileGemmArgs a{};
+      a.a[0] = dy; a.b[0] = t.ws.w[p].aux[l]; a.n_src = 1; a.b_mn = 1; a.N = 64; a.passes = c.passes; a.epi = GEPI_F32;
+      a.out_f32 = L.aux == 1 ? t.ws.g_encx : t.ws.g_encd; a.out_f32_ld = 64; a.accumulate = (L.aux == 1 && encx_written) ? 1 : 0;
+      a.sc_in = sc;
+      TRY(launch_tile_gemm(a, t.n_sms, t.st));
+      if (L.aux == 1) encx_written = true;
+    }
+    // dX -> the previous layer's dY (ReLU' of the previous layer fused; + the sigma head's rank-1 term below the dir layer)
+    if (L.in_act) {
+      const TLayer& Pv = net.L[l - 1];
+      const bool dir = L.role == ROLE_DIR;
+      // |dX| <= (largest row L1 norm of dY) max|W| (+ max|d sigma| max|w_sigma| for the rank-1 term)
+      TRY(next_scale(t, MX(slot), 1.f, t.ws.wmax + wslot(p, l), dir ? MX(0) : nullptr, dir ? t.ws.wmax + wslot(p, 17) : nullptr, SC(slot + 1)));
+      TileGemmArgs a{};
+      a.a[0] = dy; a.b[0] = t.ws.w[p].act[l]; a.n_src = 1; a.b_mn = 1; a.N = L.in_act; a.passes = c.passes; a.epi = GEPI_PLANES;
+      a.out = view(t.ws.dy[cur ^ 1], L.in_act, w.S);
+      if (Pv.relu) { a.mask_hi = w.act[l - 1].hi; a.mask_ld = w.act[l - 1].ld; }
+      if (dir) { a.row_scale = w.g_raw + 3; a.row_scale_ld = 4; a.col_vec = t.par[p][2 * nl + 2]; }
+      a.sc_in = sc; a.sc_out = SC(slot + 1); a.l1max = MX(slot + 1); a.status = t.io.status;
+      TRY(launch_tile_gemm(a, t.n_sms, t.st));
+      cur ^= 1;
+      ++slot;
+    }
+  }
+  if (c.smpl) {
+    const NrfRayNetDesc* d = t.nd[p];
+    ++slot;
+    smpl_points_bwd_kernel<<<grid1(w.S, 128), 128, 0, t.st>>>(t.ws.g_encx, d->pos_freqs, d->pos_identity, t.ws.g_encd, d->dir_freqs, d->dir_identity,
+                                                               w.warped, w.u, w.dnorm, p == 0 ? w.g_dnorm : nullptr, w.S, t.ws.g_warp, MX(slot));
+    LAUNCH_CHECK("smpl_points_bwd_kernel");
+    float* const* gw = G.g[2];
+    Planes dyw = view(t.ws.dy[0], kWidth, w.S);
+    TRY(next_scale(t, MX(slot), 3.f, t.ws.wmax + 40, nullptr, nullptr, SC(slot)));
+    TRY(head_bwd(t, w.warph_f32, w.S, kWidth, t.ws.g_warp, 3, 0, 3, t.par[2][2], SC(slot), 1, gw[2], gw[3], &dyw, nullptr));
+    const int Pw = t.wd->positions_dim, Aw = t.wd->pose_dim;
+    TRY(dw_into(t, dyw, SC(slot), kWidth, w.wpe, 0, 64, Pw, gw[0], Pw + Aw, 0));
+    TRY(colsum_and_bias(t, dyw, SC(slot), kWidth, w.n, gw[1]));
+    if (Aw > 0) TRY(rayfeat_dw(t, SC(slot), t.ws.pose_feat, kWidth, Aw, gw[0], Pw + Aw, Pw));
+  }
+  return NRF_OK;
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" size_t nrf_train_workspace_bytes(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, const NrfRayNetDesc* fine,
+                                            const NrfWarpNetDesc* warp, int64_t B) {
+  TrainCfg c; TNet net[2]; TrainWs ws;
+  if (make_cfg(pipe, coarse, fine, warp, B, &c, net) != NRF_OK) return 0;
+  Bump m{nullptr, 0};
+  layout_ws(m, c, net, &ws);
+  return ws.bytes;
+}
+
+extern "C" int nrf_train_forward(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, const float* const* params_coarse, int n_coarse,
+                                 const NrfRayNetDesc* fine, const float* const* params_fine, int n_fine, const NrfWarpNetDesc* warp,
+                                 const float* const* params_warp, int n_warp, const NrfRenderIO* io, int64_t B, void* workspace,
+                                 size_t workspace_bytes, int n_sms, void* stream) {
+  static thread_local TrainCtx t;
+  TRY(setup(t, pipe, coarse, params_coarse, n_coarse, fine, params_fine, n_fine, warp, params_warp, n_warp, io, B, workspace, workspace_bytes, n_sms, stream));
+  if (!io->rgb || (t.c.run_fine && !io->rgb_fine)) { set_error("train: rgb / rgb_fine outputs are NULL"); return NRF_E_INVALID; }
+  return forward_all(t);
+}
+
+extern "C" int nrf_train_backward(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, const float* const* params_coarse, int n_coarse,
+                                  const NrfRayNetDesc* fine, const float* const* params_fine, int n_fine, const NrfWarpNetDesc* warp,
+                                  const float* const* params_warp, int n_warp, const NrfRenderIO* io, int64_t B, void* workspace,
+                                  size_t workspace_bytes, const float* grad_rgb, const float* grad_rgb_fine, float* const* grads_coarse,
+                                  float* const* grads_fine, float* const* grads_warp, int n_sms, void* stream) {
+  static thread_local TrainCtx t;
+  TRY(setup(t, pipe, coarse, params_coarse, n_coarse, fine, params_fine, n_fine, warp, params_warp, n_warp, io, B, workspace, workspace_bytes, n_sms, stream));
+  const TrainCfg& c = t.c;
+  if (c.B == 0) return NRF_OK;
+  if (!grad_rgb || !grads_coarse || (c.run_fine && (!grad_rgb_fine || !grads_fine)) || (c.smpl && !grads_warp)) { set_error("train: gradient pointers are NULL"); return NRF_E_INVALID; }
+  for (int i = 0; i < n_coarse; ++i) if (!grads_coarse[i]) { set_error("train: coarse gradient %d is NULL", i); return NRF_E_INVALID; }
+  if (c.run_fine) for (int i = 0; i < n_fine; ++i) if (!grads_fine[i]) { set_error("train: fine gradient %d is NULL", i); return NRF_E_INVALID; }
+  if (c.smpl) for (int i = 0; i < 4; ++i) if (!grads_warp[i]) { set_error("train: warp gradient %d is NULL", i); return NRF_E_INVALID; }
+  // the workspace holds what nrf_train_forward left there for this batch; re-derive the pointers the forward set at run time
+  t.ws.pass[0].pts = t.io.ray_samples; t.ws.pass[0].z = const_cast<float*>(t.io.z_vals);
+  if (c.run_fine) { t.ws.pass[1].pts = t.io.samples_out ? t.io.samples_out : t.ws.pts_fine; t.ws.pass[1].z = t.ws.z_all; }
+  cudaError_t e = cudaMemsetAsync(t.ws.mx, 0, kScaleSlots * sizeof(unsigned int), t.st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(mx)");
+  const int n_pass = c.run_fine ? 2 : 1;
+  for (int p = 0; p < n_pass; ++p) {
+    PassWs& w = t.ws.pass[p];
+    const bool per_sample = c.smpl && p == 0;
+    const int wpb = 4;
+    const size_t smem = static_cast<size_t>(wpb) * (4 * w.n + 6 * ((w.n + 3) & ~3)) * sizeof(float);
+    e = cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem > 48 * 1024 ? smem : 48 * 1024));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(composite_bwd)");
+    composite_bwd_kernel<<<grid1(c.B, wpb), wpb * 32, smem, t.st>>>(w.raw, w.z, per_sample ? w.dnorm : t.ws.ray_norm, per_sample ? 1 : 0,
+                                                                     p == 0 ? t.io.noise_coarse : t.io.noise_fine, c.B, w.n, c.white,
+                                                                     p == 0 ? grad_rgb : grad_rgb_fine, w.g_raw, per_sample ? w.g_dnorm : nullptr, t.ws.mx);
+    LAUNCH_CHECK("composite_bwd_kernel");
+  }
+  Grads G; G.g[0] = grads_coarse; G.g[1] = grads_fine; G.g[2] = grads_warp;
+  for (int p = 0; p < n_pass; ++p) TRY(backward_pass(t, p, G));
+  return NRF_OK;
+}
+
+// ---- building blocks exported for stage-wise tests (tests/test_gpu_train.py) ----
+extern "C" int nrf_split_planes(const float* src, int64_t rows, int32_t cols, int32_t ld, void* hi, void* lo, int32_t ld_dst, int32_t cols_pad, void* stream) {
+  if (!src || !hi || rows < 0 || cols < 1 || cols_pad < cols) { set_error("split_planes: bad arguments"); return NRF_E_INVALID; }
+  if (rows == 0) return NRF_OK;
+  static thread_local SplitTable tab;
+  tab.n = 1;
+  SplitJob& j = tab.j[0];
+  j.src = src; j.rows = static_cast<int32_t>(rows); j.cols = cols; j.ld = ld; j.col0 = 0; j.hi = static_cast<__half*>(hi); j.lo = static_cast<__half*>(lo);
+  j.ld_dst = ld_dst; j.cols_pad = cols_pad;
+  split_planes_kernel<<<dim3(64, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(tab);
+  LAUNCH_CHECK("split_planes_kernel");
+  return NRF_OK;
+}
+
+extern "C" int nrf_gemm_planes(int32_t b_mn, const void* a_hi, const void* a_lo, int64_t S, int32_t K, const void* b_hi, const void* b_lo, int32_t N,
+                               int32_t passes, const float* bias, int32_t relu, float* out_f32, void* out_hi, void* out_lo, void* stream) {
+  TileGemmArgs g{};
+  g.a[0] = Planes{static_cast<__half*>(const_cast<void*>(a_hi)), static_cast<__half*>(const_cast<void*>(a_lo)), S, K, K};
+  g.b[0] = b_mn ? Planes{static_cast<__half*>(const_cast<void*>(b_hi)), static_cast<__half*>(const_cast<void*>(b_lo)), K, N, N}
+                : Planes{static_cast<__half*>(const_cast<void*>(b_hi)), static_cast<__half*>(const_cast<void*>(b_lo)), N, K, K};
+  g.n_src = 1; g.b_mn = b_mn; g.N = N; g.passes = passes; g.relu = relu; g.bias = bias;
+  if (out_hi) { g.epi = GEPI_PLANES; g.out = Planes{static_cast<__half*>(out_hi), static_cast<__half*>(out_lo), S, N, N}; g.out_f32 = out_f32; g.out_f32_ld = N; }
+  else { g.epi = GEPI_F32; g.out_f32 = out_f32; g.out_f32_ld = N; }
+  return launch_tile_gemm(g, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nrf_gemm_dw(const void* a_hi, const void* a_lo, int32_t M, const void* b_hi, const void* b_lo, int32_t N, int64_t S, int32_t passes,
+                           float* partial, int32_t max_split, float* out /* [M, N], accumulated into */, void* stream) {
+  if (!partial || !out || max_split < 1) { set_error("gemm_dw: bad arguments"); return NRF_E_INVALID; }
+  Planes a{static_cast<__half*>(const_cast<void*>(a_hi)), static_cast<__half*>(const_cast<void*>(a_lo)), S, M, M};
+  Planes b{static_cast<__half*>(const_cast<void*>(b_hi)), static_cast<__half*>(const_cast<void*>(b_lo)), S, N, N};
+  int split = 0;
+  TRY(launch_dw_gemm(a, 0, M, b, 0, N, passes, partial, max_split, &split, 0, static_cast<cudaStream_t>(stream)));
+  // unit scale: scale2 = {1, 1} lives behind the partial sums
+  float* scale2 = partial + static_cast<size_t>(max_split) * M * N;
+  const float one[2] = {1.f, 1.f};
+  cudaError_t e = cudaMemcpyAsync(scale2, one, sizeof(one), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(scale)");
+  dw_reduce_kernel<<<grid1(static_cast<int64_t>(M) * N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, split, M, N, N, scale2, out, N, 0);
+  LAUNCH_CHECK("dw_reduce_kernel");
+  return NRF_OK;
+}

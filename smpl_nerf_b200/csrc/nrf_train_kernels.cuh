@@ -1,0 +1,478 @@
+// CUDA-core kernels of the training path: everything around the tcgen05 GEMMs of nrf_gemm.cu.
+// All of them are HBM-bound streaming / reduction kernels (one pass over a [samples x features] plane or a [rays x n] table).
+//
+// Reference code being differentiated: models/render_ray_net.py:42-61, models/warp_field_net.py:17-21, utils.py:114-131
+// (encoding), utils.py:134-191 (compositing), models/*_pipeline.py (orchestration); the loss side is
+// solver/nerf_solver.py:48-51 (MSE on rgb and rgb_fine).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "nrf_plan.h"
+#include "nrf_stages.cuh"
+
+namespace nrf {
+
+__device__ __forceinline__ void split_store(float x, __half* hi, __half* lo) {
+  const __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+  *hi = h;
+  if (lo) *lo = __float2half_rn(x - __half2float(h));
+}
+
+// ---------------------------------------------------------------------------------- fp32 matrix -> hi/lo planes (weights)
+struct SplitJob { const float* src; int32_t rows, cols, ld, col0; __half* hi; __half* lo; int32_t ld_dst, cols_pad; unsigned int* wmax; };   // wmax: max |src| (float bits), optional
+struct SplitTable { int32_t n; SplitJob j[40]; };
+
+__global__ void split_planes_kernel(const __grid_constant__ SplitTable t) {
+  const SplitJob& j = t.j[blockIdx.y];
+  const int total = j.rows * j.cols_pad;
+  float m = 0.f;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / j.cols_pad, c = idx - r * j.cols_pad;
+    const float v = c < j.cols ? j.src[static_cast<size_t>(r) * j.ld + j.col0 + c] : 0.f;
+    split_store(v, j.hi + static_cast<size_t>(r) * j.ld_dst + c, j.lo ? j.lo + static_cast<size_t>(r) * j.ld_dst + c : nullptr);
+    m = fmaxf(m, fabsf(v));
+  }
+  if (j.wmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && isfinite(m)) atomicMax(j.wmax, __float_as_uint(m));
+  }
+}
+// max |x| of a small fp32 tensor (head weights) into float bits
+__global__ void absmax_kernel(const float* __restrict__ x, int n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && isfinite(m)) atomicMax(out, __float_as_uint(m));
+}
+
+// ---------------------------------------------------------------------------------- positional encoding -> planes
+// utils.py:127-131 in REFERENCE feature order ([x?] ++ for k: sin(2^k x), cos(2^k x), each over the 3 components), zero
+// padded to 64 features, as fp16 hi/lo planes [S, 64]: the K-chunk an MLP layer multiplies with its xyz / direction columns.
+__global__ void encode_planes_kernel(const float* __restrict__ x, int64_t S, int freqs, int identity, __half* __restrict__ hi,
+                                     __half* __restrict__ lo) {
+  const int64_t total = S * 8;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t s = idx >> 3;
+    const int f0 = static_cast<int>(idx & 7) * 8;
+    const float v[3] = {x[s * 3], x[s * 3 + 1], x[s * 3 + 2]};
+    const int n_id = identity ? 3 : 0, width = n_id + 6 * freqs;
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = f0 + i;
+      float val = 0.f;
+      if (f < n_id) val = v[f];
+      else if (f < width) {
+        const int j = f - n_id, k = j / 6, rem = j - 6 * k;
+        float sv, cv;
+        sincos_pe(v[rem % 3] * __int_as_float((127 + k) << 23), sv, cv);
+        val = rem < 3 ? sv : cv;
+      }
+      split_store(val, &h[i], &l[i]);
+    }
+    *reinterpret_cast<uint4*>(hi + s * 64 + f0) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + s * 64 + f0) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// ---------------------------------------------------------------------------------- per-ray features
+// pose features [B, A]: encode(goal_pose[:, cols]) in the reference's order (models/append_to_nerf_pipeline.py:26-37,
+// models/append_smpl_params_pipeline.py:30-37, models/smpl_nerf_pipeline.py:28-30); direction features [B, D]:
+// encode(ray_direction / |ray_direction|) (models/nerf_pipeline.py:30-35); ray_norm [B] = |ray_direction|.
+__global__ void ray_feats_kernel(const float* __restrict__ goal_pose, int pose_stride, int n_sel, int col0, int col1, int pose_all,
+                                 int pose_freqs, int pose_identity, int pose_encoded, const float* __restrict__ ray_dir,
+                                 int dir_freqs, int dir_identity, int64_t B, int A, int D, float* __restrict__ pose_feat,
+                                 float* __restrict__ dir_feat, float* __restrict__ ray_norm) {
+  const int per = A + D + 1;
+  const int64_t total = B * per;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = idx / per;
+    int i = static_cast<int>(idx - b * per);
+    if (i < A) {
+      auto comp = [&](int c) { return goal_pose[b * pose_stride + (pose_all ? c : (c == 0 ? col0 : col1))]; };
+      float val;
+      if (!pose_encoded) val = comp(i);
+      else if (pose_identity && i < n_sel) val = comp(i);
+      else {
+        const int j = i - (pose_identity ? n_sel : 0), k = j / (2 * n_sel), rem = j - k * 2 * n_sel;
+        const float a = comp(rem % n_sel) * __int_as_float((127 + k) << 23);
+        float sv, cv;
+        sincos_pe(a, sv, cv);
+        val = rem < n_sel ? sv : cv;
+      }
+      pose_feat[b * A + i] = val;
+      continue;
+    }
+    i -= A;
+    const float d0 = ray_dir[b * 3], d1 = ray_dir[b * 3 + 1], d2 = ray_dir[b * 3 + 2];
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+    if (i == D) { ray_norm[b] = nrm; continue; }
+    const float u[3] = {__fdiv_rn(d0, nrm), __fdiv_rn(d1, nrm), __fdiv_rn(d2, nrm)};
+    float val;
+    if (dir_identity && i < 3) val = u[i];
+    else {
+      const int j = i - (dir_identity ? 3 : 0), k = j / 6, rem = j - 6 * k;
+      float sv, cv;
+      sincos_pe(u[rem % 3] * __int_as_float((127 + k) << 23), sv, cv);
+      val = rem < 3 ? sv : cv;
+    }
+    dir_feat[b * D + i] = val;
+  }
+}
+
+// out[b, n] = bias[n] + sum_k W[n, col0 + k] * feat[b, k]: the per-ray constant inputs of a layer folded into a per-ray bias
+// (8 rays per CTA, features staged in shared memory, thread = output feature).
+__global__ void ray_bias2_kernel(const float* __restrict__ W, int ld, int col0, int K, const float* __restrict__ bias,
+                                 const float* __restrict__ feat, int64_t B, int n_out, float* __restrict__ out) {
+  extern __shared__ float fs[];     // [8][K]
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * 8;
+  for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
+    const int64_t b = b0 + i / K;
+    fs[i] = b < B ? feat[b * K + i % K] : 0.f;
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < n_out; n += blockDim.x) {
+    float acc[8];
+    const float bn = bias[n];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = bn;
+    const float* w = W + static_cast<size_t>(n) * ld + col0;
+    for (int k = 0; k < K; ++k) {
+      const float wk = __ldg(w + k);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] = fmaf(wk, fs[r * K + k], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if (b0 + r < B) out[(b0 + r) * n_out + n] = acc[r];
+  }
+}
+
+// ---------------------------------------------------------------------------------- small heads (N = 1 or 3: CUDA cores)
+// out[s, c0 + c] = b[c] + sum_k W[c, k] x[s, k]     (sigma_out_layer / rgb_out_layer / WarpFieldNet.linear2)
+__global__ void heads_kernel(const float* __restrict__ x, int64_t S, int K, const float* __restrict__ W, const float* __restrict__ b, int nh,
+                             float* __restrict__ out, int out_ld, int c0) {
+  extern __shared__ float ws[];     // [nh][K]
+  for (int i = threadIdx.x; i < nh * K; i += blockDim.x) ws[i] = W[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t s = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); s < S; s += static_cast<int64_t>(gridDim.x) * wpb) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float v = x[s * K + k];
+      a0 = fmaf(v, ws[k], a0);
+      if (nh > 1) { a1 = fmaf(v, ws[K + k], a1); a2 = fmaf(v, ws[2 * K + k], a2); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+      out[s * out_ld + c0] = a0 + b[0];
+      if (nh > 1) { out[s * out_ld + c0 + 1] = a1 + b[1]; out[s * out_ld + c0 + 2] = a2 + b[2]; }
+    }
+  }
+}
+
+// Backward of a head over a block of rows: thread = input feature k.
+//   dW[c, k] += sum_s g[s, c] x[s, k]      db[c] += sum_s g[s, c]      dY[s, k] = sum_c g[s, c] W[c, k]   (-> planes, masked by x > 0)
+// g is the upstream gradient in REAL units (fp32); the planes are written as real * sc_out[0].  l1max: see TileGemmParams.
+__global__ void head_bwd_kernel(const float* __restrict__ x, int64_t S, int K, const float* __restrict__ g, int g_ld, int c0, int nh,
+                                const float* __restrict__ W, const float* __restrict__ sc_out, int relu_mask,
+                                float* __restrict__ dW, float* __restrict__ db, __half* __restrict__ dy_hi, __half* __restrict__ dy_lo, int dy_ld,
+                                int rows_per_block, unsigned int* __restrict__ l1max) {
+  const int k = threadIdx.x;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  const float sc = sc_out ? __ldg(sc_out) : 1.f;
+  float l1_run = 0.f;
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+  if (k < K) { w0 = W[k]; if (nh > 1) { w1 = W[K + k]; w2 = W[2 * K + k]; } }
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  for (int64_t s = r0; s < r0 + rows_per_block && s < S; ++s) {
+    const float g0 = g[s * g_ld + c0], g1 = nh > 1 ? g[s * g_ld + c0 + 1] : 0.f, g2 = nh > 1 ? g[s * g_ld + c0 + 2] : 0.f;
+    b0 += g0; b1 += g1; b2 += g2;
+    float dy = 0.f;
+    if (k < K) {
+      const float xv = x[s * K + k];
+      a0 = fmaf(g0, xv, a0); a1 = fmaf(g1, xv, a1); a2 = fmaf(g2, xv, a2);
+      if (dy_hi) {
+        dy = fmaf(g0, w0, fmaf(g1, w1, g2 * w2));
+        if (relu_mask && !(xv > 0.f)) dy = 0.f;
+        split_store(dy * sc, dy_hi + s * dy_ld + k, dy_lo ? dy_lo + s * dy_ld + k : nullptr);
+      }
+    }
+    if (l1max) {          // L1 norm of this warp's 32 columns of the row (real units)
+      float a = fabsf(dy);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      l1_run = fmaxf(l1_run, a);
+    }
+  }
+  if (l1max && (threadIdx.x & 31) == 0 && isfinite(l1_run)) atomicMax(l1max, __float_as_uint(l1_run * static_cast<float>((K + 31) / 32)));
+  const float f = 1.f;
+  if (k < K) {
+    atomicAdd(dW + k, a0 * f);
+    if (nh > 1) { atomicAdd(dW + K + k, a1 * f); atomicAdd(dW + 2 * K + k, a2 * f); }
+  }
+  if (k == 0) {
+    atomicAdd(db, b0 * f);
+    if (nh > 1) { atomicAdd(db + 1, b1 * f); atomicAdd(db + 2, b2 * f); }
+  }
+}
+
+// ---------------------------------------------------------------------------------- compositing (forward / backward)
+// One warp per ray; dnorm is per sample ([B, n], the SMPL coarse pass: |warped - o|, smpl_nerf_pipeline.py:52,63) or per ray ([B]).
+__global__ void composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ dnorm, int per_sample,
+                                     const float* __restrict__ noise, int64_t B, int n, int white, float* __restrict__ rgb,
+                                     float* __restrict__ weights, float* __restrict__ alpha) {
+  extern __shared__ __align__(16) float smem[];
+  const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n4 = (n + 3) & ~3;
+  float4* raw4 = reinterpret_cast<float4*>(smem) + static_cast<size_t>(w) * n;
+  float* tf = smem + static_cast<size_t>(wpb) * n * 4 + static_cast<size_t>(w) * (4 * n4 + kTeamScratch);
+  float* tt = tf + n4; float* zs = tt + n4; float* dn = zs + n4; float* ts = tf + 4 * n4;
+  for (int64_t ray = blockIdx.x * static_cast<int64_t>(wpb) + w; ray < B; ray += static_cast<int64_t>(gridDim.x) * wpb) {
+    for (int i = lane; i < n; i += 32) {
+      raw4[i] = *reinterpret_cast<const float4*>(raw + (ray * n + i) * 4);
+      zs[i] = z[ray * n + i];
+      dn[i] = per_sample ? dnorm[ray * n + i] : dnorm[ray];
+    }
+    __syncwarp();
+    composite_ray(raw4, zs, dn, 0.f, n, noise ? noise + ray * n : nullptr, white, rgb + ray * 3, alpha ? alpha + ray * n : nullptr,
+                  weights ? weights + ray * n : nullptr, tf, tt, ts, lane);
+    __syncwarp();
+  }
+}
+
+// d(loss)/d(raw) [B, n, 4] from d(loss)/d(rgb) [B, 3] (see raw2outputs_bwd_kernel in nrf_ops.cu for the formulas), plus
+// d(loss)/d(dnorm) [B, n] when the per-sample norm is itself a function of the nets (SMPL coarse pass), and the running
+// maximum of |d raw| (as float bits: non-negative floats order like unsigned integers) for the gradient scale.
+__global__ void composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ dnorm, int per_sample,
+                                     const float* __restrict__ noise, int64_t B, int n, int white, const float* __restrict__ g_rgb,
+                                     float* __restrict__ g_raw, float* __restrict__ g_dnorm, unsigned int* __restrict__ gmax_bits) {
+  extern __shared__ __align__(16) float smem[];
+  const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n4 = (n + 3) & ~3;
+  float4* act4 = reinterpret_cast<float4*>(smem) + static_cast<size_t>(w) * n;
+  float* base = smem + static_cast<size_t>(wpb) * n * 4 + static_cast<size_t>(w) * 6 * n4;
+  float* keep = base; float* T = keep + n4; float* gw = T + n4; float* suf = gw + n4; float* dsig = suf + n4; float* ddel = dsig + n4;
+  float gmax = 0.f;
+  for (int64_t ray = blockIdx.x * static_cast<int64_t>(wpb) + w; ray < B; ray += static_cast<int64_t>(gridDim.x) * wpb) {
+    const float gr = g_rgb[ray * 3], gg = g_rgb[ray * 3 + 1], gb = g_rgb[ray * 3 + 2];
+    for (int i = lane; i < n; i += 32) {
+      const float4 r = *reinterpret_cast<const float4*>(raw + (ray * n + i) * 4);
+      const float nrm = per_sample ? dnorm[ray * n + i] : dnorm[ray];
+      const float dz = (i < n - 1) ? __fsub_rn(z[ray * n + i + 1], z[ray * n + i]) : 1e10f;
+      const float delta = __fmul_rn(dz, nrm);
+      const float s = noise ? __fadd_rn(r.w, noise[ray * n + i]) : r.w;
+      const float e = expf(-__fmul_rn(fmaxf(s, 0.f), delta));          // = 1 - alpha
+      const float a = __fsub_rn(1.f, e);
+      act4[i] = make_float4(sigmoidf_ref(r.x), sigmoidf_ref(r.y), sigmoidf_ref(r.z), a);
+      keep[i] = __fadd_rn(__fsub_rn(1.f, a), 1e-10f);
+      dsig[i] = s > 0.f ? delta * e : 0.f;                              // d alpha / d sigma
+      ddel[i] = s > 0.f ? s * e * dz : 0.f;                             // d alpha / d dnorm
+    }
+    __syncwarp();
+    if (lane == 0) serial_scan<true>(keep, T, n);
+    __syncwarp();
+    const float bg = white ? (gr + gg + gb) : 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const float4 c = act4[i];
+      const float g = gr * c.x + gg * c.y + gb * c.z - bg;
+      gw[i] = g;
+      suf[i] = g * (c.w * T[i]);
+    }
+    __syncwarp();
+    if (lane == 0) { float run = 0.f; for (int i = n - 1; i >= 0; --i) { const float v = suf[i]; suf[i] = run; run += v; } }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const float4 c = act4[i];
+      const float wi = c.w * T[i];
+      const float ga = gw[i] * T[i] - suf[i] / keep[i];
+      float4 o;
+      o.x = wi * gr * c.x * (1.f - c.x);
+      o.y = wi * gg * c.y * (1.f - c.y);
+      o.z = wi * gb * c.z * (1.f - c.z);
+      o.w = ga * dsig[i];
+      *reinterpret_cast<float4*>(g_raw + (ray * n + i) * 4) = o;
+      if (g_dnorm) g_dnorm[ray * n + i] = ga * ddel[i];
+      gmax = fmaxf(gmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  if (lane == 0 && isfinite(gmax)) atomicMax(gmax_bits, __float_as_uint(gmax));
+}
+
+// sc = {s, 1/s} with s the largest power of two such that s * bound <= 2^15, where
+//   bound = lmax * mul * wmax + ea * eb
+// is an upper bound of the magnitudes about to be written into fp16 gradient planes (lmax: largest row L1 norm of the incoming
+// gradient or max |d raw|; wmax: max |W| of the layer it is multiplied with; ea * eb: the sigma head's rank-1 term).  The
+// bound is typically 30-150x above the actual maximum, which then sits around 2^8..2^10: ~24 octaves of normal fp16 range
+// below it, 5 above -- per LAYER, so neither growth nor decay along the backward chain can leave the range.
+__global__ void scale_from_bound_kernel(const unsigned int* __restrict__ lmax, float mul, const unsigned int* __restrict__ wmax,
+                                        const unsigned int* __restrict__ ea, const unsigned int* __restrict__ eb, float* __restrict__ sc) {
+  float bound = __uint_as_float(*lmax) * mul * (wmax ? __uint_as_float(*wmax) : 1.f);
+  if (ea && eb) bound += __uint_as_float(*ea) * __uint_as_float(*eb);
+  float s = 1.f;
+  if (bound > 0.f && isfinite(bound)) {
+    int e;
+    frexpf(bound, &e);                  // bound = f * 2^e, f in [0.5, 1)  ->  bound <= 2^e
+    e = 15 - e;
+    e = e > 120 ? 120 : (e < -120 ? -120 : e);
+    s = ldexpf(1.f, e);
+  }
+  sc[0] = s; sc[1] = 1.f / s;
+}
+
+// ---------------------------------------------------------------------------------- reductions for bias / per-ray-input grads
+// dysum[b, f] = sum over the n samples of ray b of (hi + lo)[s, f]      (block = ray, thread = feature)
+__global__ void ray_colsum_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int ld, int F, int n, float* __restrict__ dysum) {
+  const int64_t b = blockIdx.x;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const int64_t o = (b * n + i) * ld + f;
+      acc += __half2float(hi[o]) + (lo ? __half2float(lo[o]) : 0.f);
+    }
+    dysum[b * F + f] = acc;
+  }
+}
+// db[f] += inv_scale * sum_b dysum[b, f]      (block = 32 features x 8 ray lanes)
+__global__ void bias_grad_kernel(const float* __restrict__ dysum, int64_t B, int F, const float* __restrict__ scale2, float* __restrict__ db) {
+  __shared__ float red[8][33];
+  const int fx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int f = blockIdx.x * 32 + fx;
+  float acc = 0.f;
+  if (f < F) for (int64_t b = ry; b < B; b += 8) acc += dysum[b * F + f];
+  red[ry][fx] = acc;
+  __syncthreads();
+  if (ry == 0 && f < F) {
+    float t = 0.f;
+    for (int r = 0; r < 8; ++r) t += red[r][fx];
+    db[f] += t * __ldg(scale2 + 1);
+  }
+}
+// dW[n, col0 + k] += inv_scale * sum_b dysum[b, n] feat[b, k]      (16 x 16 output tile per CTA, rays in steps of 16 via smem)
+__global__ void rayfeat_dw_kernel(const float* __restrict__ dysum, const float* __restrict__ feat, int64_t B, int n_out, int K,
+                                  const float* __restrict__ scale2, float* __restrict__ dW, int ld, int col0) {
+  __shared__ float ys[16][17], fs[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int k = blockIdx.x * 16 + tx, n = blockIdx.y * 16 + ty;
+  float acc = 0.f;
+  for (int64_t b0 = 0; b0 < B; b0 += 16) {
+    const int64_t b = b0 + ty;
+    ys[ty][tx] = (b < B && blockIdx.y * 16 + tx < n_out) ? dysum[b * n_out + blockIdx.y * 16 + tx] : 0.f;
+    fs[ty][tx] = (b < B && k < K) ? feat[b * K + k] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc = fmaf(ys[r][ty], fs[r][tx], acc);
+    __syncthreads();
+  }
+  if (k < K && n < n_out) dW[static_cast<size_t>(n) * ld + col0 + k] += acc * __ldg(scale2 + 1);
+}
+// dst[m, col0 + c] += inv_scale * sum_split partial[split][m][c]        (c < cols; the partials are N wide)
+__global__ void dw_reduce_kernel(const float* __restrict__ partial, int n_split, int M, int N, int cols, const float* __restrict__ scale2,
+                                 float* __restrict__ dst, int ld, int col0) {
+  const int total = M * cols;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int m = idx / cols, c = idx - m * cols;
+    float acc = 0.f;
+    for (int s = 0; s < n_split; ++s) acc += partial[(static_cast<size_t>(s) * M + m) * N + c];
+    dst[static_cast<size_t>(m) * ld + col0 + c] += acc * __ldg(scale2 + 1);
+  }
+}
+
+// pts[b, i, :] = o[b] + d[b] * z[b, i] with separate multiply and add (utils.py:262); also copies z (teacher-forced fine depths)
+__global__ void points_from_z_kernel(const float* __restrict__ origin, const float* __restrict__ dir, const float* __restrict__ z_in, int64_t B, int n,
+                                     float* __restrict__ z_out, float* __restrict__ pts) {
+  const int64_t total = B * n;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = idx / n;
+    const float zz = z_in[idx];
+    z_out[idx] = zz;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pts[idx * 3 + k] = __fadd_rn(origin[b * 3 + k], __fmul_rn(dir[b * 3 + k], zz));
+  }
+}
+
+// ---------------------------------------------------------------------------------- SMPL: warp -> warped points -> view directions
+// warped = pts + warp; v = warped - o; dnorm = |v|; u = v / |v|      (models/smpl_nerf_pipeline.py:48-56)
+__global__ void smpl_points_kernel(const float* __restrict__ pts, const float* __restrict__ warp, const float* __restrict__ origin, int64_t S,
+                                   int n, float* __restrict__ warped, float* __restrict__ u, float* __restrict__ dnorm,
+                                   float* __restrict__ warp_out, float* __restrict__ warped_out) {
+  for (int64_t s = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; s < S; s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = s / n;
+    float wv[3], v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float w = warp[s * 3 + k];
+      wv[k] = __fadd_rn(pts[s * 3 + k], w);
+      v[k] = __fsub_rn(wv[k], origin[b * 3 + k]);
+      warped[s * 3 + k] = wv[k];
+      if (warp_out) warp_out[s * 3 + k] = w;
+      if (warped_out) warped_out[s * 3 + k] = wv[k];
+    }
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2])));
+    dnorm[s] = nrm;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u[s * 3 + k] = __fdiv_rn(v[k], nrm);
+  }
+}
+
+// Backward of the chain above: g_warp[s, :] from the gradients of the two encodings (fp32 [S, 64], reference feature order)
+// and of dnorm (may be NULL) -- everything in REAL units; gmax_bits receives max |g_warp| for the warp head's plane scale.
+//   d enc(x)/dx_j: sum_k 2^k (cos(2^k x_j) g_sin[k, j] - sin(2^k x_j) g_cos[k, j]) (+ identity)
+//   u = v / |v|:   g_v = (g_u - u (u . g_u)) / |v|         dnorm = |v|:  g_v += g_dnorm u
+__global__ void smpl_points_bwd_kernel(const float* __restrict__ g_encx, int xf, int xid, const float* __restrict__ g_encd, int df, int did,
+                                       const float* __restrict__ warped, const float* __restrict__ u, const float* __restrict__ dnorm,
+                                       const float* __restrict__ g_dnorm, int64_t S, float* __restrict__ g_warp,
+                                       unsigned int* __restrict__ gmax_bits) {
+  const float sc = 1.f;
+  float gmax = 0.f;
+  for (int64_t s = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; s < S; s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float gx[3], gu[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float* g = g_encx + s * 64;
+      const float x = warped[s * 3 + j];
+      float acc = xid ? g[j] : 0.f;
+      const int base = xid ? 3 : 0;
+      for (int k = 0; k < xf; ++k) {
+        const float f = __int_as_float((127 + k) << 23);
+        float sv, cv;
+        sincos_pe(x * f, sv, cv);
+        acc = fmaf(f, fmaf(cv, g[base + 6 * k + j], -sv * g[base + 6 * k + 3 + j]), acc);
+      }
+      gx[j] = acc;
+      const float* gd = g_encd + s * 64;
+      const float uu = u[s * 3 + j];
+      float accd = did ? gd[j] : 0.f;
+      const int based = did ? 3 : 0;
+      for (int k = 0; k < df; ++k) {
+        const float f = __int_as_float((127 + k) << 23);
+        float sv, cv;
+        sincos_pe(uu * f, sv, cv);
+        accd = fmaf(f, fmaf(cv, gd[based + 6 * k + j], -sv * gd[based + 6 * k + 3 + j]), accd);
+      }
+      gu[j] = accd;
+    }
+    const float u0 = u[s * 3], u1 = u[s * 3 + 1], u2 = u[s * 3 + 2];
+    const float dot = gu[0] * u0 + gu[1] * u1 + gu[2] * u2;
+    const float inv = 1.f / dnorm[s];
+    const float gd = g_dnorm ? g_dnorm[s] * sc : 0.f;
+    g_warp[s * 3 + 0] = gx[0] + (gu[0] - u0 * dot) * inv + gd * u0;
+    g_warp[s * 3 + 1] = gx[1] + (gu[1] - u1 * dot) * inv + gd * u1;
+    g_warp[s * 3 + 2] = gx[2] + (gu[2] - u2 * dot) * inv + gd * u2;
+    gmax = fmaxf(gmax, fmaxf(fabsf(g_warp[s * 3]), fmaxf(fabsf(g_warp[s * 3 + 1]), fabsf(g_warp[s * 3 + 2]))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  if ((threadIdx.x & 31) == 0 && isfinite(gmax)) atomicMax(gmax_bits, __float_as_uint(gmax));
+}
+
+}  // namespace nrf

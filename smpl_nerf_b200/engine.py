@@ -172,14 +172,20 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
             raise ValueError(f'goal_pose must be [B, >= {max(POSE_COLS) + 1}], got {tuple(goal.shape)}')
     full_pose = kind == 'append_full'     # AppendSmplParamsPipeline: all pose parameters, hoisted per ray by nrf_ray_bias
 
+    # autograd is recording and a net is trainable: the differentiable layer-by-layer path (train.py) instead of the fused kernel
+    from . import train as _train
+    train_mode = _train.needs_grad(model_coarse, model_fine if run_fine else None, model_warp if smpl else None)
+    if train_mode and (taps or trace_cap > 0):
+        raise ValueError('debug taps / trace are inference-only: call under torch.no_grad()')
+
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
         dc = raynet_desc(model_coarse, pos_enc, dir_enc, smpl, full_pose, fold)
-        pc = packed(model_coarse, dc, device, stream)
+        pc = None if train_mode else packed(model_coarse, dc, device, stream)
         df, pf = None, None
         if run_fine:
             df = raynet_desc(model_fine, pos_enc, dir_enc, smpl, full_pose, fold)
-            pf = packed(model_fine, df, device, stream)
+            pf = None if train_mode else packed(model_fine, df, device, stream)
         pipe = PipelineDesc()
         pipe.kind = KIND[kind]
         pipe.n_coarse, pipe.n_fine, pipe.run_fine = nc, nf, run_fine
@@ -187,7 +193,12 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
         pipe.precision = int(precision)
         dw, pw = None, None
         ray_bias = []
-        if full_pose:
+        if full_pose and train_mode:
+            pipe.pose_all = 1
+            pipe.pose_freqs, pipe.pose_identity = _enc_cfg(pose_enc)
+            pipe.pose_encoded = 1 if args.human_pose_encoding else 0
+            pipe.pose_stride, pipe.pose_col0, pipe.pose_col1 = int(goal.shape[1]), 0, 0
+        elif full_pose:
             # pose features exactly as models/append_smpl_params_pipeline.py:30-37 builds them, then one SGEMM per net
             encoded = bool(args.human_pose_encoding)
             A = int(goal.shape[1]) * (pose_enc.output_dim if encoded else 1)
@@ -220,7 +231,7 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
             pose_dim = 2 * (2 * pipe.pose_freqs + pipe.pose_identity) if pipe.pose_encoded else 2
             if smpl:
                 dw = warpnet_desc(model_warp, pos_enc, pose_dim, bool(pipe.pose_encoded))
-                pw = packed(model_warp, dw, device, stream)
+                pw = None if train_mode else packed(model_warp, dw, device, stream)
 
         io = RenderIO()
         out: Dict[str, torch.Tensor] = {}
@@ -236,7 +247,7 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
         if goal is not None:
             io.goal_pose = goal.data_ptr()
         keep = [samples, origin, direction, z, goal]
-        if full_pose:
+        if full_pose and not train_mode:
             io.ray_bias_nonuniform = ray_bias[-1].data_ptr()
             io.ray_bias_coarse = ray_bias[0].data_ptr()
             if run_fine:
@@ -289,7 +300,9 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
         out['status'] = status
         io.status = status.data_ptr()
 
-        if B > 0:
+        if train_mode:
+            _train.render_train(kind, model_coarse, model_fine, model_warp, pipe, dc, df, dw, io, out, keep, B, device, n_sms)
+        elif B > 0:
             rc = L.nrf_render(C.byref(pipe), C.byref(dc), pc.data_ptr(), C.byref(df) if df is not None else None,
                               pf.data_ptr() if pf is not None else None, C.byref(dw) if dw is not None else None,
                               pw.data_ptr() if pw is not None else None, C.byref(io), B, int(n_sms), stream)

@@ -37,7 +37,7 @@ def test_struct_sizes_match_header(L):
     # int32 counts in the C structs (include/nrf_b200.h)
     assert C.sizeof(_lib.RayNetDesc) == 4 * (7 + 4 + 7)
     assert C.sizeof(_lib.WarpNetDesc) == 4 * 5
-    assert C.sizeof(_lib.PipelineDesc) == 4 * 12
+    assert C.sizeof(_lib.PipelineDesc) == 4 * 13
     assert C.sizeof(_lib.RenderIO) == 8 * 25
 
 
