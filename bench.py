@@ -51,6 +51,10 @@ WORKLOADS = {
     'cfg1': dict(kind='nerf', side=128, n_coarse=32, n_fine=0, run_fine=0, n_layers=4, skips=[],
                  text='vanilla nerf_pipeline, 128x128, netdepth=4, 32 coarse, run_fine=0 (BASELINE configs[0])'),
     # configs[4]: ONE 512x512 frame per step, its rays sharded over the ranks (strong scaling), one all-gather of the tiles
+    # training step of the headline architecture: forward + backward + Adam, reference default batchsize (config_parser.py:53)
+    'train': dict(kind='smpl', side=128, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4], train=True, batch=2048,
+                  text='smpl_nerf_pipeline TRAINING step (solver/smpl_nerf_solver.py:66-83: forward, MSE coarse+fine, backward, Adam), '
+                       'netdepth=8, 64 coarse + 128 fine, batchsize=2048'),
     'cfg5': dict(kind='smpl', side=512, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4], strong=True,
                  text='smpl_nerf_pipeline, 512x512 full-frame render, rays sharded over the GPUs (BASELINE configs[4])'),
 }
@@ -330,6 +334,157 @@ def measure(a, w, pipe, rank, world, dev, clocks=True):
                 clocks=clk)
 
 
+def cpu_train_rays_per_s(w, state, n_steps, batch, seed=0):
+    """The reference's training step (oracle port + torch autograd + Adam) on the host cores: bounded sample."""
+    from oracle import nerf_oracle as O
+    from smpl_nerf_b200 import scene
+    torch.set_num_threads(os.cpu_count() or 1)
+    c, f, wn, pe, de, he = O.build_nets(w['kind'], seed, 'default', n_layers=w['n_layers'], skips=tuple(w['skips']))
+    for net, sd in zip((c, f, wn), state):
+        if net is not None:
+            net.load_state_dict(sd)
+            net.train()
+    args = O.make_args(run_fine=1, number_fine_samples=w['n_fine'], sigma_noise_std=0.)
+    rays = scene.make_rays(w['side'], w['side'], w['n_coarse'], seed=seed, with_colours=True)
+    opt = torch.optim.Adam([p for m in (c, f, wn) if m is not None for p in m.parameters()], lr=5e-4)
+    times = []
+    for i in range(1 + n_steps):
+        data = scene.data_list(rays, w['kind'], slice(i * batch, (i + 1) * batch))
+        t0 = time.perf_counter()
+        o = O.smpl_nerf_forward(c, f, wn, pe, de, he, args, data)
+        loss = torch.mean((o['rgb'] - data[-1]) ** 2) + torch.mean((o['rgb_fine'] - data[-1]) ** 2)
+        opt.zero_grad(); loss.backward(); opt.step()
+        if i >= 1:
+            times.append(time.perf_counter() - t0)
+    return batch / statistics.median(times), times
+
+
+def run_train(a, w, rank, world, local_rank):
+    """--workload train: rays/s of one optimisation step through the drop-in pipeline (autograd.Function over
+    nrf_train_forward / nrf_train_backward), data-parallel over the ranks with one all-reduce of the flattened gradients."""
+    import torch.distributed as dist
+    from smpl_nerf_b200 import _lib, scene
+    from smpl_nerf_b200.models import SmplNerfPipeline
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    coarse, fine, warp, pe, de, he = build_models(w)
+    state = [m.state_dict() if m is not None else None for m in (coarse, fine, warp)]
+    fl_ray = flops_per_ray(w, coarse, fine, warp)
+    nets = [coarse.to(dev), fine.to(dev), warp.to(dev)]
+    for m in nets:
+        m.train()
+    pargs = make_args(w)
+    pipe = SmplNerfPipeline(nets[0], nets[1], nets[2], pargs, pe, de, he)
+    pipe.precision = 1 if a.precision == 'fast' else 0
+    params = [p for m in nets for p in m.parameters()]
+    opt = torch.optim.Adam(params, lr=5e-4, fused=True)
+    B = w['batch']
+    rays = scene.make_rays(w['side'], w['side'], w['n_coarse'], seed=7 + rank, with_colours=True, arm_angle_deg=30.0)
+    host = [t.pin_memory() for t in scene.data_list(rays, 'smpl')]
+    n_b = host[0].shape[0] // B
+    batches_host = [[t[i * B:(i + 1) * B] for t in host] for i in range(n_b)]
+    batches = [[t.to(dev) for t in b] for b in batches_host]
+    stream = torch.cuda.current_stream(dev)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(data):
+        out = pipe(data)
+        loss = torch.mean((out[0] - data[-1]) ** 2) + torch.mean((out[1] - data[-1]) ** 2)
+        opt.zero_grad(set_to_none=False)
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.flatten() for p in params])
+            dist.all_reduce(flat)
+            flat /= world
+            o = 0
+            for p in params:
+                p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    t0, i = time.perf_counter(), 0
+    while i < a.warmup or time.perf_counter() - t0 < WARM_SECONDS:
+        step(batches[i % n_b]); i += 1
+        torch.cuda.synchronize(dev)
+    barrier()
+    sampler = ClockSampler(dev.index) if rank == 0 else None
+    _lib.lib().nrf_train_launch_count(1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(a.steps):
+        ev[i][0].record(stream)
+        step(batches[i % n_b])
+        ev[i][1].record(stream)
+    e1.record(stream)
+    barrier()
+    launches = int(_lib.lib().nrf_train_launch_count(1))
+    ms_total = e0.elapsed_time(e1)
+    ms_steps = [x.elapsed_time(y) for x, y in ev]
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for i in range(a.steps):
+        data = [t.to(dev, non_blocking=True) for t in batches_host[i % n_b]]
+        loss_host.copy_(step(data).detach().reshape(1), non_blocking=True)
+    f1.record(stream)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total, ms_e2e, statistics.median(ms_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e, ms_median = [float(x) for x in t.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        pass
+    capped = bool(clocks and clocks.get('sm_mhz') and clocks['sm_mhz'] < 0.95 * clocks['sm_max_mhz'])
+    burst = ms_total < 1000.0 and not capped
+    peak_tf = float(peaks.get('bf16_tflops' if burst else 'bf16_tflops_sustained', 1650.0 if burst else 1400.0))
+    n_total = B * world
+    achieved = 3.0 * fl_ray * B / (ms_median / 1e3) / 1e12
+    h2d = sum(x.numel() * x.element_size() for x in batches_host[0])
+    line = {
+        'metric': 'rays/sec', 'value': n_total / (ms_median / 1e3), 'unit': 'rays/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+        'ms_per_step': ms_median, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16x3-split (fp32-equivalent) forward and backward, fp32 accumulate' if a.precision != 'fast' else 'f16 (1 pass) forward and backward, fp32 accumulate',
+        'data': 'synthetic',
+        'config': {'workload': w['text'], 'rays_per_step_per_gpu': B, 'precision_mode': a.precision, 'optimizer': 'torch.optim.Adam(fused=True), lr 5e-4',
+                   'weights': 'random init (seed 0, sigma head x20, bias +1)', 'l2_policy': f'{n_b} distinct batches rotate; a step streams ~{17 * B * 256 / 1e6:.0f} MB of saved activations (> 126 MB L2)',
+                   'parallelism': f'data parallel over {world} GPU(s), one all-reduce of the flattened gradients per step' if world > 1 else 'single GPU',
+                   'timing': f'value = rays / MEDIAN step time (CUDA events); K steps back to back: {ms_total:.1f} ms'},
+        'clocks': clocks,
+        'e2e': {'value': n_total * a.steps / (ms_e2e / 1e3), 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
+        'gpu_launches': launches,
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None,
+                     'flop_per_ray': 3.0 * fl_ray, 'kernel': 'tile_gemm_kernel + dw_gemm_kernel (whole step timed)', 'kernel_ms': ms_median,
+                     'peak_source': ('MEASURED_PEAKS.json ' if peaks else 'fallback ') + ('burst' if burst else 'sustained'),
+                     'note': 'algorithmic FLOPs = 3 x (2 x MACs of the reference nn.Linear layers): forward + dX + dW; the whole optimisation '
+                             'step (encodings, heads, compositing, reductions, Adam) is inside the timed region'},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        rps, times = cpu_train_rays_per_s(w, state, 3, 256)
+        cores = os.cpu_count() or 1
+        line['cpu_baseline'] = {'value': rps, 'unit': 'rays/s', 'cores': cores, 'kind': 'port', 'cpu': cpu_model(),
+                                'sample': f'median of 3 training steps of 256 rays after 1 warm-up ({sum(times):.1f} s), {cores} torch threads; '
+                                          f'oracle port of the reference pipeline + torch autograd + Adam'}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(a, w, rank, world, local_rank):
     import torch.distributed as dist
     from smpl_nerf_b200 import dist as nd
@@ -464,8 +619,21 @@ def main():
     if a.workload is None:
         a.workload = 'cfg2' if max(world, a.gpus) == 1 else 'cfg5'      # both arms: same config at the same N
     w = WORKLOADS[a.workload]
-    if a.impl == 'reference':
+    if a.impl == 'reference' and w.get('train'):
+        if rank == 0:
+            coarse, fine, warp, *_ = build_models(w)
+            rps, times = cpu_train_rays_per_s(w, [m.state_dict() for m in (coarse, fine, warp)], max(a.steps, 2), 256)
+            print(json.dumps({'impl': 'reference', 'device': 'cpu', 'metric': 'rays/sec', 'value': rps, 'unit': 'rays/s', 'n_gpus': a.gpus,
+                              'steps': a.steps, 'warmup': 1, 'ms_per_step': 1e3 * statistics.median(times), 'higher_is_better': True,
+                              'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                              'config': {'workload': w['text'], 'rays_per_step': 256},
+                              'cpu_baseline': {'value': rps, 'unit': 'rays/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+                                               'sample': f'{len(times)} training steps of 256 rays'},
+                              'e2e': {'value': rps, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
+    elif a.impl == 'reference':
         run_reference(a, w, rank, world)
+    elif w.get('train'):
+        run_train(a, w, rank, world, local_rank)
     else:
         run_ours(a, w, rank, world, local_rank)
 

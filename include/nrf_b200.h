@@ -5,6 +5,7 @@
  *   models/nerf_pipeline.py:14-67, models/smpl_nerf_pipeline.py:16-100,
  *   models/append_to_nerf_pipeline.py:14-90          -> nrf_render()           (one fused kernel)
  *   models/append_smpl_params_pipeline.py:14-91        -> nrf_ray_bias() + nrf_render()   (69-parameter pose hoisted per ray)
+ *   solver/nerf_solver.py:81-87 (pipeline(data); loss.backward()) -> nrf_train_forward() + nrf_train_backward()
  *   models/render_ray_net.py:6-61 (weights, [out,in])  -> nrf_pack_raynet()      (fp32 -> packed fp16 hi/lo)
  *   models/warp_field_net.py:6-21                      -> nrf_pack_warpnet()
  *   utils.py:114-131  PositionalEncoder.encode         -> nrf_positional_encoding()
@@ -151,16 +152,19 @@ int nrf_pack_raynet(const NrfRayNetDesc* d, const float* const* params, int n_pa
 int nrf_pack_warpnet(const NrfWarpNetDesc* d, const float* const* params, int n_params, void* packed, void* stream);
 
 /* Per-ray bias vectors of the layers that read the A additional inputs (first layer and every skip layer):
- *   out[b, e, :] = bias_e + W_e[:, pose columns] * feats[b, :]        (fp32 FMA, CUDA cores)
+ *   out[b, e, :] = bias_e + W_e[:, pose columns] * feats[b, :]        (tcgen05, three fp16 hi/lo passes, fp32 accumulate)
  * feats: [B, A] (pose parameters, positionally encoded by the caller when the pipeline encodes them);
  * params: as for nrf_pack_raynet (the ORIGINAL fp32 nn.Linear tensors are read in place); out: [B, n_ext, 256]
  * with n_ext = nrf_raynet_ext_slots(d).  Must run on the same stream before nrf_render.
+ * workspace: caller-owned device buffer of nrf_ray_bias_workspace_bytes(d, B) bytes, 256-byte aligned (fp16 hi/lo planes of
+ * the features and of the pose columns of the weights).
  * nonuniform (optional, DEVICE int32[1]): set to 0 when all B feature rows are bit-identical (every ray of a rendered
- * frame carries the same pose) -- then only row 0 is computed -- else to 1; hand it to nrf_render through
+ * frame carries the same pose) -- nrf_render then reads row 0 only -- else to 1; hand it to nrf_render through
  * NrfRenderIO.ray_bias_nonuniform.  Decided on the device, no host synchronisation. */
 int nrf_raynet_ext_slots(const NrfRayNetDesc* d);
+size_t nrf_ray_bias_workspace_bytes(const NrfRayNetDesc* d, int64_t B);
 int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, int n_params, const float* feats, int64_t B,
-                 float* out, int32_t* nonuniform, void* stream);
+                 float* out, int32_t* nonuniform, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The fused forward of the three pipelines for B rays.  packed_warp/warp may be NULL unless
  * kind == NRF_KIND_SMPL.  n_sms <= 0 means "all SMs of the current device". */
@@ -203,6 +207,19 @@ int nrf_fine_sampling(const float* origin, const float* dir, const float* z, con
 int nrf_generate_rays(int32_t H, int32_t W, double focal, const double* camera_transform_host, const double* lower,
                       const double* span, const double* jitter, int32_t n_coarse, float* ray_samples, float* ray_origin,
                       float* ray_dir, float* z_vals, void* stream);
+/* The same for the rays [ray0, ray0 + n_rays) of the view only (row-major pixel index): a rank of a sharded render generates
+ * just its own rays.  jitter: [n_rays] (the window's scalars); outputs are [n_rays, ...]. */
+int nrf_generate_rays_range(int32_t H, int32_t W, double focal, const double* camera_transform_host, const double* lower,
+                            const double* span, const double* jitter, int32_t n_coarse, int64_t ray0, int64_t n_rays,
+                            float* ray_samples, float* ray_origin, float* ray_dir, float* z_vals, void* stream);
+/* util/scores.py:88-173 ssim / _ssim_per_channel: x, y [n_planes, H, W] (n_planes = N * C channel planes), kernel2d: DEVICE
+ * [ks, ks] window (the caller builds it like gaussian_filter, util/scores.py:68-86); c1 = (k1 data_range)^2, c2 = (k2 data_range)^2.
+ * ssim_out / cs_out: [n_planes] means over the valid positions (cs_out optional).  partial: nrf_ssim_partial_floats() floats. */
+int64_t nrf_ssim_partial_floats(int64_t n_planes, int32_t H, int32_t W, int32_t ks);
+int nrf_ssim(const float* x, const float* y, int64_t n_planes, int32_t H, int32_t W, const float* kernel2d, int32_t ks, float c1,
+             float c2, float* partial, float* ssim_out, float* cs_out, void* stream);
+/* inference.py:260-262: rgb [n_pixels, 3] float -> uint8 (clip to [0,1], * 255, truncate), channels flipped to BGR when to_bgr. */
+int nrf_quantize_image(const float* rgb, int64_t n_pixels, uint8_t* out, int32_t to_bgr, void* stream);
 /* torchsearchsorted: a[rows_a, na], v[rows_v, nv] (rows broadcast when one side has 1 row) -> res int64 */
 int nrf_searchsorted(const float* a, int64_t rows_a, int64_t na, const float* v, int64_t rows_v, int64_t nv,
                      int64_t* res, int32_t side_left, void* stream);
@@ -227,6 +244,8 @@ int nrf_train_backward(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse,
                        const float* const* params_warp, int n_warp, const NrfRenderIO* io, int64_t B, void* workspace,
                        size_t workspace_bytes, const float* grad_rgb, const float* grad_rgb_fine, float* const* grads_coarse,
                        float* const* grads_fine, float* const* grads_warp, int n_sms, void* stream);
+/* Kernels launched by the training entry points on this thread since the last reset (bench.py's gpu_launches accounting). */
+long long nrf_train_launch_count(int reset);
 /* Building blocks of the training path, exported for stage-wise tests.  "planes" = a matrix as two fp16 tensors hi, lo
  * (x ~= hi + lo), row-major [rows, ld]; lo may be NULL with passes = 1.
  * nrf_split_planes: fp32 [rows, cols] (row pitch ld) -> planes [rows, cols_pad] (row pitch ld_dst), zero padded.

@@ -58,10 +58,11 @@ class RenderIO(C.Structure):
 
 EXPORTS = ['nrf_last_error', 'nrf_abi_version', 'nrf_device_supported', 'nrf_raynet_packed_bytes',
            'nrf_warpnet_packed_bytes', 'nrf_pack_raynet', 'nrf_pack_warpnet', 'nrf_render', 'nrf_render_launches',
-           'nrf_raynet_ext_slots', 'nrf_ray_bias', 'nrf_generate_rays',
+           'nrf_raynet_ext_slots', 'nrf_ray_bias', 'nrf_ray_bias_workspace_bytes', 'nrf_generate_rays', 'nrf_generate_rays_range',
+           'nrf_ssim', 'nrf_ssim_partial_floats', 'nrf_quantize_image',
            'nrf_positional_encoding', 'nrf_positional_encoding_backward', 'nrf_raw2outputs', 'nrf_raw2outputs_backward', 'nrf_sample_pdf', 'nrf_fine_sampling', 'nrf_searchsorted',
            'nrf_selftest_umma', 'nrf_selftest_umma2', 'nrf_bench_umma', 'nrf_bench_umma2',
-           'nrf_train_workspace_bytes', 'nrf_train_forward', 'nrf_train_backward', 'nrf_split_planes', 'nrf_gemm_planes', 'nrf_gemm_dw']
+           'nrf_train_workspace_bytes', 'nrf_train_forward', 'nrf_train_backward', 'nrf_split_planes', 'nrf_gemm_planes', 'nrf_gemm_dw', 'nrf_train_launch_count']
 
 
 def _stale() -> bool:
@@ -115,9 +116,18 @@ def lib() -> C.CDLL:
                              C.c_void_p]
     L.nrf_raynet_ext_slots.argtypes = [C.POINTER(RayNetDesc)]
     L.nrf_ray_bias.argtypes = [C.POINTER(RayNetDesc), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
-                               C.c_void_p]
+                               C.c_void_p, C.c_size_t, C.c_void_p]
+    L.nrf_ray_bias_workspace_bytes.restype = C.c_size_t
+    L.nrf_ray_bias_workspace_bytes.argtypes = [C.POINTER(RayNetDesc), C.c_int64]
     L.nrf_generate_rays.argtypes = [C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nrf_generate_rays_range.argtypes = [C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nrf_ssim_partial_floats.restype = C.c_int64
+    L.nrf_ssim_partial_floats.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32]
+    L.nrf_ssim.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p,
+                           C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nrf_quantize_image.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]
     L.nrf_positional_encoding.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.nrf_raw2outputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -142,6 +152,8 @@ def lib() -> C.CDLL:
                  C.POINTER(RenderIO), C.c_int64, C.c_void_p, C.c_size_t]
     L.nrf_train_forward.argtypes = _net_args + [C.c_int, C.c_void_p]
     L.nrf_train_backward.argtypes = _net_args + [C.c_void_p, C.c_void_p, PP, PP, PP, C.c_int, C.c_void_p]
+    L.nrf_train_launch_count.restype = C.c_longlong
+    L.nrf_train_launch_count.argtypes = [C.c_int]
     L.nrf_split_planes.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     L.nrf_gemm_planes.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
   const uint32_t planes = P.passes == 3 ? 2u : 1u;
   const int nk = P.kc[0] + (P.n_src > 1 ? P.kc[1] : 0);
   const uint32_t b_chunk = static_cast<uint32_t>(P.n_tile) * 128u;
-  const uint32_t b_bytes = static_cast<uint32_t>(nk) * planes * b_chunk;
-  const uint32_t a_stage = planes * kATile;
+  const uint32_t b_bytes = P.b_stream ? 0u : static_cast<uint32_t>(nk) * planes * b_chunk;
+  const uint32_t a_stage = planes * kATile + (P.b_stream ? planes * b_chunk : 0u);      // streaming mode: [A planes | B planes] per stage
   const uint32_t smem_b = smem_u32(smem), smem_a = smem_b + b_bytes;
   GemmBars* bars = reinterpret_cast<GemmBars*>(smem + b_bytes + static_cast<uint32_t>(P.n_stages) * a_stage);
   const int n0 = blockIdx.y * P.n_tile;
@@ -70,17 +70,21 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
 
   if (warp == 0) {
     if (lane == 0) {
+      auto load_b = [&](int j, int lc, uint32_t dst0, uint32_t bar) {
+        for (uint32_t p = 0; p < planes; ++p) {
+          const CUtensorMap* map = p ? &P.b_lo[j] : &P.b_hi[j];
+          const uint32_t dst = dst0 + p * b_chunk;
+          if (!P.b_mn) tma_load_2d(dst, map, 64 * lc, n0, bar);
+          else for (int g = 0; g < P.n_tile / 64; ++g) tma_load_2d(dst + g * 8192u, map, n0 + 64 * g, 64 * lc, bar);
+        }
+      };
       // ---- resident weight slice
-      mbar_arrive_expect_tx(smem_u32(&bars->b_full), b_bytes);
-      int c = 0;
-      for (int j = 0; j < P.n_src; ++j)
-        for (int lc = 0; lc < P.kc[j]; ++lc, ++c)
-          for (uint32_t p = 0; p < planes; ++p) {
-            const CUtensorMap* map = p ? &P.b_lo[j] : &P.b_hi[j];
-            const uint32_t dst = smem_b + (static_cast<uint32_t>(c) * planes + p) * b_chunk;
-            if (!P.b_mn) tma_load_2d(dst, map, 64 * lc, n0, smem_u32(&bars->b_full));
-            else for (int g = 0; g < P.n_tile / 64; ++g) tma_load_2d(dst + g * 8192u, map, n0 + 64 * g, 64 * lc, smem_u32(&bars->b_full));
-          }
+      if (!P.b_stream) {
+        mbar_arrive_expect_tx(smem_u32(&bars->b_full), b_bytes);
+        int c = 0;
+        for (int j = 0; j < P.n_src; ++j)
+          for (int lc = 0; lc < P.kc[j]; ++lc, ++c) load_b(j, lc, smem_b + static_cast<uint32_t>(c) * planes * b_chunk, smem_u32(&bars->b_full));
+      }
       // ---- sample tiles
       uint32_t stage = 0, phase = 0;
       for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x)
@@ -91,12 +95,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             const uint32_t dst = smem_a + stage * a_stage;
             tma_load_2d(dst, &P.a_hi[j], 64 * lc, static_cast<int32_t>(mt * 128), smem_u32(&bars->a_full[stage]));
             if (planes == 2) tma_load_2d(dst + kATile, &P.a_lo[j], 64 * lc, static_cast<int32_t>(mt * 128), smem_u32(&bars->a_full[stage]));
+            if (P.b_stream) load_b(j, lc, dst + planes * kATile, smem_u32(&bars->a_full[stage]));
             if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
           }
     }
   } else if (warp == 1) {
     const uint32_t idesc = umma_idesc_f16_major(128, static_cast<uint32_t>(P.n_tile), 0u, P.b_mn ? 1u : 0u);
-    mbar_wait(smem_u32(&bars->b_full), 0);
+    if (!P.b_stream) mbar_wait(smem_u32(&bars->b_full), 0);
     tc_fence_after_sync();
     uint32_t stage = 0, phase = 0, it = 0;
     for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x, ++it) {
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
         mbar_wait(smem_u32(&bars->a_full[stage]), phase);
         tc_fence_after_sync();
         const uint32_t a_hi = smem_a + stage * a_stage, a_lo = a_hi + kATile;
-        const uint32_t b_hi = smem_b + static_cast<uint32_t>(c) * planes * b_chunk, b_lo = b_hi + b_chunk;
+        const uint32_t b_hi = P.b_stream ? a_hi + planes * kATile : smem_b + static_cast<uint32_t>(c) * planes * b_chunk, b_lo = b_hi + b_chunk;
         for (uint32_t pass = 0; pass < static_cast<uint32_t>(P.passes); ++pass) {
           const uint32_t a = pass == 1 ? a_lo : a_hi, b = pass == 2 ? b_lo : b_hi;      // hi*hi, lo*hi, hi*lo
           const uint64_t ad = umma_desc_sw128(a);
@@ -380,8 +385,12 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
     }
   }
   const uint32_t planes = a.passes == 3 ? 2u : 1u;
-  const uint32_t b_bytes = static_cast<uint32_t>(nk) * planes * P.n_tile * 128u, a_stage = planes * kATile;
-  if (b_bytes + 2 * a_stage + 256 > kGemmSmemLimit) { set_error("tile_gemm: K = %d too large for a resident weight slice", 64 * nk); return NRF_E_INVALID; }
+  uint32_t b_bytes = static_cast<uint32_t>(nk) * planes * P.n_tile * 128u, a_stage = planes * kATile;
+  if (b_bytes + 2 * a_stage + 256 > kGemmSmemLimit) {      // K too large for a resident weight slice: stream the B chunks with the A chunks
+    P.b_stream = 1;
+    a_stage += planes * P.n_tile * 128u;
+    b_bytes = 0;
+  }
   int stages = static_cast<int>((kGemmSmemLimit - 256 - b_bytes) / a_stage);
   P.n_stages = stages > 4 ? 4 : stages;
   P.epi = a.epi; P.relu = a.relu; P.bias = a.bias; P.bias_ld = a.bias_ld; P.rows_per_ray = a.rows_per_ray > 0 ? a.rows_per_ray : 1;
@@ -399,6 +408,7 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(tile_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tile_gemm)");
   tile_gemm_kernel<<<dim3(gx, slices), kTileThreads, smem_bytes, stream>>>(P);
+  ++g_train_launches;
   e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "tile_gemm_kernel launch");
 }
@@ -440,6 +450,7 @@ int launch_dw_gemm(const Planes& a, int m0, int M, const Planes& b, int n0, int 
   cudaError_t e = cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dw_gemm)");
   dw_gemm_kernel<<<dim3(M / 128, split), kDwThreads, static_cast<uint32_t>(P.n_stages) * stage_bytes + 256, stream>>>(P);
+  ++g_train_launches;
   e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "dw_gemm_kernel launch");
 }

@@ -30,6 +30,7 @@ struct TileGemmParams {
   CUtensorMap b_hi[2], b_lo[2];   // B sources: b_mn = 0: [N, 64 * kc[j]] box {64, n_tile}; b_mn = 1: [64 * kc[j], N] box {64, 64}
   int32_t kc[2];
   int32_t n_src, b_mn, n_tile, passes, n_stages;
+  int32_t b_stream;               // 1: K too large for a resident weight slice -- the B chunk travels with every A chunk through the ring
   int64_t S;
   int32_t epi, relu;
   const float* bias; int32_t bias_ld; int32_t rows_per_ray;      // bias[(row / rows_per_ray) * bias_ld + col]  (bias_ld = 0: one vector)

@@ -331,17 +331,8 @@ static int grid_for(int64_t total, int block) {
 }
 
 
-// ------------------------------------------------------------------------------ per-ray pose bias (SGEMM)
-// out[b, e, n] = bias_e[n] + sum_k W_e[n, col0_e + k] * feats[b, k]      b < B, n < 256, k < A
-// for the n_ext layers of a RenderRayNet that read the A additional inputs (models/render_ray_net.py:43-49 with
-// the input built by models/append_smpl_params_pipeline.py:46-48: pose features FIRST).  The pose is constant
-// along a ray, so this replaces A of the K columns of two layers for every SAMPLE by one small GEMM per RAY.
-// Classic fp32 register-tiled SGEMM: 128 rays x 64 outputs per CTA, K in steps of 16 through shared memory.
-struct RayBiasJob { const float* w; const float* bias; int32_t ld, col0; };
-struct RayBiasTable { int32_t n; RayBiasJob j[NRF_MAX_SKIPS + 1]; };
-
-constexpr int kRbM = 128, kRbN = 64, kRbK = 16;
-
+// ------------------------------------------------------------------------------ per-ray pose bias: row-uniformity probe
+// (the GEMM itself is tcgen05: nrf_ray_bias in nrf_train.cu)
 // flag <- 1 if any feature row differs (bitwise) from row 0
 __global__ void rows_differ_kernel(const float* __restrict__ feats, int64_t B, int A, int32_t* __restrict__ flag) {
   const int64_t total = B * A;
@@ -351,58 +342,86 @@ __global__ void rows_differ_kernel(const float* __restrict__ feats, int64_t B, i
     differ |= __float_as_uint(feats[idx]) != __float_as_uint(__ldg(feats + idx % A));
   if (__any_sync(0xffffffffu, differ) && (threadIdx.x & 31) == 0) atomicExch(flag, 1);
 }
-
-__global__ void __launch_bounds__(256) ray_bias_kernel(const __grid_constant__ RayBiasTable t, const float* __restrict__ feats, int64_t B,
-                                                       int A, float* __restrict__ out, const int32_t* __restrict__ nonuniform) {
-  __shared__ __align__(16) float As[kRbK][kRbM + 4];
-  __shared__ __align__(16) float Bs[kRbK][kRbN + 4];
-  if (nonuniform && *nonuniform == 0 && blockIdx.x > 0) return;      // one pose for the whole batch: row 0 is all that is read
-  const RayBiasJob& job = t.j[blockIdx.z];
-  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kRbM;
-  const int n0 = blockIdx.y * kRbN;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < A; k0 += kRbK) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {               // 128 x 16 feature tile, 16 consecutive threads read 16 consecutive floats
-      const int idx = threadIdx.x + 256 * i, r = idx >> 4, k = idx & 15;
-      const int64_t b = b0 + r;
-      As[k][r] = (b < B && k0 + k < A) ? feats[b * A + k0 + k] : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {               // 64 x 16 weight tile
-      const int idx = threadIdx.x + 256 * i, n = idx >> 4, k = idx & 15;
-      Bs[k][n] = (k0 + k < A) ? job.w[static_cast<size_t>(n0 + n) * job.ld + job.col0 + k0 + k] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kRbK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][8 * ty]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][8 * ty + 4]);
-      const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][4 * tx]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-  const float4 bias = *reinterpret_cast<const float4*>(job.bias + n0 + 4 * tx);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int64_t b = b0 + 8 * ty + i;
-    if (b >= B) continue;
-    float4 o = make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w);
-    *reinterpret_cast<float4*>(out + (b * t.n + blockIdx.z) * kWidth + n0 + 4 * tx) = o;
-  }
+int launch_rows_differ(const float* feats, int64_t B, int A, int32_t* flag, cudaStream_t stream) {
+  cudaError_t e0 = cudaMemsetAsync(flag, 0, sizeof(int32_t), stream);
+  if (e0 != cudaSuccess) return cuda_fail(e0, "cudaMemsetAsync(nonuniform)");
+  rows_differ_kernel<<<grid_for(B * A, 256), 256, 0, stream>>>(feats, B, A, flag);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "rows_differ_kernel launch");
 }
 
+
+// ------------------------------------------------------------------------------ SSIM (util/scores.py:88-173)
+// Per image plane (one channel of one image, [H, W]): Gaussian-window means / variances / covariance with a valid (no padding)
+// ks x ks window, cs = (2 s12 + c2) / (s1 + s2 + c2), ssim = (2 m1 m2 + c1) / (m1^2 + m2^2 + c1) * cs, averaged over the
+// (H - ks + 1) x (W - ks + 1) positions.  One 16 x 16 output tile per CTA (inputs staged in shared memory); per-tile sums go
+// to `partial` and ssim_reduce_kernel adds them in a fixed order (deterministic, no atomics).
+constexpr int kSsimTile = 16, kSsimMaxK = 15;
+__global__ void __launch_bounds__(kSsimTile * kSsimTile) ssim_tile_kernel(const float* __restrict__ x, const float* __restrict__ y, int H, int W,
+                                                                           const float* __restrict__ kern, int ks, float c1, float c2,
+                                                                           float* __restrict__ partial) {
+  __shared__ float xs[(kSsimTile + kSsimMaxK - 1) * (kSsimTile + kSsimMaxK - 1)], ys[(kSsimTile + kSsimMaxK - 1) * (kSsimTile + kSsimMaxK - 1)];
+  __shared__ float kw[kSsimMaxK * kSsimMaxK];
+  __shared__ float red[2][kSsimTile * kSsimTile / 32];
+  const int Ho = H - ks + 1, Wo = W - ks + 1;
+  const int tiles_x = (Wo + kSsimTile - 1) / kSsimTile;
+  const int ty0 = (blockIdx.x / tiles_x) * kSsimTile, tx0 = (blockIdx.x % tiles_x) * kSsimTile;
+  const float* xp = x + static_cast<size_t>(blockIdx.y) * H * W;
+  const float* yp = y + static_cast<size_t>(blockIdx.y) * H * W;
+  const int span = kSsimTile + ks - 1;
+  for (int i = threadIdx.x; i < span * span; i += blockDim.x) {
+    const int r = ty0 + i / span, c = tx0 + i % span;
+    const bool ok = r < H && c < W;
+    xs[i] = ok ? xp[r * W + c] : 0.f;
+    ys[i] = ok ? yp[r * W + c] : 0.f;
+  }
+  for (int i = threadIdx.x; i < ks * ks; i += blockDim.x) kw[i] = kern[i];
+  __syncthreads();
+  const int oy = threadIdx.x / kSsimTile, ox = threadIdx.x % kSsimTile;
+  float sv = 0.f, cv = 0.f;
+  if (ty0 + oy < Ho && tx0 + ox < Wo) {
+    float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    for (int i = 0; i < ks; ++i)
+      for (int j = 0; j < ks; ++j) {
+        const float w = kw[i * ks + j], a = xs[(oy + i) * span + ox + j], b = ys[(oy + i) * span + ox + j];
+        m1 = fmaf(w, a, m1); m2 = fmaf(w, b, m2);
+        e11 = fmaf(w, a * a, e11); e22 = fmaf(w, b * b, e22); e12 = fmaf(w, a * b, e12);
+      }
+    const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+    const float s1 = e11 - m11, s2 = e22 - m22, s12 = e12 - m12;
+    cv = (2.f * s12 + c2) / (s1 + s2 + c2);
+    sv = ((2.f * m12 + c1) / (m11 + m22 + c1)) * cv;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, o); cv += __shfl_xor_sync(0xffffffffu, cv, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sv; red[1][threadIdx.x >> 5] = cv; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < kSsimTile * kSsimTile / 32; ++i) { a += red[0][i]; b += red[1][i]; }
+    float* dst = partial + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 2;
+    dst[0] = a; dst[1] = b;
+  }
+}
+__global__ void ssim_reduce_kernel(const float* __restrict__ partial, int n_tiles, float inv_count, float* __restrict__ ssim, float* __restrict__ cs) {
+  const int plane = blockIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n_tiles; i += 32) { a += partial[(static_cast<size_t>(plane) * n_tiles + i) * 2]; b += partial[(static_cast<size_t>(plane) * n_tiles + i) * 2 + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if (threadIdx.x == 0) { ssim[plane] = static_cast<float>(a * inv_count); if (cs) cs[plane] = static_cast<float>(b * inv_count); }
+}
+
+// inference.py:260-262: clip to [0, 1], * 255, truncate to uint8, RGB -> BGR (the reference flips channels before writing)
+__global__ void quantize_bgr_kernel(const float* __restrict__ rgb, int64_t n_pix, uint8_t* __restrict__ out, int flip) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_pix; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = fminf(fmaxf(rgb[i * 3 + c], 0.f), 1.f) * 255.f;
+      out[i * 3 + (flip ? 2 - c : c)] = static_cast<uint8_t>(v);
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------ ray generation + coarse sampling
 // utils.py:26-54 get_rays + datasets/transforms.py:82-89 CoarseSampling + :13-19 ToTensor, for one view:
@@ -411,17 +430,18 @@ __global__ void __launch_bounds__(256) ray_bias_kernel(const __grid_constant__ R
 //   z     = lower + (upper - lower) * jitter[ray]               one jitter scalar per ray
 //   pts   = origin + dir * z                                     float64, rounded ONCE to fp32 on store
 // One thread per (ray, sample); HBM-bound (12 B/sample written).
-struct CamParams { double r[9]; double t[3]; double focal; int32_t H, W, n; };
+struct CamParams { double r[9]; double t[3]; double focal; int32_t H, W, n; int64_t ray0, n_rays; };   // rays [ray0, ray0 + n_rays) of the H x W view
 
 __global__ void generate_rays_kernel(const __grid_constant__ CamParams cam, const double* __restrict__ lower, const double* __restrict__ span,
                                      const double* __restrict__ jitter, float* __restrict__ samples, float* __restrict__ origin,
                                      float* __restrict__ dir, float* __restrict__ z_vals) {
-  const int64_t total = static_cast<int64_t>(cam.H) * cam.W * cam.n;
+  const int64_t total = cam.n_rays * cam.n;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t ray = idx / cam.n;
+    const int64_t ray = idx / cam.n;                  // index inside the window (outputs, jitter)
     const int s = static_cast<int>(idx - ray * cam.n);
-    const int j = static_cast<int>(ray / cam.W), i = static_cast<int>(ray - static_cast<int64_t>(j) * cam.W);
+    const int64_t pix = cam.ray0 + ray;               // pixel of the full view
+    const int j = static_cast<int>(pix / cam.W), i = static_cast<int>(pix - static_cast<int64_t>(j) * cam.W);
     const float fi = __fsub_rn(static_cast<float>(i), static_cast<float>(cam.W * .5));
     const float fj = __fsub_rn(static_cast<float>(j), static_cast<float>(cam.H * .5));
     const double l0 = __ddiv_rn(static_cast<double>(fi), cam.focal);
@@ -540,47 +560,16 @@ extern "C" int nrf_raynet_ext_slots(const NrfRayNetDesc* d) {
   return plan_raynet(d, &p) == NRF_OK ? p.n_ext_slots : -1;
 }
 
-extern "C" int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, int n_params, const float* feats, int64_t B,
-                            float* out, int32_t* nonuniform, void* stream) {
-  static thread_local NetPlan plan;
-  int rc = plan_raynet(d, &plan);
-  if (rc != NRF_OK) return rc;
-  if (plan.n_ext_slots < 1) { set_error("ray_bias: the net has no external pose-bias layers (ext_pose_bias = 0 or additional_input_dim = 0)"); return NRF_E_INVALID; }
-  const int nl = d->n_layers, A = d->additional_input_dim, P = d->positions_dim;
-  if (!params || n_params != 2 * (nl + 5)) { set_error("ray_bias: RenderRayNet expects %d parameter tensors, got %d", 2 * (nl + 5), n_params); return NRF_E_INVALID; }
-  if (!feats || !out) { set_error("ray_bias: NULL argument"); return NRF_E_INVALID; }
-  if (B < 0) { set_error("ray_bias: B < 0"); return NRF_E_INVALID; }
-  if (B == 0) return NRF_OK;
-  if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) { set_error("ray_bias: out must be 16-byte aligned"); return NRF_E_INVALID; }
-  RayBiasTable t;
-  t.n = plan.n_ext_slots;
-  for (int li = 0; li < plan.n_layers; ++li) {
-    const Layer& L = plan.layers[li];
-    if (L.ray_src != RAY_POSE_EXT) continue;
-    RayBiasJob& j = t.j[L.ext_idx];
-    // layer 0 = positions_pose_input: columns [pose(A) | xyz(P)]; layer li >= 1 = positional_net[li-1] with a skip:
-    // columns [activations(256) | pose(A) | xyz(P)]   (models/render_ray_net.py:22-31,43-49)
-    const int pidx = L.pidx;
-    if (!params[pidx] || !params[pidx + 1]) { set_error("ray_bias: parameter %d is NULL", pidx); return NRF_E_INVALID; }
-    if ((reinterpret_cast<uintptr_t>(params[pidx + 1]) & 15u) != 0) { set_error("ray_bias: bias tensors must be 16-byte aligned"); return NRF_E_INVALID; }
-    j.w = params[pidx]; j.bias = params[pidx + 1];
-    j.ld = li == 0 ? A + P : kWidth + A + P;
-    j.col0 = li == 0 ? 0 : kWidth;
-  }
-  if (nonuniform) {
-    cudaError_t e0 = cudaMemsetAsync(nonuniform, 0, sizeof(int32_t), static_cast<cudaStream_t>(stream));
-    if (e0 != cudaSuccess) return cuda_fail(e0, "cudaMemsetAsync(nonuniform)");
-    rows_differ_kernel<<<grid_for(B * A, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(feats, B, A, nonuniform);
-  }
-  const dim3 grid(static_cast<unsigned>((B + kRbM - 1) / kRbM), kWidth / kRbN, static_cast<unsigned>(t.n));
-  ray_bias_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, feats, B, A, out, nonuniform);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "ray_bias_kernel launch");
-}
-
 extern "C" int nrf_generate_rays(int32_t H, int32_t W, double focal, const double* camera_transform_host, const double* lower,
                                  const double* span, const double* jitter, int32_t n_coarse, float* ray_samples, float* ray_origin,
                                  float* ray_dir, float* z_vals, void* stream) {
+  return nrf_generate_rays_range(H, W, focal, camera_transform_host, lower, span, jitter, n_coarse, 0, static_cast<int64_t>(H) * W, ray_samples,
+                                 ray_origin, ray_dir, z_vals, stream);
+}
+
+extern "C" int nrf_generate_rays_range(int32_t H, int32_t W, double focal, const double* camera_transform_host, const double* lower,
+                                       const double* span, const double* jitter, int32_t n_coarse, int64_t ray0, int64_t n_rays,
+                                       float* ray_samples, float* ray_origin, float* ray_dir, float* z_vals, void* stream) {
   if (!camera_transform_host || !lower || !span || !jitter || !ray_samples || !ray_origin || !ray_dir || !z_vals) { set_error("generate_rays: NULL argument"); return NRF_E_INVALID; }
   if (H < 1 || W < 1 || n_coarse < 1 || !(focal > 0.0)) { set_error("generate_rays: bad shape H=%d W=%d n_coarse=%d focal=%g", H, W, n_coarse, focal); return NRF_E_INVALID; }
   CamParams cam;
@@ -588,8 +577,10 @@ extern "C" int nrf_generate_rays(int32_t H, int32_t W, double focal, const doubl
     for (int c = 0; c < 3; ++c) cam.r[3 * k + c] = camera_transform_host[4 * k + c];
     cam.t[k] = camera_transform_host[4 * k + 3];
   }
-  cam.focal = focal; cam.H = H; cam.W = W; cam.n = n_coarse;
-  const int64_t total = static_cast<int64_t>(H) * W * n_coarse;
+  if (ray0 < 0 || n_rays < 0 || ray0 + n_rays > static_cast<int64_t>(H) * W) { set_error("generate_rays: ray window [%lld, +%lld) outside the %d x %d view", (long long)ray0, (long long)n_rays, H, W); return NRF_E_INVALID; }
+  if (n_rays == 0) return NRF_OK;
+  cam.focal = focal; cam.H = H; cam.W = W; cam.n = n_coarse; cam.ray0 = ray0; cam.n_rays = n_rays;
+  const int64_t total = n_rays * n_coarse;
   generate_rays_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cam, lower, span, jitter, ray_samples, ray_origin,
                                                                                            ray_dir, z_vals);
   cudaError_t e = cudaGetLastError();
@@ -621,4 +612,32 @@ extern "C" int nrf_positional_encoding_backward(const float* x, const float* gra
   pe_bwd_kernel<<<grid_for(n * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, grad_out, n, c, freqs, identity, grad_x);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "pe_bwd_kernel launch");
+}
+
+extern "C" int nrf_ssim(const float* x, const float* y, int64_t n_planes, int32_t H, int32_t W, const float* kernel2d, int32_t ks, float c1,
+                        float c2, float* partial, float* ssim_out, float* cs_out, void* stream) {
+  if (!x || !y || !kernel2d || !partial || !ssim_out) { set_error("ssim: NULL argument"); return NRF_E_INVALID; }
+  if (ks < 1 || ks > kSsimMaxK || !(ks & 1)) { set_error("ssim: kernel size %d unsupported (odd, <= %d)", ks, kSsimMaxK); return NRF_E_INVALID; }
+  if (H < ks || W < ks) { set_error("ssim: Kernel size can't be greater than actual input size (%d x %d, kernel %d)", H, W, ks); return NRF_E_INVALID; }
+  if (n_planes < 0 || n_planes > 65535) { set_error("ssim: %lld image planes unsupported (max 65535)", (long long)n_planes); return NRF_E_INVALID; }
+  if (n_planes == 0) return NRF_OK;
+  const int Ho = H - ks + 1, Wo = W - ks + 1;
+  const int tiles = ((Ho + kSsimTile - 1) / kSsimTile) * ((Wo + kSsimTile - 1) / kSsimTile);
+  ssim_tile_kernel<<<dim3(tiles, static_cast<unsigned>(n_planes)), kSsimTile * kSsimTile, 0, static_cast<cudaStream_t>(stream)>>>(x, y, H, W, kernel2d, ks, c1, c2, partial);
+  ssim_reduce_kernel<<<static_cast<unsigned>(n_planes), 32, 0, static_cast<cudaStream_t>(stream)>>>(partial, tiles, 1.f / (static_cast<float>(Ho) * static_cast<float>(Wo)), ssim_out, cs_out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "ssim kernels launch");
+}
+extern "C" int64_t nrf_ssim_partial_floats(int64_t n_planes, int32_t H, int32_t W, int32_t ks) {
+  if (H < ks || W < ks || ks < 1) return 0;
+  const int Ho = H - ks + 1, Wo = W - ks + 1;
+  return n_planes * 2 * ((Ho + kSsimTile - 1) / kSsimTile) * ((Wo + kSsimTile - 1) / kSsimTile);
+}
+
+extern "C" int nrf_quantize_image(const float* rgb, int64_t n_pixels, uint8_t* out, int32_t to_bgr, void* stream) {
+  if (!rgb || !out || n_pixels < 0) { set_error("quantize_image: bad arguments"); return NRF_E_INVALID; }
+  if (n_pixels == 0) return NRF_OK;
+  quantize_bgr_kernel<<<grid_for(n_pixels, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rgb, n_pixels, out, to_bgr);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? NRF_OK : cuda_fail(e, "quantize_bgr_kernel launch");
 }

@@ -85,7 +85,10 @@ struct NetPlan {
 int plan_raynet(const NrfRayNetDesc* d, NetPlan* plan);
 int plan_warpnet(const NrfWarpNetDesc* d, NetPlan* plan);
 
+int launch_rows_differ(const float* feats, int64_t B, int A, int32_t* flag, cudaStream_t stream);   // nrf_ops.cu
 void set_error(const char* fmt, ...);
+// per-thread count of kernels launched by the training path (nrf_train_launch_count(): bench.py's gpu_launches accounting)
+extern thread_local long long g_train_launches;
 int cuda_fail(int err, const char* what);
 
 // Number of aux features (<= 64) an encoder produces for a 3-vector, and the reference column of

@@ -187,7 +187,7 @@ static int grid1(int64_t total, int block) {
   return static_cast<int>(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g));
 }
 #define TRY(x) do { int rc__ = (x); if (rc__ != NRF_OK) return rc__; } while (0)
-#define LAUNCH_CHECK(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return cuda_fail(e__, what); } while (0)
+#define LAUNCH_CHECK(what) do { ++g_train_launches; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return cuda_fail(e__, what); } while (0)
 
 struct TrainCtx {
   TrainCfg c; TNet net[2]; TrainWs ws;
@@ -369,6 +369,7 @@ static int forward_all(TrainCtx& t) {
       LAUNCH_CHECK("points_from_z_kernel");
     } else {
       TRY(nrf_fine_sampling(t.io.ray_origin, t.io.ray_dir, t.io.z_vals, t.ws.weights_c, t.io.u_fine, c.B, c.nc, c.nf, t.ws.z_all, pts, t.st));
+      ++g_train_launches;
     }
     t.ws.pass[1].pts = pts;
     t.ws.pass[1].z = t.ws.z_all;
@@ -548,6 +549,72 @@ extern "C" int nrf_train_backward(const NrfPipelineDesc* pipe, const NrfRayNetDe
   }
   Grads G; G.g[0] = grads_coarse; G.g[1] = grads_fine; G.g[2] = grads_warp;
   for (int p = 0; p < n_pass; ++p) TRY(backward_pass(t, p, G));
+  return NRF_OK;
+}
+
+extern "C" long long nrf_train_launch_count(int reset) { const long long n = g_train_launches; if (reset) g_train_launches = 0; return n; }
+
+// ------------------------------------------------------------------------------ per-ray pose bias of AppendSmplParamsPipeline (tcgen05)
+// out[b, e, n] = bias_e[n] + sum_k W_e[n, col0_e + k] * feats[b, k]     b < B, n < 256, k < A  (A = 69 or 1380)
+// for the n_ext layers of a RenderRayNet that read the A additional inputs (models/render_ray_net.py:43-49 with the input built by
+// models/append_smpl_params_pipeline.py:46-48: pose features FIRST).  The pose is constant along a ray, so this replaces A of
+// the K columns of two layers for every SAMPLE by one GEMM per RAY -- three fp16 hi/lo passes on the tensor cores
+// (tile_gemm, weight chunks streamed with the feature chunks: K = 1408 does not fit a resident slice).
+static size_t ray_bias_ws(const NetPlan& plan, int64_t B, int A, Planes* feats, Planes w[NRF_MAX_SKIPS + 1], uint8_t* base) {
+  const int Kp = (A + 63) & ~63;
+  Bump m{base, 0};
+  *feats = m.planes(B, Kp, true);
+  for (int e = 0; e < plan.n_ext_slots; ++e) w[e] = m.planes(kWidth, Kp, true);
+  return (m.off + 255) & ~static_cast<size_t>(255);
+}
+
+extern "C" size_t nrf_ray_bias_workspace_bytes(const NrfRayNetDesc* d, int64_t B) {
+  NetPlan plan;
+  if (plan_raynet(d, &plan) != NRF_OK || plan.n_ext_slots < 1 || B < 0) return 0;
+  Planes f, w[NRF_MAX_SKIPS + 1];
+  return ray_bias_ws(plan, B, d->additional_input_dim, &f, w, nullptr);
+}
+
+extern "C" int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, int n_params, const float* feats, int64_t B,
+                            float* out, int32_t* nonuniform, void* workspace, size_t workspace_bytes, void* stream) {
+  static thread_local NetPlan plan;
+  TRY(plan_raynet(d, &plan));
+  if (plan.n_ext_slots < 1) { set_error("ray_bias: the net has no external pose-bias layers (ext_pose_bias = 0 or additional_input_dim = 0)"); return NRF_E_INVALID; }
+  const int nl = d->n_layers, A = d->additional_input_dim, P = d->positions_dim;
+  if (!params || n_params != 2 * (nl + 5)) { set_error("ray_bias: RenderRayNet expects %d parameter tensors, got %d", 2 * (nl + 5), n_params); return NRF_E_INVALID; }
+  if (!feats || !out) { set_error("ray_bias: NULL argument"); return NRF_E_INVALID; }
+  if (B < 0) { set_error("ray_bias: B < 0"); return NRF_E_INVALID; }
+  if (B == 0) return NRF_OK;
+  if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) { set_error("ray_bias: out must be 16-byte aligned"); return NRF_E_INVALID; }
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) { set_error("ray_bias: workspace must be a 256-byte aligned device buffer"); return NRF_E_INVALID; }
+  Planes fp, wp[NRF_MAX_SKIPS + 1];
+  const size_t need = ray_bias_ws(plan, B, A, &fp, wp, static_cast<uint8_t*>(workspace));
+  if (need > workspace_bytes) { set_error("ray_bias: workspace too small (%zu bytes given, %zu needed)", workspace_bytes, need); return NRF_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static thread_local SplitTable tab;
+  tab.n = 0;
+  { SplitJob& j = tab.j[tab.n++]; j.src = feats; j.rows = static_cast<int32_t>(B); j.cols = A; j.ld = A; j.col0 = 0; j.hi = fp.hi; j.lo = fp.lo; j.ld_dst = fp.ld; j.cols_pad = fp.cols; j.wmax = nullptr; }
+  const float* bias[NRF_MAX_SKIPS + 1];
+  for (int li = 0; li < plan.n_layers; ++li) {
+    const Layer& L = plan.layers[li];
+    if (L.ray_src != RAY_POSE_EXT) continue;
+    // layer 0 = positions_pose_input: columns [pose(A) | xyz(P)]; a skip layer: [activations(256) | pose(A) | xyz(P)]   (render_ray_net.py:22-31,43-49)
+    if (!params[L.pidx] || !params[L.pidx + 1]) { set_error("ray_bias: parameter %d is NULL", L.pidx); return NRF_E_INVALID; }
+    if ((reinterpret_cast<uintptr_t>(params[L.pidx + 1]) & 15u) != 0) { set_error("ray_bias: bias tensors must be 16-byte aligned"); return NRF_E_INVALID; }
+    SplitJob& j = tab.j[tab.n++];
+    j.src = params[L.pidx]; j.rows = kWidth; j.cols = A; j.ld = li == 0 ? A + P : kWidth + A + P; j.col0 = li == 0 ? 0 : kWidth;
+    j.hi = wp[L.ext_idx].hi; j.lo = wp[L.ext_idx].lo; j.ld_dst = wp[L.ext_idx].ld; j.cols_pad = wp[L.ext_idx].cols; j.wmax = nullptr;
+    bias[L.ext_idx] = params[L.pidx + 1];
+  }
+  split_planes_kernel<<<dim3(148, tab.n), 256, 0, st>>>(tab);
+  LAUNCH_CHECK("split_planes_kernel");
+  if (nonuniform) TRY(launch_rows_differ(feats, B, A, nonuniform, st));
+  for (int e = 0; e < plan.n_ext_slots; ++e) {
+    TileGemmArgs g{};
+    g.a[0] = fp; g.b[0] = wp[e]; g.n_src = 1; g.N = kWidth; g.passes = 3; g.epi = GEPI_F32; g.bias = bias[e];
+    g.out_f32 = out + static_cast<size_t>(e) * kWidth; g.out_f32_ld = plan.n_ext_slots * kWidth;
+    TRY(launch_tile_gemm(g, 0, st));
+  }
   return NRF_OK;
 }
 

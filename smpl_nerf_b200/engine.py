@@ -199,7 +199,7 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
             pipe.pose_encoded = 1 if args.human_pose_encoding else 0
             pipe.pose_stride, pipe.pose_col0, pipe.pose_col1 = int(goal.shape[1]), 0, 0
         elif full_pose:
-            # pose features exactly as models/append_smpl_params_pipeline.py:30-37 builds them, then one SGEMM per net
+            # pose features exactly as models/append_smpl_params_pipeline.py:30-37 builds them, then one tcgen05 GEMM per net and hoisted layer
             encoded = bool(args.human_pose_encoding)
             A = int(goal.shape[1]) * (pose_enc.output_dim if encoded else 1)
             if A != dc.additional_input_dim:
@@ -210,6 +210,7 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
                 check(L.nrf_positional_encoding(goal.data_ptr(), B, int(goal.shape[1]), *_enc_cfg(pose_enc), feats.data_ptr(),
                                                 stream), 'nrf_positional_encoding(goal_pose)')
             flag = torch.empty(1, dtype=torch.int32, device=device)     # 0 after nrf_ray_bias: one pose for the whole batch
+            rb_out = []
             for net, desc in ((model_coarse, dc),) + (((model_fine, df),) if run_fine else ()):
                 n_ext = L.nrf_raynet_ext_slots(C.byref(desc))
                 if n_ext < 1:
@@ -218,12 +219,15 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
                 ps = _params(net, device)
                 arr = (C.c_void_p * len(ps))(*[p.data_ptr() for p in ps])
                 if B > 0:
-                    check(L.nrf_ray_bias(C.byref(desc), arr, len(ps), feats.data_ptr(), B, rb.data_ptr(), flag.data_ptr(), stream),
-                          'nrf_ray_bias')
-                ray_bias.append(rb)
-                ray_bias.append(ps)          # keep (possibly re-laid-out) parameter tensors alive until the launch
-            ray_bias.append(feats)
-            ray_bias.append(flag)
+                    wsb = L.nrf_ray_bias_workspace_bytes(C.byref(desc), B)
+                    wsp = torch.empty(wsb + 256, dtype=torch.uint8, device=device)
+                    woff = (-wsp.data_ptr()) % 256
+                    check(L.nrf_ray_bias(C.byref(desc), arr, len(ps), feats.data_ptr(), B, rb.data_ptr(), flag.data_ptr(),
+                                         wsp.data_ptr() + woff, wsb, stream), 'nrf_ray_bias')
+                    ray_bias.append(wsp)
+                rb_out.append(rb)
+                ray_bias += [rb] + list(ps)          # keep (possibly re-laid-out) parameter tensors alive until the launch
+            ray_bias += [feats, flag]
         elif kind != 'nerf':
             pipe.pose_freqs, pipe.pose_identity = _enc_cfg(pose_enc)
             pipe.pose_encoded = 1 if args.human_pose_encoding else 0
@@ -248,10 +252,10 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
             io.goal_pose = goal.data_ptr()
         keep = [samples, origin, direction, z, goal]
         if full_pose and not train_mode:
-            io.ray_bias_nonuniform = ray_bias[-1].data_ptr()
-            io.ray_bias_coarse = ray_bias[0].data_ptr()
+            io.ray_bias_nonuniform = flag.data_ptr()
+            io.ray_bias_coarse = rb_out[0].data_ptr()
             if run_fine:
-                io.ray_bias_fine = ray_bias[2].data_ptr()
+                io.ray_bias_fine = rb_out[1].data_ptr()
             keep += [t for t in ray_bias if isinstance(t, torch.Tensor)]
         if run_fine:
             u = _u_fine(nf, device)
@@ -316,6 +320,6 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
 def launches_per_render(kind: str = 'nerf', run_fine: bool = True, pose_encoded: bool = True) -> int:
     """Kernels of this library launched by one render() call with warm weight caches."""
     n = int(_lib.lib().nrf_render_launches())
-    if kind == 'append_full':      # pose encoding + (row-uniformity check, per-ray bias SGEMM) per net
-        n += (1 if pose_encoded else 0) + 2 * (2 if run_fine else 1)
+    if kind == 'append_full':      # pose encoding + per net: plane split, row-uniformity probe, one tcgen05 GEMM per hoisted layer (2)
+        n += (1 if pose_encoded else 0) + 4 * (2 if run_fine else 1)
     return n

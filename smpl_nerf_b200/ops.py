@@ -6,6 +6,7 @@
     utils.py:194-228  sample_pdf          -> sample_pdf
     utils.py:231-264  fine_sampling       -> fine_sampling
     torchsearchsorted/src/torchsearchsorted/searchsorted.py:20-53 -> searchsorted (same asserts)
+    util/scores.py:88-173  ssim / gaussian_filter / img2mse / img2psnr -> ssim, gaussian_filter, img2mse, img2psnr
 
 CUDA tensors only -- there is no CPU path in this package.
 """
@@ -199,4 +200,72 @@ def searchsorted(a: torch.Tensor, v: torch.Tensor, out: Optional[torch.Tensor] =
         check(_lib.lib().nrf_searchsorted(a32.data_ptr(), a32.shape[0], a32.shape[1], v32.data_ptr(), v32.shape[0],
                                           v32.shape[1], out.data_ptr(), 1 if side == 'left' else 0,
                                           _stream(a.device)), 'nrf_searchsorted')
+    return out
+
+
+# --------------------------------------------------------------------------------------------------- metrics (util/scores.py)
+def gaussian_filter(size: int, sigma: float) -> torch.Tensor:
+    """2-D Gaussian window [1, size, size], built exactly like util/scores.py:68-86 (fp32 on the host)."""
+    coords = torch.arange(size).to(dtype=torch.float32)
+    coords -= (size - 1) / 2.
+    g = coords ** 2
+    g = (- (g.unsqueeze(0) + g.unsqueeze(1)) / (2 * sigma ** 2)).exp()
+    g /= g.sum()
+    return g.unsqueeze(0)
+
+
+_window_cache = {}
+
+
+def ssim(x: torch.Tensor, y: torch.Tensor, kernel_size: int = 11, kernel_sigma: float = 1.5, data_range=1., reduction: str = 'mean',
+         full: bool = False, k1: float = 0.01, k2: float = 0.03):
+    """Structural similarity with the signature and semantics of util/scores.py:88-131 for 4-D inputs ``(N, C, H, W)``
+    (CUDA, fp32): per-channel valid-window SSIM (one kernel + a fixed-order reduction on the device), mean over channels, then
+    ``reduction`` over the batch.  ``full=True`` also returns the contrast-structure term."""
+    _need_cuda(x, 'x')
+    if x.dim() != 4 or x.shape != y.shape:
+        raise ValueError(f'ssim expects two (N, C, H, W) tensors of the same shape, got {tuple(x.shape)} and {tuple(y.shape)}')
+    dev = x.device
+    N, Cn, H, W = (int(v) for v in x.shape)
+    if H < kernel_size or W < kernel_size:
+        raise ValueError(f"Kernel size can't be greater than actual input size. Input size: {x.size()}. Kernel size: {kernel_size}")
+    xx, yy = _f32(x, 'x', dev), _f32(y, 'y', dev)
+    key = (kernel_size, float(kernel_sigma), str(dev))
+    if key not in _window_cache:
+        _window_cache[key] = gaussian_filter(kernel_size, kernel_sigma)[0].contiguous().to(dev)
+    win = _window_cache[key]
+    L = _lib.lib()
+    planes = N * Cn
+    partial = torch.empty(max(1, int(L.nrf_ssim_partial_floats(planes, H, W, kernel_size))), dtype=torch.float32, device=dev)
+    s_out = torch.empty(N, Cn, dtype=torch.float32, device=dev)
+    c_out = torch.empty(N, Cn, dtype=torch.float32, device=dev)
+    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+    with torch.cuda.device(dev):
+        check(L.nrf_ssim(xx.data_ptr(), yy.data_ptr(), planes, H, W, win.data_ptr(), kernel_size, c1, c2, partial.data_ptr(),
+                         s_out.data_ptr(), c_out.data_ptr(), _stream(dev)), 'nrf_ssim')
+    ssim_val, cs = s_out.mean(1), c_out.mean(1)
+    if reduction != 'none':
+        op = {'mean': torch.mean, 'sum': torch.sum}[reduction]
+        ssim_val, cs = op(ssim_val, dim=0), op(cs, dim=0)
+    return (ssim_val, cs) if full else ssim_val
+
+
+def img2mse(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    return torch.mean((x - y) ** 2)           # util/scores.py:11-28
+
+
+def img2psnr(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    return -10. * torch.log10(torch.mean((x - y) ** 2))       # util/scores.py:30-48 (log / log(10))
+
+
+def to_uint8_bgr(images: torch.Tensor, to_bgr: bool = True) -> torch.Tensor:
+    """inference.py:260-262 on the device: ``clip(img, 0, 1) * 255`` -> uint8 (truncating cast), channels flipped to BGR."""
+    _need_cuda(images, 'images')
+    img = _f32(images, 'images', images.device)
+    if img.shape[-1] != 3:
+        raise ValueError('images must be [..., 3]')
+    out = torch.empty(img.shape, dtype=torch.uint8, device=img.device)
+    with torch.cuda.device(img.device):
+        check(_lib.lib().nrf_quantize_image(img.data_ptr(), img.numel() // 3, out.data_ptr(), 1 if to_bgr else 0, _stream(img.device)),
+              'nrf_quantize_image')
     return out

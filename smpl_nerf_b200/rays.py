@@ -31,12 +31,14 @@ def _bins(n_coarse: int, near: float, far: float, device):
 
 def generate_view(h: int, w: int, camera_transform: np.ndarray, *, camera_angle_x: float = scene.CAMERA_ANGLE_X,
                   near: float = scene.NEAR, far: float = scene.FAR, n_coarse: int = 64, jitter=None,
-                  rng: Optional[np.random.RandomState] = None, device='cuda:0') -> List[torch.Tensor]:
+                  rng: Optional[np.random.RandomState] = None, device=None, ray_range=None) -> List[torch.Tensor]:
     """-> ``[ray_samples[B,Nc,3], ray_translation[B,3], ray_direction[B,3], z_vals[B,Nc]]`` (fp32, on ``device``),
     B = h*w rays in row-major pixel order.  ``jitter``: [B] float64 (host array or device tensor) -- the one
     ``np.random.rand()`` scalar CoarseSampling draws per ray; drawn from ``rng`` (default: numpy's global stream,
-    like the reference) when omitted."""
-    device = torch.device(device)
+    like the reference) when omitted.  ``ray_range = (start, stop)``: build only those rays of the view (a rank's shard of a
+    multi-GPU render); the jitter stream is still drawn for the WHOLE view so every rank sees the same scalars.
+    ``device``: default = the current CUDA device."""
+    device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
     if device.type != 'cuda':
         raise RuntimeError('smpl_nerf_b200.rays runs on CUDA devices only (no CPU fallback)')
     cam = np.ascontiguousarray(np.asarray(camera_transform, dtype=np.float64))
@@ -47,9 +49,13 @@ def generate_view(h: int, w: int, camera_transform: np.ndarray, *, camera_angle_
         jitter = (rng.rand(B) if rng is not None else np.random.rand(B))
     if not isinstance(jitter, torch.Tensor):
         jitter = torch.from_numpy(np.ascontiguousarray(np.asarray(jitter, dtype=np.float64)))
-    jitter = jitter.to(device=device, dtype=torch.float64).contiguous()
     if jitter.numel() != B:
         raise ValueError(f'jitter must have {B} entries, got {jitter.numel()}')
+    r0, r1 = (0, B) if ray_range is None else (int(ray_range[0]), int(ray_range[1]))
+    if not (0 <= r0 <= r1 <= B):
+        raise ValueError(f'ray_range {ray_range} outside [0, {B}]')
+    jitter = jitter.reshape(-1)[r0:r1].to(device=device, dtype=torch.float64).contiguous()      # only the shard crosses PCIe
+    B = r1 - r0
     focal = float(.5 * w / np.tan(.5 * camera_angle_x))          # datasets/smpl_nerf_dataset.py:58
     with torch.cuda.device(device):
         lower, span = _bins(n_coarse, near, far, device)
@@ -58,8 +64,8 @@ def generate_view(h: int, w: int, camera_transform: np.ndarray, *, camera_angle_
         direction = torch.empty(B, 3, dtype=torch.float32, device=device)
         z = torch.empty(B, n_coarse, dtype=torch.float32, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
-        check(_lib.lib().nrf_generate_rays(h, w, focal, cam.ctypes.data_as(C.POINTER(C.c_double)), lower.data_ptr(), span.data_ptr(),
-                                           jitter.data_ptr(), n_coarse, samples.data_ptr(), origin.data_ptr(), direction.data_ptr(),
-                                           z.data_ptr(), stream), 'nrf_generate_rays')
+        check(_lib.lib().nrf_generate_rays_range(h, w, focal, cam.ctypes.data_as(C.POINTER(C.c_double)), lower.data_ptr(), span.data_ptr(),
+                                                 jitter.data_ptr(), n_coarse, r0, B, samples.data_ptr(), origin.data_ptr(),
+                                                 direction.data_ptr(), z.data_ptr(), stream), 'nrf_generate_rays_range')
         jitter.record_stream(torch.cuda.current_stream(device))
     return [samples, origin, direction, z]

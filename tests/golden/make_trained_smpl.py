@@ -3,7 +3,8 @@
     python tests/golden/make_trained_smpl.py
 
 Trains the HEADLINE architecture -- SmplNerfPipeline, two RenderRayNet 8x256 (skips=[4]) + WarpFieldNet, 64 coarse +
-128 fine samples -- for a few hundred Adam steps with the REFERENCE classes (imported from /root/reference; loss =
+128 fine samples, starting from the 'dense' init (default init with the sigma head x20 / bias +1: from the plain default init
+this scene collapses to "all white" within 700 steps) -- for a few hundred Adam steps with the REFERENCE classes (imported from /root/reference; loss =
 MSE(rgb) + MSE(rgb_fine), solver/smpl_nerf_solver.py:35-43 without the optional GMM term) on 64x64 views of the synthetic
 capsule figure whose arms MOVE with the pose (arm angle 0..60 degrees, goal_pose columns 38 and 41), then renders a
 held-out view (unseen camera, unseen arm angle) with the reference pipeline in fp32 AND in fp64 and stores:
@@ -38,7 +39,7 @@ def main():
     torch.manual_seed(0)
     np.random.seed(0)
     torch.set_num_threads(int(os.environ.get('NRF_TRAIN_THREADS', os.cpu_count() or 1)))
-    c, f, w, pe, de, he = O.build_nets('smpl', 41, 'default', net_cls=ref.RenderRayNet, warp_cls=ref.WarpFieldNet,
+    c, f, w, pe, de, he = O.build_nets('smpl', 41, 'dense', net_cls=ref.RenderRayNet, warp_cls=ref.WarpFieldNet,
                                        enc_cls=ref.PositionalEncoder)
     for m in (c, f, w):
         m.train()

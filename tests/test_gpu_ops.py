@@ -88,10 +88,10 @@ def test_fine_sampling(nc, nf):
     err = (z_got - z_want).abs()
     assert float(torch.quantile(err.flatten(), 0.98)) <= 1e-5
     assert float(err.max()) <= float((z[:, 1:] - z[:, :-1]).max()) + 1e-5
-    # where the kernel's depths agree with the oracle's to 1e-6 the points do too
-    close = (err.max(-1).values <= 1e-6)
-    assert int(close.sum()) > B // 2
-    assert float((pts_got[close] - pts_want[close]).abs().max()) <= 1e-5
+    # where the kernel's depths agree with the oracle's to a few ulp the points do too
+    close = err <= 2e-6
+    assert float(close.float().mean()) > 0.9
+    assert float((pts_got[close] - pts_want[close]).abs().max()) <= 2e-5
 
 
 @pytest.mark.parametrize('Ba,Bv', [(1, 1), (100, 100), (1, 100), (100, 1)])
@@ -163,6 +163,52 @@ def test_render_driver_matches_batched_pipeline_calls():
         assert torch.equal(frames[k].reshape(-1, 3), want)
     psnr = render.psnr_per_frame(frames, frames.clone() + 0.1)
     assert all(abs(p - 20.0) < 1e-3 for p in psnr)
+    # a rank's window of the view == the same rows of the whole view (what a sharded render generates)
+    import numpy as np
+    from smpl_nerf_b200 import rays
+    jit = np.random.RandomState(3).rand(h * w)
+    full = rays.generate_view(h, w, cams[0], n_coarse=64, jitter=jit)
+    part = rays.generate_view(h, w, cams[0], n_coarse=64, jitter=jit, ray_range=(37, 101))
+    for a, b in zip(full, part):
+        assert torch.equal(a[37:101], b)
+
+
+@pytest.mark.parametrize('shape,ks', [((2, 3, 64, 64), 11), ((1, 3, 37, 53), 11), ((3, 1, 16, 128), 7), ((1, 3, 11, 11), 11)])
+def test_ssim_matches_the_reference_formula(shape, ks):
+    """ops.ssim (nrf_ssim) against the oracle restatement of util/scores.py:88-173 (pinned to the reference on the CPU)."""
+    from oracle import scores_oracle as S
+    torch.manual_seed(sum(shape))
+    x = torch.rand(shape)
+    y = (x + 0.1 * torch.randn(shape)).clamp(0, 1)
+    want, want_cs = S.ssim(x, y, kernel_size=ks, full=True)
+    got, got_cs = ops.ssim(x.to(DEV), y.to(DEV), kernel_size=ks, full=True)
+    assert abs(float(got) - float(want)) <= 2e-6 and abs(float(got_cs) - float(want_cs)) <= 2e-6
+    none = ops.ssim(x.to(DEV), y.to(DEV), kernel_size=ks, reduction='none')
+    assert none.shape == (shape[0],) and float((none.cpu() - S.ssim(x, y, kernel_size=ks, reduction='none')).abs().max()) <= 2e-6
+    assert abs(float(ops.ssim(x.to(DEV), x.to(DEV), kernel_size=ks)) - 1.0) <= 1e-6
+    assert abs(float(ops.img2psnr(x.to(DEV), y.to(DEV))) - float(S.psnr(x, y))) <= 1e-4
+    with pytest.raises(ValueError):
+        ops.ssim(x.to(DEV)[..., :5, :5], y.to(DEV)[..., :5, :5], kernel_size=ks)
+
+
+def test_scores_and_png_writer(tmp_path):
+    """render.scores (MSE / PSNR / SSIM on the device) and render.save_frames (inference.py:260-274: clip, x255, uint8, BGR, PNG)."""
+    import cv2
+    import numpy as np
+    from oracle import scores_oracle as S
+    from smpl_nerf_b200 import render
+    torch.manual_seed(3)
+    frames = torch.rand(2, 24, 20, 3) * 1.2 - 0.1
+    truth = frames.clamp(0, 1) * 0.9
+    sc = render.scores(frames.to(DEV), truth.to(DEV))
+    x, y = frames.permute(0, 3, 1, 2), truth.permute(0, 3, 1, 2)
+    assert abs(sc['mse'] - float(S.mse(x, y))) <= 1e-7 and abs(sc['psnr'] - float(S.psnr(x, y))) <= 1e-4
+    assert abs(sc['ssim'] - float(S.ssim(x, y))) <= 2e-6
+    paths = render.save_frames(frames.to(DEV), str(tmp_path / 'run'))
+    assert [p.split('/')[-1] for p in paths] == ['img_000.png', 'img_001.png']
+    want = (np.clip(frames.numpy(), 0, 1) * 255).astype(np.uint8)[..., ::-1]       # inference.py:260-262
+    for p, w in zip(paths, want):
+        assert np.array_equal(cv2.imread(p, cv2.IMREAD_UNCHANGED), w)
 
 
 @pytest.mark.parametrize('white,with_noise', [(1, False), (0, True)])

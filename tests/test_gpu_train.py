@@ -28,7 +28,8 @@ def _planes(x, pad=None):
 
 
 @pytest.mark.parametrize('passes', [3, 1])
-@pytest.mark.parametrize('S,K,N', [(1000, 256, 256), (128, 64, 256), (777, 128, 128), (4096, 256, 64), (50, 256, 128)])
+@pytest.mark.parametrize('S,K,N', [(1000, 256, 256), (128, 64, 256), (777, 128, 128), (4096, 256, 64), (50, 256, 128),
+                                   (500, 1408, 256), (300, 576, 512)])      # the last two: K too large for a resident weight slice
 def test_gemm_forward_and_dx(S, K, N, passes):
     """nrf_gemm_planes: C = A B^T (weights K-major, the forward of nn.Linear, bias + ReLU fused) and C = A B (weights
     N-major: dX = dY W) against fp64 matmuls of the same fp32 inputs."""

@@ -136,7 +136,7 @@ def test_render_argument_errors_are_reported_without_a_gpu(L):
     pipe.kind = 7
     assert L.nrf_render(C.byref(pipe), C.byref(dc), blob, None, None, None, None, C.byref(io), 8, 0, None) == -1
     assert b'kind' in L.nrf_last_error()
-    assert L.nrf_ray_bias(C.byref(dc), None, 0, None, 8, None, None, None) == -1          # not an ext_pose_bias net
+    assert L.nrf_ray_bias(C.byref(dc), None, 0, None, 8, None, None, None, 0, None) == -1          # not an ext_pose_bias net
     assert b'ext_pose_bias' in L.nrf_last_error()
     assert L.nrf_generate_rays(0, 4, 1.0, None, None, None, None, 8, None, None, None, None, None) == -1
 

@@ -117,3 +117,21 @@ def test_sigma_noise_same_draw(reference):
         got = O.as_tuple(O.nerf_forward(mine[0], mine[1], mine[3], mine[4], args, data, noise_coarse=n_c, noise_fine=n_f))
     for a, b in zip(want, got):
         assert torch.equal(a, b)
+
+
+def test_scores_match_reference(reference):
+    """oracle/scores_oracle.py == util/scores.py (ssim, gaussian_filter, img2mse, img2psnr), bit for bit on the CPU."""
+    import importlib
+    try:
+        sc = importlib.import_module('util.scores')
+    except Exception as e:       # noqa: BLE001  (torchvision / cv2 missing would only skip this pin)
+        pytest.skip(f'util.scores not importable here: {e!r}')
+    from oracle import scores_oracle as S
+    torch.manual_seed(0)
+    for shape, ks in (((2, 3, 40, 37), 11), ((1, 1, 16, 16), 7)):
+        x, y = torch.rand(shape), torch.rand(shape)
+        assert torch.equal(sc.gaussian_filter(ks, 1.5), S.gaussian_filter(ks, 1.5))
+        for red in ('mean', 'none', 'sum'):
+            a, b = sc.ssim(x, y, kernel_size=ks, reduction=red, full=True), S.ssim(x, y, kernel_size=ks, reduction=red, full=True)
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        assert torch.equal(sc.img2mse(x, y), S.mse(x, y)) and torch.equal(sc.img2psnr(x, y), S.psnr(x, y))
