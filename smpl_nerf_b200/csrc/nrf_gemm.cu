@@ -427,7 +427,7 @@ int launch_dw_gemm(const Planes& a, int m0, int M, const Planes& b, int n0, int 
   if (passes != 1 && passes != 3) { set_error("dw_gemm: passes must be 1 or 3"); return NRF_E_INVALID; }
   if (M < 128 || (M & 127) || N < 64 || N > 256 || (N & 63)) { set_error("dw_gemm: M = %d (multiple of 128) / N = %d (64..256, multiple of 64) unsupported", M, N); return NRF_E_INVALID; }
   if (a.rows != b.rows || a.rows <= 0) { set_error("dw_gemm: operand row counts differ (%lld vs %lld)", (long long)a.rows, (long long)b.rows); return NRF_E_INVALID; }
-  if (m0 + M > a.cols || n0 + N > b.cols) { set_error("dw_gemm: column window outside the planes"); return NRF_E_INVALID; }
+  if (m0 + M > ((a.cols + 127) & ~127) || n0 + N > b.cols) { set_error("dw_gemm: column window outside the planes"); return NRF_E_INVALID; }     // dY columns past a.cols are zero-filled by the TMA
   if (passes == 3 && (!a.lo || !b.lo)) { set_error("dw_gemm: 3 passes need the lo planes"); return NRF_E_INVALID; }
   int rc;
   if ((rc = encode_planes_map(&P.a_hi, a.hi, a.rows, a.cols, a.ld, 64, 64)) != NRF_OK) return rc;

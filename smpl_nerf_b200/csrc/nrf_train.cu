@@ -24,17 +24,20 @@ struct TLayer {
   int role, pidx, n_out, in_act, aux /*0 none, 1 xyz encoding, 2 direction encoding*/, aux_cols;
   int ray_src /*0, 1 pose, 2 dir*/, ray_k, ld, col_act, col_ray, col_aux, relu;
 };
-struct TNet { int n; int nl; TLayer L[kMaxLayers]; int A, P, D; };
+struct TNet { int n; int nl; int W; TLayer L[kMaxLayers]; int A, P, D; };      // W: hidden width of this net (128 / 256 / 512)
 
 static int plan_train_net(const NrfRayNetDesc* d, TNet* t) {
   NetPlan tmp;
   NrfRayNetDesc dd = *d;
   dd.fold_linear = 0;
   dd.ext_pose_bias = d->additional_input_dim > 0 ? 1 : 0;     // any A is fine here: pose inputs are always hoisted per ray
-  int rc = plan_raynet(&dd, &tmp);                             // shape validation (same limits as the renderer)
+  dd.width = kWidth;                                           // the layer-by-layer path is not tied to the fused kernel's width ...
+  int rc = plan_raynet(&dd, &tmp);                             // ... every other shape check is shared with the renderer
   if (rc != NRF_OK) return rc;
+  if (d->width != 128 && d->width != 256 && d->width != 512) { set_error("RenderRayNet width %d unsupported (128, 256 or 512)", d->width); return NRF_E_INVALID; }
   memset(t, 0, sizeof(*t));
-  const int nl = d->n_layers, W = kWidth, A = d->additional_input_dim, P = d->positions_dim;
+  const int nl = d->n_layers, W = d->width, A = d->additional_input_dim, P = d->positions_dim;
+  t->W = W;
   const int D = d->use_directional_input ? d->directions_dim : 0;
   t->nl = nl; t->A = A; t->P = P; t->D = D;
   auto is_skip = [&](int i) { for (int s = 0; s < d->n_skips; ++s) if (d->skips[s] == i) return true; return false; };
@@ -94,6 +97,7 @@ struct TrainWs {
 
 struct TrainCfg {
   int kind, nc, nf, na, run_fine, white, passes, smpl, A_pose /*per-ray pose features of the pipeline*/, n_sel;
+  int Ww /*warp net width*/, Wmax /*largest hidden width of any net*/;
   int64_t B;
 };
 
@@ -106,7 +110,7 @@ static void layout_ws(Bump& m, const TrainCfg& c, const TNet net[2], TrainWs* ws
       if (L.in_act) ws->w[p].act[l] = m.planes(L.n_out, L.in_act, lo);
       if (L.aux) ws->w[p].aux[l] = m.planes(L.n_out, 64, lo);
     }
-  if (c.smpl) ws->warp_w = m.planes(kWidth, 64, lo);
+  if (c.smpl) ws->warp_w = m.planes(c.Ww, 64, lo);
   ws->pose_feat = m.take<float>(static_cast<size_t>(c.B) * (c.A_pose > 0 ? c.A_pose : 1));
   ws->dir_feat = m.take<float>(static_cast<size_t>(c.B) * 64);
   ws->ray_norm = m.take<float>(c.B);
@@ -121,27 +125,27 @@ static void layout_ws(Bump& m, const TrainCfg& c, const TNet net[2], TrainWs* ws
     w.S = c.B * w.n;
     Smax = w.S > Smax ? w.S : Smax;
     w.encx = m.planes(w.S, 64, lo);
-    if (c.smpl) { w.encd = m.planes(w.S, 64, lo); w.wpe = m.planes(w.S, 64, lo); w.warph = m.planes(w.S, kWidth, lo);
-                  w.warph_f32 = m.take<float>(static_cast<size_t>(w.S) * kWidth); w.warp_raw = m.take<float>(static_cast<size_t>(w.S) * 3);
+    if (c.smpl) { w.encd = m.planes(w.S, 64, lo); w.wpe = m.planes(w.S, 64, lo); w.warph = m.planes(w.S, c.Ww, lo);
+                  w.warph_f32 = m.take<float>(static_cast<size_t>(w.S) * c.Ww); w.warp_raw = m.take<float>(static_cast<size_t>(w.S) * 3);
                   w.warped = m.take<float>(static_cast<size_t>(w.S) * 3); w.u = m.take<float>(static_cast<size_t>(w.S) * 3);
-                  w.rbw = m.take<float>(static_cast<size_t>(c.B) * kWidth); w.g_dnorm = m.take<float>(w.S); }
+                  w.rbw = m.take<float>(static_cast<size_t>(c.B) * c.Ww); w.g_dnorm = m.take<float>(w.S); }
     w.dnorm = m.take<float>(w.S);
     for (int l = 0; l < net[p].n; ++l) {
       const TLayer& L = net[p].L[l];
       w.act[l] = m.planes(w.S, L.n_out, lo);
       if (L.ray_src) w.rb[l] = m.take<float>(static_cast<size_t>(c.B) * L.n_out);
     }
-    w.a_f32 = m.take<float>(static_cast<size_t>(w.S) * kWidth);
-    w.h2_f32 = m.take<float>(static_cast<size_t>(w.S) * (kWidth / 2));
+    w.a_f32 = m.take<float>(static_cast<size_t>(w.S) * net[p].W);
+    w.h2_f32 = m.take<float>(static_cast<size_t>(w.S) * (net[p].W / 2));
     w.raw = m.take<float>(static_cast<size_t>(w.S) * 4);
     w.g_raw = m.take<float>(static_cast<size_t>(w.S) * 4);
   }
-  ws->dy[0] = m.planes(Smax, kWidth, true);
-  ws->dy[1] = m.planes(Smax, kWidth, true);
-  ws->dysum = m.take<float>(static_cast<size_t>(c.B) * kWidth);
+  ws->dy[0] = m.planes(Smax, c.Wmax, true);
+  ws->dy[1] = m.planes(Smax, c.Wmax, true);
+  ws->dysum = m.take<float>(static_cast<size_t>(c.B) * c.Wmax);
   if (c.smpl) { ws->g_encx = m.take<float>(static_cast<size_t>(Smax) * 64); ws->g_encd = m.take<float>(static_cast<size_t>(Smax) * 64);
                 ws->g_warp = m.take<float>(static_cast<size_t>(Smax) * 3); }
-  ws->partial = m.take<float>(static_cast<size_t>(148) * kWidth * kWidth);
+  ws->partial = m.take<float>(static_cast<size_t>(148) * 128 * 256);     // split x M x N <= (148 / (M / 128)) x M x 256
   ws->sc = m.take<float>(2 * kScaleSlots);
   ws->mx = reinterpret_cast<unsigned int*>(m.take<float>(kScaleSlots));
   ws->wmax = reinterpret_cast<unsigned int*>(m.take<float>(kWmaxSlots));
@@ -165,6 +169,9 @@ static int make_cfg(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, co
     if ((rc = plan_train_net(fine, &net[1])) != NRF_OK) return rc;
     if (fine->additional_input_dim != coarse->additional_input_dim) { set_error("train: coarse/fine additional_input_dim differ"); return NRF_E_INVALID; }
   }
+  c->Wmax = net[0].W;
+  if (c->run_fine && net[1].W > c->Wmax) c->Wmax = net[1].W;
+  if (pipe->kind == NRF_KIND_SMPL && warp && warp->width > c->Wmax) c->Wmax = warp->width;
   if (pipe->kind != NRF_KIND_NERF) {
     c->n_sel = pipe->pose_all ? pipe->pose_stride : 2;
     c->A_pose = pipe->pose_encoded ? c->n_sel * (2 * pipe->pose_freqs + (pipe->pose_identity ? 1 : 0)) : c->n_sel;
@@ -172,7 +179,8 @@ static int make_cfg(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, co
   if (c->smpl) {
     if (!warp) { set_error("train: the smpl pipeline needs the warp net"); return NRF_E_INVALID; }
     if (!pipe->pose_encoded) { set_error("train: the smpl pipeline is trainable with human_pose_encoding=1 only (the reference's fine pass always feeds the warp net encoded inputs, smpl_nerf_pipeline.py:71-77)"); return NRF_E_INVALID; }
-    if (warp->width != kWidth || warp->positions_dim != enc_dim(warp->in_freqs, warp->in_identity) || warp->positions_dim > 64) { set_error("train: unsupported warp net shape"); return NRF_E_INVALID; }
+    if ((warp->width != 128 && warp->width != 256 && warp->width != 512) || warp->positions_dim != enc_dim(warp->in_freqs, warp->in_identity) || warp->positions_dim > 64) { set_error("train: unsupported warp net shape (width 128 / 256 / 512, <= 64 position features)"); return NRF_E_INVALID; }
+    c->Ww = warp->width;
     if (warp->pose_dim != c->A_pose) { set_error("train: warp net pose_dim %d != pipeline pose features %d", warp->pose_dim, c->A_pose); return NRF_E_INVALID; }
     if (!coarse->per_sample_dirs || (c->run_fine && !fine->per_sample_dirs)) { set_error("train: smpl pipeline needs per_sample_dirs=1 nets"); return NRF_E_INVALID; }
   } else {
@@ -245,14 +253,14 @@ static int split_weights(TrainCtx& t) {
       if (L.in_act) TRY(add(W, L.n_out, L.in_act, L.ld, L.col_act, t.ws.w[p].act[l], t.ws.wmax + wslot(p, l)));
       if (L.aux) TRY(add(W, L.n_out, L.aux_cols, L.ld, L.col_aux, t.ws.w[p].aux[l], nullptr));
     }
-  if (t.c.smpl) TRY(add(t.par[2][0], kWidth, t.wd->positions_dim, t.wd->positions_dim + t.wd->pose_dim, 0, t.ws.warp_w, nullptr));
+  if (t.c.smpl) TRY(add(t.par[2][0], t.c.Ww, t.wd->positions_dim, t.wd->positions_dim + t.wd->pose_dim, 0, t.ws.warp_w, nullptr));
   TRY(flush());
   for (int p = 0; p < n_pass; ++p) {
     const int nl = t.net[p].nl;
-    absmax_kernel<<<1, 128, 0, t.st>>>(t.par[p][2 * nl + 8], 3 * (kWidth / 2), t.ws.wmax + wslot(p, 16));
-    absmax_kernel<<<1, 128, 0, t.st>>>(t.par[p][2 * nl + 2], kWidth, t.ws.wmax + wslot(p, 17));
+    absmax_kernel<<<1, 128, 0, t.st>>>(t.par[p][2 * nl + 8], 3 * (t.net[p].W / 2), t.ws.wmax + wslot(p, 16));
+    absmax_kernel<<<1, 128, 0, t.st>>>(t.par[p][2 * nl + 2], t.net[p].W, t.ws.wmax + wslot(p, 17));
   }
-  if (t.c.smpl) absmax_kernel<<<1, 128, 0, t.st>>>(t.par[2][2], 3 * kWidth, t.ws.wmax + 40);
+  if (t.c.smpl) absmax_kernel<<<1, 128, 0, t.st>>>(t.par[2][2], 3 * t.c.Ww, t.ws.wmax + 40);
   LAUNCH_CHECK("absmax_kernel");
   return NRF_OK;
 }
@@ -291,13 +299,13 @@ static int forward_pass(TrainCtx& t, int p) {
     const int Pw = t.wd->positions_dim, Aw = t.wd->pose_dim;
     TRY(encode(t, pts, w.S, t.wd->in_freqs, t.wd->in_identity, w.wpe));
     const float* bias = t.par[2][1];
-    if (Aw > 0) { TRY(ray_bias(t, t.par[2][0], Pw + Aw, Pw, Aw, t.par[2][1], t.ws.pose_feat, kWidth, w.rbw)); bias = w.rbw; }
+    if (Aw > 0) { TRY(ray_bias(t, t.par[2][0], Pw + Aw, Pw, Aw, t.par[2][1], t.ws.pose_feat, c.Ww, w.rbw)); bias = w.rbw; }
     TileGemmArgs g{};
-    g.a[0] = w.wpe; g.b[0] = t.ws.warp_w; g.n_src = 1; g.N = kWidth; g.passes = c.passes; g.epi = GEPI_PLANES; g.relu = 1;
-    g.bias = bias; g.bias_ld = Aw > 0 ? kWidth : 0; g.rows_per_ray = w.n; g.out = w.warph; g.out_f32 = w.warph_f32; g.out_f32_ld = kWidth;
+    g.a[0] = w.wpe; g.b[0] = t.ws.warp_w; g.n_src = 1; g.N = c.Ww; g.passes = c.passes; g.epi = GEPI_PLANES; g.relu = 1;
+    g.bias = bias; g.bias_ld = Aw > 0 ? c.Ww : 0; g.rows_per_ray = w.n; g.out = w.warph; g.out_f32 = w.warph_f32; g.out_f32_ld = c.Ww;
     g.status = t.io.status;
     TRY(launch_tile_gemm(g, t.n_sms, t.st));
-    TRY(heads(t, w.warph_f32, w.S, kWidth, t.par[2][2], t.par[2][3], 3, w.warp_raw, 3, 0));
+    TRY(heads(t, w.warph_f32, w.S, c.Ww, t.par[2][2], t.par[2][3], 3, w.warp_raw, 3, 0));
     smpl_points_kernel<<<grid1(w.S, 256), 256, 0, t.st>>>(pts, w.warp_raw, t.io.ray_origin, w.S, w.n, w.warped, w.u, w.dnorm,
                                                            last ? t.io.warp_out : nullptr, last ? t.io.warped_out : nullptr);
     LAUNCH_CHECK("smpl_points_kernel");
@@ -321,14 +329,14 @@ static int forward_pass(TrainCtx& t, int p) {
     if (L.aux) { g.a[ns] = L.aux == 1 ? w.encx : w.encd; g.b[ns] = t.ws.w[p].aux[l]; ++ns; }
     g.n_src = ns; g.N = L.n_out; g.passes = c.passes; g.epi = GEPI_PLANES; g.relu = L.relu;
     g.bias = bias; g.bias_ld = L.ray_src ? L.n_out : 0; g.rows_per_ray = w.n; g.out = w.act[l];
-    if (L.role == ROLE_LINEAR) { g.out_f32 = w.a_f32; g.out_f32_ld = kWidth; }
-    if (L.role == ROLE_RGB) { g.out_f32 = w.h2_f32; g.out_f32_ld = kWidth / 2; }
+    if (L.role == ROLE_LINEAR) { g.out_f32 = w.a_f32; g.out_f32_ld = net.W; }
+    if (L.role == ROLE_RGB) { g.out_f32 = w.h2_f32; g.out_f32_ld = net.W / 2; }
     g.status = t.io.status;
     TRY(launch_tile_gemm(g, t.n_sms, t.st));
   }
   const int nl = net.nl;
-  TRY(heads(t, w.h2_f32, w.S, kWidth / 2, t.par[p][2 * nl + 8], t.par[p][2 * nl + 9], 3, w.raw, 4, 0));
-  TRY(heads(t, w.a_f32, w.S, kWidth, t.par[p][2 * nl + 2], t.par[p][2 * nl + 3], 1, w.raw, 4, 3));
+  TRY(heads(t, w.h2_f32, w.S, net.W / 2, t.par[p][2 * nl + 8], t.par[p][2 * nl + 9], 3, w.raw, 4, 0));
+  TRY(heads(t, w.a_f32, w.S, net.W, t.par[p][2 * nl + 2], t.par[p][2 * nl + 3], 1, w.raw, 4, 3));
   // ---- compositing: the SMPL coarse pass scales its deltas by |warped - o| per sample, every other pass by |ray_direction|
   const bool per_sample = c.smpl && p == 0;
   const float* dn = per_sample ? w.dnorm : t.ws.ray_norm;
@@ -382,10 +390,18 @@ static int forward_all(TrainCtx& t) {
 struct Grads { float* const* g[3]; };
 
 static int dw_into(TrainCtx& t, const Planes& dy, const float* sc, int M, const Planes& x, int n0, int N, int cols, float* dst, int ld, int col0) {
-  int split = 0;
-  TRY(launch_dw_gemm(dy, 0, M, x, n0, N, t.c.passes, t.ws.partial, 148, &split, t.n_sms, t.st));
-  dw_reduce_kernel<<<grid1(static_cast<int64_t>(M) * cols, 256), 256, 0, t.st>>>(t.ws.partial, split, M, N, cols, sc, dst, ld, col0);
-  LAUNCH_CHECK("dw_reduce_kernel");
+  // dW[M, cols] += dY^T X[:, n0 : n0 + N], in blocks of at most 256 X columns (one TMEM accumulator); M < 128 (the 64-wide layers of
+  // a width-128 net) runs as one 128-row tile whose upper half multiplies zero-filled (out-of-bounds) dY columns and is dropped
+  const int Mp = (M + 127) & ~127;
+  for (int nb = 0; nb < N; nb += 256) {
+    const int Nb = N - nb < 256 ? N - nb : 256;
+    const int cb = cols - nb < Nb ? cols - nb : Nb;
+    if (cb <= 0) break;
+    int split = 0;
+    TRY(launch_dw_gemm(dy, 0, Mp, x, n0 + nb, Nb, t.c.passes, t.ws.partial, 148, &split, t.n_sms, t.st));
+    dw_reduce_kernel<<<grid1(static_cast<int64_t>(M) * cb, 256), 256, 0, t.st>>>(t.ws.partial, split, Mp, M, Nb, cb, sc, dst, ld, col0 + nb);
+    LAUNCH_CHECK("dw_reduce_kernel");
+  }
   return NRF_OK;
 }
 
@@ -406,7 +422,7 @@ static int rayfeat_dw(TrainCtx& t, const float* sc, const float* feat, int n_out
 static int head_bwd(TrainCtx& t, const float* x, int64_t S, int K, const float* g, int g_ld, int c0, int nh, const float* W, const float* sc_out,
                     int relu_mask, float* dW, float* db, const Planes* dy, unsigned int* l1max) {
   const int rows = 128;
-  head_bwd_kernel<<<static_cast<unsigned>((S + rows - 1) / rows), 256, 0, t.st>>>(x, S, K, g, g_ld, c0, nh, W, sc_out, relu_mask, dW, db,
+  head_bwd_kernel<<<static_cast<unsigned>((S + rows - 1) / rows), K < 32 ? 32 : K, 0, t.st>>>(x, S, K, g, g_ld, c0, nh, W, sc_out, relu_mask, dW, db,
                                                                                   dy ? dy->hi : nullptr, dy ? dy->lo : nullptr, dy ? dy->ld : 0, rows, l1max);
   LAUNCH_CHECK("head_bwd_kernel");
   return NRF_OK;
@@ -432,11 +448,11 @@ static int backward_pass(TrainCtx& t, int p, const Grads& G) {
   auto SC = [&](int k) { return t.ws.sc + 2 * k; };
   auto MX = [&](int k) { return t.ws.mx + k; };
   // ---- rgb head -> dY of the last (ReLU) layer: |dY| <= 3 max|d raw| max|W_rgb|
-  Planes dy = view(t.ws.dy[cur], kWidth / 2, w.S);
+  Planes dy = view(t.ws.dy[cur], net.W / 2, w.S);
   TRY(next_scale(t, MX(0), 3.f, t.ws.wmax + wslot(p, 16), nullptr, nullptr, SC(slot)));
-  TRY(head_bwd(t, w.h2_f32, w.S, kWidth / 2, w.g_raw, 4, 0, 3, t.par[p][2 * nl + 8], SC(slot), 1, g[2 * nl + 8], g[2 * nl + 9], &dy, MX(slot)));
+  TRY(head_bwd(t, w.h2_f32, w.S, net.W / 2, w.g_raw, 4, 0, 3, t.par[p][2 * nl + 8], SC(slot), 1, g[2 * nl + 8], g[2 * nl + 9], &dy, MX(slot)));
   // ---- sigma head (its contribution to d(additional_linear_layer output) is the rank-1 term of the dir layer's dX epilogue)
-  TRY(head_bwd(t, w.a_f32, w.S, kWidth, w.g_raw, 4, 3, 1, t.par[p][2 * nl + 2], nullptr, 0, g[2 * nl + 2], g[2 * nl + 3], nullptr, nullptr));
+  TRY(head_bwd(t, w.a_f32, w.S, net.W, w.g_raw, 4, 3, 1, t.par[p][2 * nl + 2], nullptr, 0, g[2 * nl + 2], g[2 * nl + 3], nullptr, nullptr));
   bool encx_written = false;
   for (int l = net.n - 1; l >= 0; --l) {
     const TLayer& L = net.L[l];
@@ -482,13 +498,13 @@ static int backward_pass(TrainCtx& t, int p, const Grads& G) {
                                                                w.warped, w.u, w.dnorm, p == 0 ? w.g_dnorm : nullptr, w.S, t.ws.g_warp, MX(slot));
     LAUNCH_CHECK("smpl_points_bwd_kernel");
     float* const* gw = G.g[2];
-    Planes dyw = view(t.ws.dy[0], kWidth, w.S);
+    Planes dyw = view(t.ws.dy[0], c.Ww, w.S);
     TRY(next_scale(t, MX(slot), 3.f, t.ws.wmax + 40, nullptr, nullptr, SC(slot)));
-    TRY(head_bwd(t, w.warph_f32, w.S, kWidth, t.ws.g_warp, 3, 0, 3, t.par[2][2], SC(slot), 1, gw[2], gw[3], &dyw, nullptr));
+    TRY(head_bwd(t, w.warph_f32, w.S, c.Ww, t.ws.g_warp, 3, 0, 3, t.par[2][2], SC(slot), 1, gw[2], gw[3], &dyw, nullptr));
     const int Pw = t.wd->positions_dim, Aw = t.wd->pose_dim;
-    TRY(dw_into(t, dyw, SC(slot), kWidth, w.wpe, 0, 64, Pw, gw[0], Pw + Aw, 0));
-    TRY(colsum_and_bias(t, dyw, SC(slot), kWidth, w.n, gw[1]));
-    if (Aw > 0) TRY(rayfeat_dw(t, SC(slot), t.ws.pose_feat, kWidth, Aw, gw[0], Pw + Aw, Pw));
+    TRY(dw_into(t, dyw, SC(slot), c.Ww, w.wpe, 0, 64, Pw, gw[0], Pw + Aw, 0));
+    TRY(colsum_and_bias(t, dyw, SC(slot), c.Ww, w.n, gw[1]));
+    if (Aw > 0) TRY(rayfeat_dw(t, SC(slot), t.ws.pose_feat, c.Ww, Aw, gw[0], Pw + Aw, Pw));
   }
   return NRF_OK;
 }
@@ -656,7 +672,7 @@ extern "C" int nrf_gemm_dw(const void* a_hi, const void* a_lo, int32_t M, const 
   const float one[2] = {1.f, 1.f};
   cudaError_t e = cudaMemcpyAsync(scale2, one, sizeof(one), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(scale)");
-  dw_reduce_kernel<<<grid1(static_cast<int64_t>(M) * N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, split, M, N, N, scale2, out, N, 0);
+  dw_reduce_kernel<<<grid1(static_cast<int64_t>(M) * N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, split, M, M, N, N, scale2, out, N, 0);
   LAUNCH_CHECK("dw_reduce_kernel");
   return NRF_OK;
 }

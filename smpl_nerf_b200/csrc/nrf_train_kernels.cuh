@@ -375,14 +375,14 @@ __global__ void rayfeat_dw_kernel(const float* __restrict__ dysum, const float* 
   }
   if (k < K && n < n_out) dW[static_cast<size_t>(n) * ld + col0 + k] += acc * __ldg(scale2 + 1);
 }
-// dst[m, col0 + c] += inv_scale * sum_split partial[split][m][c]        (c < cols; the partials are N wide)
-__global__ void dw_reduce_kernel(const float* __restrict__ partial, int n_split, int M, int N, int cols, const float* __restrict__ scale2,
+// dst[m, col0 + c] += inv_scale * sum_split partial[split][m][c]        (m < M <= Mp rows of the partials, c < cols <= N)
+__global__ void dw_reduce_kernel(const float* __restrict__ partial, int n_split, int Mp, int M, int N, int cols, const float* __restrict__ scale2,
                                  float* __restrict__ dst, int ld, int col0) {
   const int total = M * cols;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int m = idx / cols, c = idx - m * cols;
     float acc = 0.f;
-    for (int s = 0; s < n_split; ++s) acc += partial[(static_cast<size_t>(s) * M + m) * N + c];
+    for (int s = 0; s < n_split; ++s) acc += partial[(static_cast<size_t>(s) * Mp + m) * N + c];
     dst[static_cast<size_t>(m) * ld + col0 + c] += acc * __ldg(scale2 + 1);
   }
 }

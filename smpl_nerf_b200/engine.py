@@ -175,8 +175,14 @@ def render(kind: str, model_coarse, model_fine, model_warp, args, pos_enc, dir_e
     # autograd is recording and a net is trainable: the differentiable layer-by-layer path (train.py) instead of the fused kernel
     from . import train as _train
     train_mode = _train.needs_grad(model_coarse, model_fine if run_fine else None, model_warp if smpl else None)
+    # hidden widths other than 256 (config_parser.py:20,24,30 make netwidth a flag): the fused kernel is built for 256, the
+    # layer-by-layer path (one tcgen05 GEMM per nn.Linear) takes 128 / 256 / 512 -- used for inference too in that case
+    widths = [int(model_coarse.width)] + ([int(model_fine.width)] if run_fine else []) + \
+        ([int(model_warp.linear1.out_features)] if smpl else [])
+    if any(wd != 256 for wd in widths):
+        train_mode = True
     if train_mode and (taps or trace_cap > 0):
-        raise ValueError('debug taps / trace are inference-only: call under torch.no_grad()')
+        raise ValueError('debug taps / trace exist in the fused inference kernel only (width-256 nets under torch.no_grad() or .eval())')
 
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
