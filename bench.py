@@ -15,8 +15,8 @@ Printed JSON line (rank 0):
   roofline   algorithmic MLP FLOPs (2 x MACs of the reference's nn.Linear layers, un-folded,
              un-hoisted) per launch / average kernel duration, against the measured bf16 peak
   cpu_baseline  the oracle port of the reference's PyTorch-CPU path on this box's host cores (~10 s sample)
-  psnr       held-out view of the briefly trained checkpoint (tests/golden/trained_nerf_d4.ckpt): engine vs ground
-             truth, the reference's own render vs ground truth, engine vs reference render
+  psnr       two 64x64 views of the briefly trained SmplNerfPipeline checkpoint (tests/golden/trained_smpl_d8.ckpt): engine vs
+             ground truth, the reference's own render vs ground truth, engine vs reference render
 `--impl reference` times that CPU path alone (rank 0 only), on bounded samples of the same workload.
 Other workloads (--workload): cfg1 = configs[0], cfg3 = configs[2] (256x256, 10 poses), cfg4 = configs[3] (AppendToNerf),
 cfg5 = configs[4] (ONE 512x512 frame sharded over the ranks: strong scaling), nerf, paper (AppendSmplParams).
@@ -196,33 +196,40 @@ def cpu_reference_rays_per_s(w, state, n_batches, batch, warmup=1, seed=0, devic
 
 
 def heldout_psnr(dev, precision):
-    """PSNR half of the BASELINE metric: the briefly trained vanilla-NeRF checkpoint of tests/golden/ (trained and
-    rendered with the REFERENCE classes by tests/golden/make_trained.py) re-rendered by the engine on its held-out
-    32x32 view -- against the analytic ground truth and against the reference's stored render."""
+    """PSNR half of the BASELINE metric on the HEADLINE pipeline: the briefly trained SmplNerfPipeline (8 x 256 coarse + fine + warp
+    net, full fp32 weights; trained and rendered with the REFERENCE classes by tests/golden/make_trained_smpl.py) re-rendered by the
+    engine on its two stored 64 x 64 evaluation views -- against the analytic ground truth and against the reference's renders."""
     import math
     from types import SimpleNamespace
-    from smpl_nerf_b200.models import NerfPipeline, RenderRayNet
+    from smpl_nerf_b200 import scene
+    from smpl_nerf_b200.models import RenderRayNet, SmplNerfPipeline, WarpFieldNet
     from smpl_nerf_b200.ops import PositionalEncoder
-    path = os.path.join(ROOT, 'tests', 'golden', 'trained_nerf_d4.ckpt')
+    path = os.path.join(ROOT, 'tests', 'golden', 'trained_smpl_d8.ckpt')
     if not os.path.isfile(path):
         return None
     ck = torch.load(path, weights_only=False)
-    pe, de = PositionalEncoder(10, False), PositionalEncoder(4, False)
-    nets = []
-    for key in ('coarse', 'fine'):
-        net = RenderRayNet(ck['n_layers'], 256, 3 * pe.output_dim, 3 * de.output_dim, 0, list(ck['skips']))
-        net.load_state_dict({k: v.float() for k, v in ck[key].items()})
-        nets.append(net.to(dev))
+    pe, de, he = PositionalEncoder(10, False), PositionalEncoder(4, False), PositionalEncoder(10, False)
+    c = RenderRayNet(8, 256, 3 * pe.output_dim, 3 * de.output_dim, 0, [4])
+    f = RenderRayNet(8, 256, 3 * pe.output_dim, 3 * de.output_dim, 0, [4])
+    w = WarpFieldNet(8, 256, 3 * pe.output_dim, 2 * he.output_dim)
+    c.load_state_dict(ck['coarse']); f.load_state_dict(ck['fine']); w.load_state_dict(ck['warp'])
+    nets = [m.to(dev).eval() for m in (c, f, w)]
     args = SimpleNamespace(default_device=None, sigma_noise_std=0., white_background=1, run_fine=1,
                            number_fine_samples=ck['n_fine'], human_pose_encoding=1)
-    from smpl_nerf_b200 import engine
-    data = [t.to(dev) for t in ck['data']]
-    with torch.no_grad():
-        img = engine.render('nerf', nets[0], nets[1], None, args, pe, de, None, data, precision=precision)['rgb_fine'].double().cpu()
+    pipe = SmplNerfPipeline(nets[0], nets[1], nets[2], args, pe, de, he)
+    pipe.precision = precision
     db = lambda a, b: -10.0 * math.log10(max(float(torch.mean((a - b.double()) ** 2)), 1e-30))
-    return {'engine_vs_gt_db': db(img, ck['data'][-1]), 'reference_vs_gt_db': float(ck['reference_psnr']),
-            'engine_vs_reference_render_db': db(img, ck['reference_rgb_fine']),
-            'view': 'held-out 32x32 view, vanilla NeRF depth 4 (32+64 samples) trained for 1200 steps with the reference classes'}
+    res = {'pipeline': 'smpl_nerf_pipeline 8x256 + warp net, 64 coarse + 128 fine, 64x64 views; trained for %d steps with the reference classes'
+                       % ck['steps']}
+    for name, v in ck['views'].items():
+        data = scene.data_list(scene.make_rays(**v['args']), 'smpl')
+        with torch.no_grad():
+            img = pipe([t.to(dev) for t in data])[1].double().cpu()
+        res[name] = {'engine_vs_gt_db': db(img, data[-1]), 'reference_vs_gt_db': float(v['reference_psnr']),
+                     'engine_vs_reference_render_db': db(img, v['reference_rgb_fine']), 'all_white_image_db': float(v['white_psnr'])}
+    res['views'] = ("'seen' = a training camera and arm pose with fresh sampling jitter; 'heldout' = unseen camera and arm angle (700 steps on "
+                    "10 views do not interpolate cameras 36 degrees apart: below the all-white score for the reference and the engine alike)")
+    return res
 
 
 def cpu_model():

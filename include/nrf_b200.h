@@ -247,14 +247,17 @@ int nrf_train_backward(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse,
 /* Kernels launched by the training entry points on this thread since the last reset (bench.py's gpu_launches accounting). */
 long long nrf_train_launch_count(int reset);
 /* Building blocks of the training path, exported for stage-wise tests.  "planes" = a matrix as two fp16 tensors hi, lo
- * (x ~= hi + lo), row-major [rows, ld]; lo may be NULL with passes = 1.
+ * (x ~= hi + lo), row-major [rows, ld]; lo may be NULL with passes = 1.  With a third plane ll (non-NULL) the three planes hold
+ * BFLOAT16 bit patterns and x = hi + lo + ll exactly (the exact mode, passes = 6).
  * nrf_split_planes: fp32 [rows, cols] (row pitch ld) -> planes [rows, cols_pad] (row pitch ld_dst), zero padded.
  * nrf_gemm_planes:  b_mn = 0: C[S,N] = A[S,K] B[N,K]^T (the forward of nn.Linear);  b_mn = 1: C[S,N] = A[S,K] B[K,N] (dX = dY W).
  *                   out_hi != NULL: C = [relu](acc + bias) as planes (+ fp32 copy in out_f32 if given); else fp32 C in out_f32.
  * nrf_gemm_dw:      out[M,N] += A[S,M]^T B[S,N] (dW = dY^T X), split over the SMs; partial: >= (max_split * M * N + 2) floats. */
-int nrf_split_planes(const float* src, int64_t rows, int32_t cols, int32_t ld, void* hi, void* lo, int32_t ld_dst, int32_t cols_pad, void* stream);
-int nrf_gemm_planes(int32_t b_mn, const void* a_hi, const void* a_lo, int64_t S, int32_t K, const void* b_hi, const void* b_lo, int32_t N,
-                    int32_t passes, const float* bias, int32_t relu, float* out_f32, void* out_hi, void* out_lo, void* stream);
+int nrf_split_planes(const float* src, int64_t rows, int32_t cols, int32_t ld, void* hi, void* lo, void* ll, int32_t ld_dst, int32_t cols_pad,
+                     void* stream);
+int nrf_gemm_planes(int32_t b_mn, const void* a_hi, const void* a_lo, const void* a_ll, int64_t S, int32_t K, const void* b_hi, const void* b_lo,
+                    const void* b_ll, int32_t N, int32_t passes, const float* bias, int32_t relu, float* out_f32, void* out_hi, void* out_lo,
+                    void* out_ll, void* stream);
 int nrf_gemm_dw(const void* a_hi, const void* a_lo, int32_t M, const void* b_hi, const void* b_lo, int32_t N, int64_t S, int32_t passes,
                 float* partial, int32_t max_split, float* out, void* stream);
 

@@ -154,9 +154,9 @@ def lib() -> C.CDLL:
     L.nrf_train_backward.argtypes = _net_args + [C.c_void_p, C.c_void_p, PP, PP, PP, C.c_int, C.c_void_p]
     L.nrf_train_launch_count.restype = C.c_longlong
     L.nrf_train_launch_count.argtypes = [C.c_int]
-    L.nrf_split_planes.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
-    L.nrf_gemm_planes.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
-                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nrf_split_planes.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.nrf_gemm_planes.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nrf_gemm_dw.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
                               C.c_void_p, C.c_void_p]
     if L.nrf_abi_version() != ABI_VERSION:

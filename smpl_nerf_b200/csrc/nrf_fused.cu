@@ -779,6 +779,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nrf_fus
   tc_fence_before_sync();
   __syncthreads();
   if (threadIdx.x == 0 && P.io.trace && blockIdx.x == 0) P.io.trace[1] = *reinterpret_cast<uint32_t*>(smem_raw + P.off_misc + kTraceCtrOfs);
+  if (threadIdx.x == 0 && blockIdx.x == 0 && P.io.status) {      // a weight that left the fp16 range at pack time is as fatal as an activation that does
+    int bad = 0;
+    if (P.blob[0]) bad |= *(reinterpret_cast<const int32_t*>(P.blob[0] + P.net[0].f32_ofs) + P.net[0].flag_ofs);
+    if (P.blob[1]) bad |= *(reinterpret_cast<const int32_t*>(P.blob[1] + P.net[1].f32_ofs) + P.net[1].flag_ofs);
+    if (P.blob[2]) bad |= *(reinterpret_cast<const int32_t*>(P.blob[2] + P.warp.f32_ofs) + P.warp.flag_ofs);
+    if (bad) atomicOr(P.io.status, 1);
+  }
   cluster_sync_all();          // neither CTA may exit (or free TMEM) while its peer can still address it
   if (warp == 1) tmem_dealloc2<512>(tmem_base);
 }

@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda_bf16.h>
+
 #include "nrf_gemm.cuh"
 #include "nrf_plan.h"
 #include "nrf_ptx.cuh"
@@ -46,7 +48,7 @@ struct GemmBars { uint64_t b_full, a_full[4], a_empty[4], acc_full[2], acc_empty
 __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid_constant__ TileGemmParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t planes = P.passes == 3 ? 2u : 1u;
+  const uint32_t planes = P.passes == 6 ? 3u : (P.passes == 3 ? 2u : 1u);
   const int nk = P.kc[0] + (P.n_src > 1 ? P.kc[1] : 0);
   const uint32_t b_chunk = static_cast<uint32_t>(P.n_tile) * 128u;
   const uint32_t b_bytes = P.b_stream ? 0u : static_cast<uint32_t>(nk) * planes * b_chunk;
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bars->acc_full[b]), 1); mbar_init(smem_u32(&bars->acc_empty[b]), 8); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<256>(smem_u32(&bars->tmem));
+  if (warp == 1) tmem_alloc<512>(smem_u32(&bars->tmem));      // exact mode: 2 buffers x (main, correction) x n_tile columns
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
     if (lane == 0) {
       auto load_b = [&](int j, int lc, uint32_t dst0, uint32_t bar) {
         for (uint32_t p = 0; p < planes; ++p) {
-          const CUtensorMap* map = p ? &P.b_lo[j] : &P.b_hi[j];
+          const CUtensorMap* map = &P.b_map[j][p];
           const uint32_t dst = dst0 + p * b_chunk;
           if (!P.b_mn) tma_load_2d(dst, map, 64 * lc, n0, bar);
           else for (int g = 0; g < P.n_tile / 64; ++g) tma_load_2d(dst + g * 8192u, map, n0 + 64 * g, 64 * lc, bar);
@@ -93,42 +95,58 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             mbar_wait(smem_u32(&bars->a_empty[stage]), phase ^ 1);
             mbar_arrive_expect_tx(smem_u32(&bars->a_full[stage]), a_stage);
             const uint32_t dst = smem_a + stage * a_stage;
-            tma_load_2d(dst, &P.a_hi[j], 64 * lc, static_cast<int32_t>(mt * 128), smem_u32(&bars->a_full[stage]));
-            if (planes == 2) tma_load_2d(dst + kATile, &P.a_lo[j], 64 * lc, static_cast<int32_t>(mt * 128), smem_u32(&bars->a_full[stage]));
+            for (uint32_t p = 0; p < planes; ++p)
+              tma_load_2d(dst + p * kATile, &P.a_map[j][p], 64 * lc, static_cast<int32_t>(mt * 128), smem_u32(&bars->a_full[stage]));
             if (P.b_stream) load_b(j, lc, dst + planes * kATile, smem_u32(&bars->a_full[stage]));
             if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
           }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_f16_major(128, static_cast<uint32_t>(P.n_tile), 0u, P.b_mn ? 1u : 0u);
+    const uint32_t idesc = umma_idesc_f16_major(128, static_cast<uint32_t>(P.n_tile), 0u, P.b_mn ? 1u : 0u) | (P.bf16 ? ((1u << 7) | (1u << 10)) : 0u);
     if (!P.b_stream) mbar_wait(smem_u32(&bars->b_full), 0);
     tc_fence_after_sync();
-    uint32_t stage = 0, phase = 0, it = 0;
-    for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x, ++it) {
-      const uint32_t buf = it & 1u;
-      mbar_wait(smem_u32(&bars->acc_empty[buf]), ((it >> 1) & 1u) ^ 1u);
-      tc_fence_after_sync();
-      const uint32_t acc = tmem + buf * static_cast<uint32_t>(P.n_tile);
-      uint32_t accumulate = 0;
+    uint32_t stage = 0, phase = 0, it = 0;      // it: accumulator hand-offs so far (one per tile; one per K-chunk in the exact mode)
+    for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x) {
+      uint32_t buf = it & 1u, acc = 0, accumulate = 0;
+      if (!P.bf16) {
+        mbar_wait(smem_u32(&bars->acc_empty[buf]), ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after_sync();
+        acc = tmem + buf * static_cast<uint32_t>(P.n_tile);
+      }
       for (int c = 0; c < nk; ++c) {
+        if (P.bf16) {
+          // exact mode: the tensor core ROUNDS TOWARD ZERO when it adds into an fp32 accumulator (measured: ~2^-24.5 relative per
+          // accumulating instruction, tests/test_gpu_train.py::test_gemm_exact_mode), so long chains drift.  Every K-chunk gets
+          // fresh accumulators -- `main` for the 4 hi*hi instructions, `corr` for the 20 small correction products -- and the
+          // epilogue warps add the chunks up in registers with round-to-nearest fp32 adds.
+          buf = it & 1u;
+          mbar_wait(smem_u32(&bars->acc_empty[buf]), ((it >> 1) & 1u) ^ 1u);
+          tc_fence_after_sync();
+          acc = tmem + buf * 2u * static_cast<uint32_t>(P.n_tile);
+        }
         mbar_wait(smem_u32(&bars->a_full[stage]), phase);
         tc_fence_after_sync();
-        const uint32_t a_hi = smem_a + stage * a_stage, a_lo = a_hi + kATile;
-        const uint32_t b_hi = P.b_stream ? a_hi + planes * kATile : smem_b + static_cast<uint32_t>(c) * planes * b_chunk, b_lo = b_hi + b_chunk;
+        const uint32_t a_hi = smem_a + stage * a_stage;
+        const uint32_t b_hi = P.b_stream ? a_hi + planes * kATile : smem_b + static_cast<uint32_t>(c) * planes * b_chunk;
         for (uint32_t pass = 0; pass < static_cast<uint32_t>(P.passes); ++pass) {
-          const uint32_t a = pass == 1 ? a_lo : a_hi, b = pass == 2 ? b_lo : b_hi;      // hi*hi, lo*hi, hi*lo
+          // (A plane, B plane): hi*hi, lo*hi, hi*lo [, ll*hi, lo*lo, hi*ll]: every product of combined order <= planes - 1
+          const uint32_t pa = (0x012010u >> (4 * pass)) & 0xFu, pb = (0x210100u >> (4 * pass)) & 0xFu;
+          const uint32_t a = a_hi + pa * kATile, b = b_hi + pb * b_chunk;
           const uint64_t ad = umma_desc_sw128(a);
+          const uint32_t dst = (P.bf16 && pass > 0) ? acc + static_cast<uint32_t>(P.n_tile) : acc;
+          if (P.bf16 && pass <= 1) accumulate = 0;       // first instruction into main (pass 0) / corr (pass 1)
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks) {
             const uint64_t bd = P.b_mn ? umma_desc_mn_sw128(b + ks * 2048u, 8192u, 1024u) : umma_desc_sw128(b) + 2u * ks;
-            umma_f16_ss_warp(acc, ad + 2u * ks, bd, idesc, accumulate);
+            umma_f16_ss_warp(dst, ad + 2u * ks, bd, idesc, accumulate);
             accumulate = 1;
           }
         }
         umma_commit_warp(smem_u32(&bars->a_empty[stage]));
         if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
+        if (P.bf16) { umma_commit_warp(smem_u32(&bars->acc_full[buf])); ++it; }
       }
-      umma_commit_warp(smem_u32(&bars->acc_full[buf]));
+      if (!P.bf16) { umma_commit_warp(smem_u32(&bars->acc_full[buf])); ++it; }
     }
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -139,20 +157,53 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
     float l1_run = 0.f;
     bool saturated = false;
     uint32_t it = 0;
-    for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x, ++it) {
-      const uint32_t buf = it & 1u;
+    for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x) {
+      uint32_t buf = it & 1u;
       const int64_t row = mt * 128 + 32 * q + lane;
       const bool row_ok = row < P.S;
       const float* bias_row = P.bias ? P.bias + (P.bias_ld ? (row_ok ? row / P.rows_per_ray : 0) * P.bias_ld : 0) : nullptr;
       const float rs = (P.row_scale && row_ok) ? P.row_scale[row * P.row_scale_ld] * s_out : 0.f;
       float l1 = 0.f;
-      mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
-      tc_fence_after_sync();
+      float sum[64];            // exact mode: this thread's cols_w (<= 64) columns, K-chunks added with round-to-nearest
+      if (P.bf16) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) sum[i] = 0.f;
+        for (int c = 0; c < nk; ++c, ++it) {
+          buf = it & 1u;
+          mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
+          tc_fence_after_sync();
+          const uint32_t ta = tmem + buf * 2u * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(half * cols_w);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < cols_w / 16) {
+              uint32_t vm[16], vc[16];
+              tmem_ld16(ta + 16u * g, vm);
+              tmem_ld16(ta + static_cast<uint32_t>(P.n_tile) + 16u * g, vc);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sum[16 * g + i] = __fadd_rn(sum[16 * g + i], __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
+            }
+          }
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
+        }
+      } else {
+        mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
+        tc_fence_after_sync();
+      }
       const uint32_t taddr = tmem + buf * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(half * cols_w);
-      for (int g = 0; g < cols_w / 16; ++g) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g >= cols_w / 16) continue;
         uint32_t v[16];
-        tmem_ld16(taddr + 16u * g, v);
-        tmem_ld_wait();
+        if (!P.bf16) {
+          tmem_ld16(taddr + 16u * g, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(sum[16 * g + i]);
+        }
         if (!row_ok) continue;
         const int col = n0 + half * cols_w + 16 * g;
         float x[16];
@@ -200,19 +251,36 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             op[i] = o;
           }
         } else {
-          uint32_t h[8], l[8];
+          uint32_t h[8], l[8], ll[8];
+          if (P.bf16) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            saturated |= fabsf(x[2 * i]) > 65504.f || fabsf(x[2 * i + 1]) > 65504.f;
-            h[i] = cvt_f16x2_satfinite(x[2 * i], x[2 * i + 1]);
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
-            l[i] = cvt_f16x2_satfinite(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+            for (int i = 0; i < 8; ++i) {      // x = hi + lo + ll exactly (3 x 8 significant bits), fp32 exponent range
+              float r0 = x[2 * i], r1 = x[2 * i + 1];
+              const __nv_bfloat162 b0 = __floats2bfloat162_rn(r0, r1);
+              r0 -= __low2float(b0); r1 -= __high2float(b0);
+              const __nv_bfloat162 b1 = __floats2bfloat162_rn(r0, r1);
+              r0 -= __low2float(b1); r1 -= __high2float(b1);
+              const __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
+              h[i] = *reinterpret_cast<const uint32_t*>(&b0); l[i] = *reinterpret_cast<const uint32_t*>(&b1); ll[i] = *reinterpret_cast<const uint32_t*>(&b2);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              saturated |= fabsf(x[2 * i]) > 65504.f || fabsf(x[2 * i + 1]) > 65504.f;
+              h[i] = cvt_f16x2_satfinite(x[2 * i], x[2 * i + 1]);
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+              l[i] = cvt_f16x2_satfinite(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+            }
           }
           uint4* ph = reinterpret_cast<uint4*>(P.out_hi + row * P.out_ld + col);
           ph[0] = make_uint4(h[0], h[1], h[2], h[3]); ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
           if (P.out_lo) {
             uint4* pl = reinterpret_cast<uint4*>(P.out_lo + row * P.out_ld + col);
             pl[0] = make_uint4(l[0], l[1], l[2], l[3]); pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+          }
+          if (P.bf16 && P.out_ll) {
+            uint4* pq = reinterpret_cast<uint4*>(P.out_ll + row * P.out_ld + col);
+            pq[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]); pq[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
           }
           if (P.out_f32) {
             float4* op = reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col);
@@ -222,9 +290,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
         }
       }
       l1_run = fmaxf(l1_run, l1);
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
+      if (!P.bf16) {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
+        ++it;
+      }
     }
     if (P.l1max) {
       l1_run *= (P.epi == GEPI_F32 ? 1.f : inv_out) * static_cast<float>(gridDim.y * 2);     // real units; 2 column segments per slice
@@ -236,7 +307,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem);
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------ dW GEMM (split-K over samples)
@@ -360,7 +431,9 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
   static thread_local TileGemmParams P;
   memset(&P, 0, sizeof(P));
   if (a.n_src < 1 || a.n_src > 2) { set_error("tile_gemm: n_src %d", a.n_src); return NRF_E_INVALID; }
-  if (a.passes != 1 && a.passes != 3) { set_error("tile_gemm: passes must be 1 or 3"); return NRF_E_INVALID; }
+  if (a.passes != 1 && a.passes != 3 && a.passes != 6) { set_error("tile_gemm: passes must be 1, 3 or 6"); return NRF_E_INVALID; }
+  const int n_planes = a.passes == 6 ? 3 : (a.passes == 3 ? 2 : 1);
+  P.bf16 = a.passes == 6 ? 1 : 0;
   if (a.N < 64 || (a.N & 63)) { set_error("tile_gemm: N = %d must be a multiple of 64", a.N); return NRF_E_INVALID; }
   const int64_t S = a.a[0].rows;
   if (S <= 0) return NRF_OK;
@@ -370,21 +443,21 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
   for (int j = 0; j < a.n_src; ++j) {
     const Planes& A = a.a[j]; const Planes& B = a.b[j];
     if (A.cols < 64 || (A.cols & 63) || A.rows != S) { set_error("tile_gemm: A source %d has %d columns / %lld rows", j, A.cols, (long long)A.rows); return NRF_E_INVALID; }
-    if (a.passes == 3 && (!A.lo || !B.lo)) { set_error("tile_gemm: 3 passes need the lo planes"); return NRF_E_INVALID; }
+    const __half* ap[3] = {A.hi, A.lo, A.ll};
+    const __half* bp[3] = {B.hi, B.lo, B.ll};
+    for (int q = 0; q < n_planes; ++q) if (!ap[q] || !bp[q]) { set_error("tile_gemm: %d passes need %d planes per operand", a.passes, n_planes); return NRF_E_INVALID; }
     P.kc[j] = A.cols / 64; nk += P.kc[j];
-    if ((rc = encode_planes_map(&P.a_hi[j], A.hi, S, A.cols, A.ld, 64, 128)) != NRF_OK) return rc;
-    if (a.passes == 3 && (rc = encode_planes_map(&P.a_lo[j], A.lo, S, A.cols, A.ld, 64, 128)) != NRF_OK) return rc;
     if (!a.b_mn) {      // B[N, K]: rows = output features
       if (B.rows != a.N || B.cols != A.cols) { set_error("tile_gemm: B source %d is [%lld x %d], expected [%d x %d]", j, (long long)B.rows, B.cols, a.N, A.cols); return NRF_E_INVALID; }
-      if ((rc = encode_planes_map(&P.b_hi[j], B.hi, B.rows, B.cols, B.ld, 64, P.n_tile)) != NRF_OK) return rc;
-      if (a.passes == 3 && (rc = encode_planes_map(&P.b_lo[j], B.lo, B.rows, B.cols, B.ld, 64, P.n_tile)) != NRF_OK) return rc;
     } else {            // B[K, N]: rows = reduction index
       if (B.rows != A.cols || B.cols != a.N) { set_error("tile_gemm: B source %d is [%lld x %d], expected [%d x %d]", j, (long long)B.rows, B.cols, A.cols, a.N); return NRF_E_INVALID; }
-      if ((rc = encode_planes_map(&P.b_hi[j], B.hi, B.rows, B.cols, B.ld, 64, 64)) != NRF_OK) return rc;
-      if (a.passes == 3 && (rc = encode_planes_map(&P.b_lo[j], B.lo, B.rows, B.cols, B.ld, 64, 64)) != NRF_OK) return rc;
+    }
+    for (int q = 0; q < n_planes; ++q) {
+      if ((rc = encode_planes_map(&P.a_map[j][q], ap[q], S, A.cols, A.ld, 64, 128)) != NRF_OK) return rc;
+      if ((rc = encode_planes_map(&P.b_map[j][q], bp[q], B.rows, B.cols, B.ld, 64, a.b_mn ? 64 : P.n_tile)) != NRF_OK) return rc;
     }
   }
-  const uint32_t planes = a.passes == 3 ? 2u : 1u;
+  const uint32_t planes = static_cast<uint32_t>(n_planes);
   uint32_t b_bytes = static_cast<uint32_t>(nk) * planes * P.n_tile * 128u, a_stage = planes * kATile;
   if (b_bytes + 2 * a_stage + 256 > kGemmSmemLimit) {      // K too large for a resident weight slice: stream the B chunks with the A chunks
     P.b_stream = 1;
@@ -394,7 +467,7 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
   int stages = static_cast<int>((kGemmSmemLimit - 256 - b_bytes) / a_stage);
   P.n_stages = stages > 4 ? 4 : stages;
   P.epi = a.epi; P.relu = a.relu; P.bias = a.bias; P.bias_ld = a.bias_ld; P.rows_per_ray = a.rows_per_ray > 0 ? a.rows_per_ray : 1;
-  P.out_hi = a.out.hi; P.out_lo = a.out.lo; P.out_ld = a.out.ld; P.out_f32 = a.out_f32; P.out_f32_ld = a.out_f32_ld; P.accumulate = a.accumulate;
+  P.out_hi = a.out.hi; P.out_lo = a.out.lo; P.out_ll = a.out.ll; P.out_ld = a.out.ld; P.out_f32 = a.out_f32; P.out_f32_ld = a.out_f32_ld; P.accumulate = a.accumulate;
   P.mask_hi = a.mask_hi; P.mask_ld = a.mask_ld; P.row_scale = a.row_scale; P.row_scale_ld = a.row_scale_ld; P.col_vec = a.col_vec;
   P.sc_in = a.sc_in; P.sc_out = a.sc_out; P.l1max = a.l1max; P.status = a.status;
   if (a.epi == GEPI_PLANES && !a.out.hi) { set_error("tile_gemm: planes epilogue without an output"); return NRF_E_INVALID; }

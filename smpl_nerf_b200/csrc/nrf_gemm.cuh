@@ -11,7 +11,9 @@
 //   dW        dW[out,in] = dY[S, out]^T . X[S, in]       A = dY M-major,  B = X  N-major     (dw_gemm, K = samples)
 //
 // Operands are staged by 2-D tensor TMA (SWIZZLE_128B boxes of 64 features) straight into the UMMA canonical layouts.
-// passes = 3 runs hi*hi + lo*hi + hi*lo (fp32-equivalent, like the renderer's parity mode); passes = 1 runs hi*hi.
+// passes = 3 runs hi*hi + lo*hi + hi*lo (fp32-equivalent, like the renderer's parity mode); passes = 1 runs hi*hi;
+// passes = 6 (tile_gemm only, bf16 planes hi/lo/ll = 24 significant bits with fp32's exponent range) adds ll*hi + lo*lo + hi*ll:
+// the operands are then EXACT fp32 values and no activation magnitude can leave the representable range.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -26,15 +28,16 @@ enum GemmEpi : int32_t {
 };
 
 struct TileGemmParams {
-  CUtensorMap a_hi[2], a_lo[2];   // A sources: planes [S, 64 * kc[j]], box {64, 128}
-  CUtensorMap b_hi[2], b_lo[2];   // B sources: b_mn = 0: [N, 64 * kc[j]] box {64, n_tile}; b_mn = 1: [64 * kc[j], N] box {64, 64}
+  CUtensorMap a_map[2][3];        // A sources x planes (hi, lo, ll): [S, 64 * kc[j]], box {64, 128}
+  CUtensorMap b_map[2][3];        // B sources x planes: b_mn = 0: [N, 64 * kc[j]] box {64, n_tile}; b_mn = 1: [64 * kc[j], N] box {64, 64}
   int32_t kc[2];
   int32_t n_src, b_mn, n_tile, passes, n_stages;
+  int32_t bf16;                   // 1: the planes hold bfloat16 (exact mode: 3 planes = 24 significant bits, fp32 range), else fp16
   int32_t b_stream;               // 1: K too large for a resident weight slice -- the B chunk travels with every A chunk through the ring
   int64_t S;
   int32_t epi, relu;
   const float* bias; int32_t bias_ld; int32_t rows_per_ray;      // bias[(row / rows_per_ray) * bias_ld + col]  (bias_ld = 0: one vector)
-  __half* out_hi; __half* out_lo; int32_t out_ld;
+  __half* out_hi; __half* out_lo; __half* out_ll; int32_t out_ld;
   float* out_f32; int32_t out_f32_ld; int32_t accumulate;
   const __half* mask_hi; int32_t mask_ld;                         // keep out[row, col] only where mask_hi[row, col] > 0 (ReLU')
   const float* row_scale; int32_t row_scale_ld; const float* col_vec;   // + row_scale[row * ld] * sc_out[0] * col_vec[col]
@@ -58,11 +61,13 @@ struct DwGemmParams {
 // host helpers (nrf_gemm.cu).  All return NRF_OK or an error code with the message set.
 int encode_planes_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows);
 
-struct Planes { __half* hi; __half* lo; int64_t rows; int32_t cols; int32_t ld; };   // cols: logical feature count (multiple of 64)
+// cols: logical feature count (multiple of 64).  ll: third plane of the exact mode (bf16 x 3), NULL otherwise; the element type of the
+// storage is 16-bit either way (fp16 or, in the exact mode, bfloat16 bit patterns).
+struct Planes { __half* hi; __half* lo; int64_t rows; int32_t cols; int32_t ld; __half* ll; };
 
 struct TileGemmArgs {
   Planes a[2]; Planes b[2]; int n_src; int b_mn; int N;      // N: output columns (multiple of 64)
-  int passes;
+  int passes;                  // 1, 3 (fp16 planes) or 6 (bf16 x 3 planes)
   int epi, relu;
   const float* bias; int bias_ld; int rows_per_ray;
   Planes out; float* out_f32; int out_f32_ld; int accumulate;

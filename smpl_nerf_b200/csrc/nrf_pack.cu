@@ -33,6 +33,7 @@ const char* last_error() { return g_err; }
 static uint32_t align4(uint32_t x) { return (x + 3u) & ~3u; }
 
 static void finish_plan(NetPlan* p, uint32_t f32_floats) {
+  p->flag_ofs = f32_floats; f32_floats += 4;       // range flag of the packed weights
   uint32_t ofs = 0;
   for (int i = 0; i < p->n_layers; ++i) {
     Layer& L = p->layers[i];
@@ -154,7 +155,7 @@ __device__ __forceinline__ int dev_enc_ref_col(int f, int freqs, int identity) {
   return (identity && c < 3) ? c : -1;
 }
 
-__global__ void pack_stream_kernel(const __grid_constant__ PackTable t, uint8_t* __restrict__ blob) {
+__global__ void pack_stream_kernel(const __grid_constant__ PackTable t, uint8_t* __restrict__ blob, int32_t* __restrict__ range_flag) {
   const PackChunk& c = t.c[blockIdx.x];
   const int part = blockIdx.y, half = part & 1, is_lo = part >> 1;   // stage order: hi/half0, hi/half1, lo/half0, lo/half1
   const int rows = c.n_out / 2;
@@ -164,6 +165,7 @@ __global__ void pack_stream_kernel(const __grid_constant__ PackTable t, uint8_t*
     int col = c.aux ? dev_enc_ref_col(k, c.freqs, c.identity) : k;
     float w = 0.f;
     if (col >= 0) w = c.w[static_cast<size_t>(half * rows + n) * c.ld + c.col0 + col];
+    if (!(fabsf(w) <= 65504.f)) *range_flag = 1;       // (also catches NaN) the fp16 hi/lo split cannot hold this weight: the renderer raises status bit 0
     __half hi, lo;
     split_f16(w, hi, lo);
     *reinterpret_cast<__half*>(stage + sw128_offset(n, k)) = is_lo ? lo : hi;
@@ -214,7 +216,8 @@ static int launch_pack(const NetPlan& plan, PackTable& pt, CopyTable& ct, void* 
   cudaError_t e = cudaSuccess;
   if (zero) e = cudaMemsetAsync(packed, 0, plan.total_bytes, s);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(packed)");
-  pack_stream_kernel<<<dim3(pt.n, 4), 256, 0, s>>>(pt, static_cast<uint8_t*>(packed));
+  pack_stream_kernel<<<dim3(pt.n, 4), 256, 0, s>>>(pt, static_cast<uint8_t*>(packed),
+                                                   reinterpret_cast<int32_t*>(static_cast<uint8_t*>(packed) + plan.f32_ofs) + plan.flag_ofs);
   pack_f32_kernel<<<ct.n, 256, 0, s>>>(ct, reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + plan.f32_ofs));
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pack kernels");

@@ -76,6 +76,7 @@ struct NetPlan {
   uint32_t sigma_ofs;     // float offset: wsigma[256], bsigma[1]
   int32_t in_freqs, in_identity;    // encoding of xyz that feeds the aux K-chunk
   int32_t dir_freqs, dir_identity;  // encoding of the view direction
+  uint32_t flag_ofs;      // float offset (fp32 section) of one int32: set to 1 by the packer when a weight left the fp16 range (|w| > 65504)
   int32_t folded;         // 1: additional_linear_layer is folded into the sigma head and directional_input at pack time
   uint32_t fold_ofs;      // float offset (fp32 section) of the folded tensors: Wdir'[128][256 + D], bdir'[128], wsigma'[256], bsigma'[1]
   Layer layers[kMaxLayers];

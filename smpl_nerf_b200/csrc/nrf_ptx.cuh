@@ -305,6 +305,7 @@ __host__ __device__ constexpr uint32_t sw64_offset(uint32_t row, uint32_t k) {
 // fp32 -> (hi, lo) fp16 split: x ~= hi + lo with ~22 significant bits.  Inputs are clamped to the
 // fp16 range first (activations of a sane NeRF MLP never get near it; the caller flags overflow).
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  x = fminf(fmaxf(x, -65504.f), 65504.f);
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
 }

@@ -65,10 +65,11 @@ struct Bump {
     off += count * sizeof(T);
     return p;
   }
-  Planes planes(int64_t rows, int cols, bool lo) {
+  Planes planes(int64_t rows, int cols, int n_planes) {      // n_planes: 1 (hi), 2 (hi, lo) or 3 (exact mode: bf16 hi, lo, ll)
     Planes p; p.rows = rows; p.cols = cols; p.ld = cols;
     p.hi = take<__half>(static_cast<size_t>(rows) * cols);
-    p.lo = lo ? take<__half>(static_cast<size_t>(rows) * cols) : nullptr;
+    p.lo = n_planes >= 2 ? take<__half>(static_cast<size_t>(rows) * cols) : nullptr;
+    p.ll = n_planes >= 3 ? take<__half>(static_cast<size_t>(rows) * cols) : nullptr;
     return p;
   }
 };
@@ -102,7 +103,7 @@ struct TrainCfg {
 };
 
 static void layout_ws(Bump& m, const TrainCfg& c, const TNet net[2], TrainWs* ws) {
-  const bool lo = c.passes == 3;
+  const int lo = c.passes == 6 ? 3 : (c.passes == 3 ? 2 : 1);      // planes per tensor
   const int n_pass = c.run_fine ? 2 : 1;
   for (int p = 0; p < n_pass; ++p)
     for (int l = 0; l < net[p].n; ++l) {
@@ -140,8 +141,8 @@ static void layout_ws(Bump& m, const TrainCfg& c, const TNet net[2], TrainWs* ws
     w.raw = m.take<float>(static_cast<size_t>(w.S) * 4);
     w.g_raw = m.take<float>(static_cast<size_t>(w.S) * 4);
   }
-  ws->dy[0] = m.planes(Smax, c.Wmax, true);
-  ws->dy[1] = m.planes(Smax, c.Wmax, true);
+  ws->dy[0] = m.planes(Smax, c.Wmax, 2);
+  ws->dy[1] = m.planes(Smax, c.Wmax, 2);
   ws->dysum = m.take<float>(static_cast<size_t>(c.B) * c.Wmax);
   if (c.smpl) { ws->g_encx = m.take<float>(static_cast<size_t>(Smax) * 64); ws->g_encd = m.take<float>(static_cast<size_t>(Smax) * 64);
                 ws->g_warp = m.take<float>(static_cast<size_t>(Smax) * 3); }
@@ -159,7 +160,7 @@ static int make_cfg(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, co
   if (B < 0) { set_error("train: B < 0"); return NRF_E_INVALID; }
   memset(c, 0, sizeof(*c));
   c->kind = pipe->kind; c->nc = pipe->n_coarse; c->run_fine = pipe->run_fine ? 1 : 0; c->nf = c->run_fine ? pipe->n_fine : 0;
-  c->na = c->nc + c->nf; c->white = pipe->white_background ? 1 : 0; c->passes = pipe->precision == 1 ? 1 : 3; c->B = B;
+  c->na = c->nc + c->nf; c->white = pipe->white_background ? 1 : 0; c->passes = pipe->precision == 1 ? 1 : (pipe->precision == 2 ? 6 : 3); c->B = B;
   c->smpl = pipe->kind == NRF_KIND_SMPL;
   if (c->nc < 2 || c->nc > 1024 || (c->run_fine && (c->nc < 3 || c->nf < 1 || c->na > 1024))) { set_error("train: unsupported sample counts %d + %d", c->nc, c->nf); return NRF_E_INVALID; }
   int rc;
@@ -228,7 +229,7 @@ static int setup(TrainCtx& t, const NrfPipelineDesc* pipe, const NrfRayNetDesc* 
 // ------------------------------------------------------------------------------ forward
 static int split_weights(TrainCtx& t) {
   static thread_local SplitTable tab;
-  tab.n = 0;
+  tab.n = 0; tab.bf16 = t.c.passes == 6 ? 1 : 0;
   auto flush = [&]() -> int {
     if (tab.n == 0) return NRF_OK;
     split_planes_kernel<<<dim3(8, tab.n), 256, 0, t.st>>>(tab);
@@ -240,9 +241,9 @@ static int split_weights(TrainCtx& t) {
   if (e0 != cudaSuccess) return cuda_fail(e0, "cudaMemsetAsync(wmax)");
   auto add = [&](const float* src, int rows, int cols, int ld, int col0, const Planes& dst, unsigned int* wmax) -> int {
     SplitJob& j = tab.j[tab.n++];
-    j.src = src; j.rows = rows; j.cols = cols; j.ld = ld; j.col0 = col0; j.hi = dst.hi; j.lo = dst.lo; j.ld_dst = dst.ld; j.cols_pad = dst.cols;
+    j.src = src; j.rows = rows; j.cols = cols; j.ld = ld; j.col0 = col0; j.hi = dst.hi; j.lo = dst.lo; j.ll = dst.ll; j.ld_dst = dst.ld; j.cols_pad = dst.cols;
     j.wmax = wmax;
-    return tab.n == 40 ? flush() : NRF_OK;
+    return tab.n == 36 ? flush() : NRF_OK;
   };
   const int n_pass = t.c.run_fine ? 2 : 1;
   for (int p = 0; p < n_pass; ++p)
@@ -282,7 +283,7 @@ static int heads(TrainCtx& t, const float* x, int64_t S, int K, const float* W, 
 }
 
 static int encode(TrainCtx& t, const float* x, int64_t S, int freqs, int identity, const Planes& dst) {
-  encode_planes_kernel<<<grid1(S * 8, 256), 256, 0, t.st>>>(x, S, freqs, identity, dst.hi, dst.lo);
+  encode_planes_kernel<<<grid1(S * 8, 256), 256, 0, t.st>>>(x, S, freqs, identity, dst.hi, dst.lo, dst.ll);
   LAUNCH_CHECK("encode_planes_kernel");
   return NRF_OK;
 }
@@ -337,6 +338,10 @@ static int forward_pass(TrainCtx& t, int p) {
   const int nl = net.nl;
   TRY(heads(t, w.h2_f32, w.S, net.W / 2, t.par[p][2 * nl + 8], t.par[p][2 * nl + 9], 3, w.raw, 4, 0));
   TRY(heads(t, w.a_f32, w.S, net.W, t.par[p][2 * nl + 2], t.par[p][2 * nl + 3], 1, w.raw, 4, 3));
+  if (float* tap = p == 0 ? t.io.raw_coarse : t.io.raw_fine) {      // debug tap (stage-wise parity tests)
+    cudaError_t et = cudaMemcpyAsync(tap, w.raw, static_cast<size_t>(w.S) * 4 * sizeof(float), cudaMemcpyDeviceToDevice, t.st);
+    if (et != cudaSuccess) return cuda_fail(et, "cudaMemcpyAsync(raw tap)");
+  }
   // ---- compositing: the SMPL coarse pass scales its deltas by |warped - o| per sample, every other pass by |ray_direction|
   const bool per_sample = c.smpl && p == 0;
   const float* dn = per_sample ? w.dnorm : t.ws.ray_norm;
@@ -350,6 +355,10 @@ static int forward_pass(TrainCtx& t, int p) {
   composite_fwd_kernel<<<grid1(c.B, wpb), wpb * 32, smem, t.st>>>(w.raw, w.z, dn, per_sample ? 1 : 0, p == 0 ? t.io.noise_coarse : t.io.noise_fine, c.B, w.n,
                                                                    c.white, rgb, p == 0 ? t.ws.weights_c : nullptr, alpha);
   LAUNCH_CHECK("composite_fwd_kernel");
+  if (p == 0 && t.io.weights_coarse) {
+    cudaError_t et = cudaMemcpyAsync(t.io.weights_coarse, t.ws.weights_c, static_cast<size_t>(c.B) * c.nc * sizeof(float), cudaMemcpyDeviceToDevice, t.st);
+    if (et != cudaSuccess) return cuda_fail(et, "cudaMemcpyAsync(weights tap)");
+  }
   return NRF_OK;
 }
 
@@ -378,6 +387,10 @@ static int forward_all(TrainCtx& t) {
     } else {
       TRY(nrf_fine_sampling(t.io.ray_origin, t.io.ray_dir, t.io.z_vals, t.ws.weights_c, t.io.u_fine, c.B, c.nc, c.nf, t.ws.z_all, pts, t.st));
       ++g_train_launches;
+    }
+    if (t.io.z_all) {
+      cudaError_t et = cudaMemcpyAsync(t.io.z_all, t.ws.z_all, static_cast<size_t>(c.B) * c.na * sizeof(float), cudaMemcpyDeviceToDevice, t.st);
+      if (et != cudaSuccess) return cuda_fail(et, "cudaMemcpyAsync(z_all tap)");
     }
     t.ws.pass[1].pts = pts;
     t.ws.pass[1].z = t.ws.z_all;
@@ -541,6 +554,7 @@ extern "C" int nrf_train_backward(const NrfPipelineDesc* pipe, const NrfRayNetDe
   TRY(setup(t, pipe, coarse, params_coarse, n_coarse, fine, params_fine, n_fine, warp, params_warp, n_warp, io, B, workspace, workspace_bytes, n_sms, stream));
   const TrainCfg& c = t.c;
   if (c.B == 0) return NRF_OK;
+  if (c.passes == 6) { set_error("train: precision 2 (exact, bf16 x 3) is an inference mode; train with precision 0 or 1"); return NRF_E_INVALID; }
   if (!grad_rgb || !grads_coarse || (c.run_fine && (!grad_rgb_fine || !grads_fine)) || (c.smpl && !grads_warp)) { set_error("train: gradient pointers are NULL"); return NRF_E_INVALID; }
   for (int i = 0; i < n_coarse; ++i) if (!grads_coarse[i]) { set_error("train: coarse gradient %d is NULL", i); return NRF_E_INVALID; }
   if (c.run_fine) for (int i = 0; i < n_fine; ++i) if (!grads_fine[i]) { set_error("train: fine gradient %d is NULL", i); return NRF_E_INVALID; }
@@ -579,8 +593,8 @@ extern "C" long long nrf_train_launch_count(int reset) { const long long n = g_t
 static size_t ray_bias_ws(const NetPlan& plan, int64_t B, int A, Planes* feats, Planes w[NRF_MAX_SKIPS + 1], uint8_t* base) {
   const int Kp = (A + 63) & ~63;
   Bump m{base, 0};
-  *feats = m.planes(B, Kp, true);
-  for (int e = 0; e < plan.n_ext_slots; ++e) w[e] = m.planes(kWidth, Kp, true);
+  *feats = m.planes(B, Kp, 2);
+  for (int e = 0; e < plan.n_ext_slots; ++e) w[e] = m.planes(kWidth, Kp, 2);
   return (m.off + 255) & ~static_cast<size_t>(255);
 }
 
@@ -608,8 +622,8 @@ extern "C" int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, 
   if (need > workspace_bytes) { set_error("ray_bias: workspace too small (%zu bytes given, %zu needed)", workspace_bytes, need); return NRF_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static thread_local SplitTable tab;
-  tab.n = 0;
-  { SplitJob& j = tab.j[tab.n++]; j.src = feats; j.rows = static_cast<int32_t>(B); j.cols = A; j.ld = A; j.col0 = 0; j.hi = fp.hi; j.lo = fp.lo; j.ld_dst = fp.ld; j.cols_pad = fp.cols; j.wmax = nullptr; }
+  tab.n = 0; tab.bf16 = 0;
+  { SplitJob& j = tab.j[tab.n++]; j.ll = nullptr; j.src = feats; j.rows = static_cast<int32_t>(B); j.cols = A; j.ld = A; j.col0 = 0; j.hi = fp.hi; j.lo = fp.lo; j.ld_dst = fp.ld; j.cols_pad = fp.cols; j.wmax = nullptr; }
   const float* bias[NRF_MAX_SKIPS + 1];
   for (int li = 0; li < plan.n_layers; ++li) {
     const Layer& L = plan.layers[li];
@@ -618,6 +632,7 @@ extern "C" int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, 
     if (!params[L.pidx] || !params[L.pidx + 1]) { set_error("ray_bias: parameter %d is NULL", L.pidx); return NRF_E_INVALID; }
     if ((reinterpret_cast<uintptr_t>(params[L.pidx + 1]) & 15u) != 0) { set_error("ray_bias: bias tensors must be 16-byte aligned"); return NRF_E_INVALID; }
     SplitJob& j = tab.j[tab.n++];
+    j.ll = nullptr;
     j.src = params[L.pidx]; j.rows = kWidth; j.cols = A; j.ld = li == 0 ? A + P : kWidth + A + P; j.col0 = li == 0 ? 0 : kWidth;
     j.hi = wp[L.ext_idx].hi; j.lo = wp[L.ext_idx].lo; j.ld_dst = wp[L.ext_idx].ld; j.cols_pad = wp[L.ext_idx].cols; j.wmax = nullptr;
     bias[L.ext_idx] = params[L.pidx + 1];
@@ -635,27 +650,30 @@ extern "C" int nrf_ray_bias(const NrfRayNetDesc* d, const float* const* params, 
 }
 
 // ---- building blocks exported for stage-wise tests (tests/test_gpu_train.py) ----
-extern "C" int nrf_split_planes(const float* src, int64_t rows, int32_t cols, int32_t ld, void* hi, void* lo, int32_t ld_dst, int32_t cols_pad, void* stream) {
-  if (!src || !hi || rows < 0 || cols < 1 || cols_pad < cols) { set_error("split_planes: bad arguments"); return NRF_E_INVALID; }
+extern "C" int nrf_split_planes(const float* src, int64_t rows, int32_t cols, int32_t ld, void* hi, void* lo, void* ll, int32_t ld_dst, int32_t cols_pad,
+                                void* stream) {
+  if (!src || !hi || rows < 0 || cols < 1 || cols_pad < cols || (ll && !lo)) { set_error("split_planes: bad arguments"); return NRF_E_INVALID; }
   if (rows == 0) return NRF_OK;
   static thread_local SplitTable tab;
-  tab.n = 1;
+  tab.n = 1; tab.bf16 = ll ? 1 : 0;
   SplitJob& j = tab.j[0];
+  j.wmax = nullptr;
   j.src = src; j.rows = static_cast<int32_t>(rows); j.cols = cols; j.ld = ld; j.col0 = 0; j.hi = static_cast<__half*>(hi); j.lo = static_cast<__half*>(lo);
-  j.ld_dst = ld_dst; j.cols_pad = cols_pad;
+  j.ll = static_cast<__half*>(ll); j.ld_dst = ld_dst; j.cols_pad = cols_pad;
   split_planes_kernel<<<dim3(64, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(tab);
   LAUNCH_CHECK("split_planes_kernel");
   return NRF_OK;
 }
 
-extern "C" int nrf_gemm_planes(int32_t b_mn, const void* a_hi, const void* a_lo, int64_t S, int32_t K, const void* b_hi, const void* b_lo, int32_t N,
-                               int32_t passes, const float* bias, int32_t relu, float* out_f32, void* out_hi, void* out_lo, void* stream) {
+extern "C" int nrf_gemm_planes(int32_t b_mn, const void* a_hi, const void* a_lo, const void* a_ll, int64_t S, int32_t K, const void* b_hi, const void* b_lo,
+                               const void* b_ll, int32_t N, int32_t passes, const float* bias, int32_t relu, float* out_f32, void* out_hi, void* out_lo,
+                               void* out_ll, void* stream) {
+  auto H = [](const void* p) { return static_cast<__half*>(const_cast<void*>(p)); };
   TileGemmArgs g{};
-  g.a[0] = Planes{static_cast<__half*>(const_cast<void*>(a_hi)), static_cast<__half*>(const_cast<void*>(a_lo)), S, K, K};
-  g.b[0] = b_mn ? Planes{static_cast<__half*>(const_cast<void*>(b_hi)), static_cast<__half*>(const_cast<void*>(b_lo)), K, N, N}
-                : Planes{static_cast<__half*>(const_cast<void*>(b_hi)), static_cast<__half*>(const_cast<void*>(b_lo)), N, K, K};
+  g.a[0] = Planes{H(a_hi), H(a_lo), S, K, K, H(a_ll)};
+  g.b[0] = b_mn ? Planes{H(b_hi), H(b_lo), K, N, N, H(b_ll)} : Planes{H(b_hi), H(b_lo), N, K, K, H(b_ll)};
   g.n_src = 1; g.b_mn = b_mn; g.N = N; g.passes = passes; g.relu = relu; g.bias = bias;
-  if (out_hi) { g.epi = GEPI_PLANES; g.out = Planes{static_cast<__half*>(out_hi), static_cast<__half*>(out_lo), S, N, N}; g.out_f32 = out_f32; g.out_f32_ld = N; }
+  if (out_hi) { g.epi = GEPI_PLANES; g.out = Planes{H(out_hi), H(out_lo), S, N, N, H(out_ll)}; g.out_f32 = out_f32; g.out_f32_ld = N; }
   else { g.epi = GEPI_F32; g.out_f32 = out_f32; g.out_f32_ld = N; }
   return launch_tile_gemm(g, 0, static_cast<cudaStream_t>(stream));
 }
@@ -663,8 +681,8 @@ extern "C" int nrf_gemm_planes(int32_t b_mn, const void* a_hi, const void* a_lo,
 extern "C" int nrf_gemm_dw(const void* a_hi, const void* a_lo, int32_t M, const void* b_hi, const void* b_lo, int32_t N, int64_t S, int32_t passes,
                            float* partial, int32_t max_split, float* out /* [M, N], accumulated into */, void* stream) {
   if (!partial || !out || max_split < 1) { set_error("gemm_dw: bad arguments"); return NRF_E_INVALID; }
-  Planes a{static_cast<__half*>(const_cast<void*>(a_hi)), static_cast<__half*>(const_cast<void*>(a_lo)), S, M, M};
-  Planes b{static_cast<__half*>(const_cast<void*>(b_hi)), static_cast<__half*>(const_cast<void*>(b_lo)), S, N, N};
+  Planes a{static_cast<__half*>(const_cast<void*>(a_hi)), static_cast<__half*>(const_cast<void*>(a_lo)), S, M, M, nullptr};
+  Planes b{static_cast<__half*>(const_cast<void*>(b_hi)), static_cast<__half*>(const_cast<void*>(b_lo)), S, N, N, nullptr};
   int split = 0;
   TRY(launch_dw_gemm(a, 0, M, b, 0, N, passes, partial, max_split, &split, 0, static_cast<cudaStream_t>(stream)));
   // unit scale: scale2 = {1, 1} lives behind the partial sums

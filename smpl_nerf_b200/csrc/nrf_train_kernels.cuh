@@ -5,6 +5,7 @@
 // (encoding), utils.py:134-191 (compositing), models/*_pipeline.py (orchestration); the loss side is
 // solver/nerf_solver.py:48-51 (MSE on rgb and rgb_fine).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -19,9 +20,19 @@ __device__ __forceinline__ void split_store(float x, __half* hi, __half* lo) {
   if (lo) *lo = __float2half_rn(x - __half2float(h));
 }
 
+// exact mode: x = hi + lo + ll exactly, three bfloat16 values (3 x 8 significant bits = fp32's 24, fp32's exponent range);
+// the bit patterns are stored through __half pointers (planes are "16-bit storage")
+__device__ __forceinline__ void split_store_bf16x3(float x, __half* hi, __half* lo, __half* ll) {
+  const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(b0);
+  const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 b2 = __float2bfloat16_rn(r1 - __bfloat162float(b1));
+  *reinterpret_cast<__nv_bfloat16*>(hi) = b0; *reinterpret_cast<__nv_bfloat16*>(lo) = b1; *reinterpret_cast<__nv_bfloat16*>(ll) = b2;
+}
+
 // ---------------------------------------------------------------------------------- fp32 matrix -> hi/lo planes (weights)
-struct SplitJob { const float* src; int32_t rows, cols, ld, col0; __half* hi; __half* lo; int32_t ld_dst, cols_pad; unsigned int* wmax; };   // wmax: max |src| (float bits), optional
-struct SplitTable { int32_t n; SplitJob j[40]; };
+struct SplitJob { const float* src; int32_t rows, cols, ld, col0; __half* hi; __half* lo; int32_t ld_dst, cols_pad; unsigned int* wmax; __half* ll; };   // wmax: max |src| (float bits), optional; ll: third plane (exact mode)
+struct SplitTable { int32_t n; int32_t bf16; SplitJob j[36]; };
 
 __global__ void split_planes_kernel(const __grid_constant__ SplitTable t) {
   const SplitJob& j = t.j[blockIdx.y];
@@ -30,7 +41,9 @@ __global__ void split_planes_kernel(const __grid_constant__ SplitTable t) {
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int r = idx / j.cols_pad, c = idx - r * j.cols_pad;
     const float v = c < j.cols ? j.src[static_cast<size_t>(r) * j.ld + j.col0 + c] : 0.f;
-    split_store(v, j.hi + static_cast<size_t>(r) * j.ld_dst + c, j.lo ? j.lo + static_cast<size_t>(r) * j.ld_dst + c : nullptr);
+    const size_t o = static_cast<size_t>(r) * j.ld_dst + c;
+    if (t.bf16) split_store_bf16x3(v, j.hi + o, j.lo + o, j.ll + o);
+    else split_store(v, j.hi + o, j.lo ? j.lo + o : nullptr);
     m = fmaxf(m, fabsf(v));
   }
   if (j.wmax) {
@@ -52,7 +65,7 @@ __global__ void absmax_kernel(const float* __restrict__ x, int n, unsigned int* 
 // utils.py:127-131 in REFERENCE feature order ([x?] ++ for k: sin(2^k x), cos(2^k x), each over the 3 components), zero
 // padded to 64 features, as fp16 hi/lo planes [S, 64]: the K-chunk an MLP layer multiplies with its xyz / direction columns.
 __global__ void encode_planes_kernel(const float* __restrict__ x, int64_t S, int freqs, int identity, __half* __restrict__ hi,
-                                     __half* __restrict__ lo) {
+                                     __half* __restrict__ lo, __half* __restrict__ ll) {
   const int64_t total = S * 8;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t s = idx >> 3;
@@ -61,6 +74,7 @@ __global__ void encode_planes_kernel(const float* __restrict__ x, int64_t S, int
     const int n_id = identity ? 3 : 0, width = n_id + 6 * freqs;
     __align__(16) __half h[8];
     __align__(16) __half l[8];
+    __align__(16) __half q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int f = f0 + i;
@@ -72,10 +86,12 @@ __global__ void encode_planes_kernel(const float* __restrict__ x, int64_t S, int
         sincos_pe(v[rem % 3] * __int_as_float((127 + k) << 23), sv, cv);
         val = rem < 3 ? sv : cv;
       }
-      split_store(val, &h[i], &l[i]);
+      if (ll) split_store_bf16x3(val, &h[i], &l[i], &q[i]);
+      else split_store(val, &h[i], &l[i]);
     }
     *reinterpret_cast<uint4*>(hi + s * 64 + f0) = *reinterpret_cast<const uint4*>(h);
     if (lo) *reinterpret_cast<uint4*>(lo + s * 64 + f0) = *reinterpret_cast<const uint4*>(l);
+    if (ll) *reinterpret_cast<uint4*>(ll + s * 64 + f0) = *reinterpret_cast<const uint4*>(q);
   }
 }
 

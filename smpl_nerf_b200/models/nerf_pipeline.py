@@ -19,7 +19,8 @@ class NerfPipeline(SmplPipeline):
 
     #: set to True to read the kernel's range flag after every call (costs one device synchronisation per call)
     strict_range = False
-    #: 0 = parity (fp16 hi/lo split, 3 MMA passes, every parity claim), 1 = fast (one fp16 pass; misses the 1e-4 alpha bar)
+    #: 0 = parity (fp16 hi/lo split, 3 MMA passes, every parity claim), 1 = fast (one fp16 pass; misses the 1e-4 alpha bar),
+    #: 2 = exact (bf16 x 3 planes, 6 passes, layer by layer: exact fp32 operands, no activation-range limit; ~8x slower, inference only)
     precision = 0
 
     def _render(self, data, **kw):
@@ -37,8 +38,9 @@ class NerfPipeline(SmplPipeline):
         saturates there, so the result would silently deviate from the fp32 reference.  Synchronises the device."""
         st = getattr(self, '_status', None)
         if st is not None and int(st.item()) & 1:
-            raise FloatingPointError('smpl_nerf_b200: a hidden activation exceeded the fp16 range (65504); the fused '
-                                     'engine cannot represent it -- rescale the offending layer or use the reference path')
+            raise FloatingPointError('smpl_nerf_b200: a hidden activation exceeded the fp16 range (65504), which the fp16 hi/lo '
+                                     'operand split cannot represent -- set pipeline.precision = 2 (exact mode: bf16 x 3 planes '
+                                     'with fp32\'s exponent range) for this net')
 
     def forward(self, data):
         if len(data) < 5:

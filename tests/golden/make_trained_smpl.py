@@ -6,12 +6,16 @@ Trains the HEADLINE architecture -- SmplNerfPipeline, two RenderRayNet 8x256 (sk
 128 fine samples, starting from the 'dense' init (default init with the sigma head x20 / bias +1: from the plain default init
 this scene collapses to "all white" within 700 steps) -- for a few hundred Adam steps with the REFERENCE classes (imported from /root/reference; loss =
 MSE(rgb) + MSE(rgb_fine), solver/smpl_nerf_solver.py:35-43 without the optional GMM term) on 64x64 views of the synthetic
-capsule figure whose arms MOVE with the pose (arm angle 0..60 degrees, goal_pose columns 38 and 41), then renders a
-held-out view (unseen camera, unseen arm angle) with the reference pipeline in fp32 AND in fp64 and stores:
+capsule figure whose arms MOVE with the pose (arm angle 0..60 degrees, goal_pose columns 38 and 41), then renders two
+evaluation views -- 'seen' (a training camera and pose with fresh sampling jitter) and 'heldout' (unseen camera and arm angle) --
+with the reference pipeline in fp32 and, fine depths teacher-forced, in fp64, and stores:
 
   * the FULL fp32 weights (no rounding: the engine's fp16 hi/lo weight split is exercised, lo != 0),
-  * the held-out rays + analytic ground truth, the reference's six outputs, its raw sigma/rgb taps, its PSNR,
-  * the reference's own fp32-vs-fp64 deviation on the same inputs (the noise floor that puts parity errors in context).
+  * per view: how to regenerate the rays (scene.make_rays arguments + checksums), the reference's rgb / rgb_fine, its PSNR against
+    the analytic ground truth, and its own fp32-vs-fp64 deviation (the noise floor that puts parity errors in context),
+  * for 'seen', every 8th ray: alpha, warped samples, merged depths and the raw sigma taps of both nets.
+
+`--eval-only` re-mints the evaluation part from the stored weights.
 
 tests/test_gpu_parity.py::test_trained_smpl_* and bench.py's `psnr` key render the same view with the engine."""
 import copy
@@ -64,48 +68,65 @@ def main():
             print(f'step {step:4d} loss {float(loss):.5f}  ({time.time() - t0:.0f} s)', flush=True)
     for m in (c, f, w):
         m.eval()
-    held = scene.make_rays(SIDE, SIDE, NC, phi=10.0, theta=52.0, arm_angle_deg=37.0, seed=999, with_colours=True)   # == held_args below
-    data = scene.data_list(held, 'smpl')
-    taps = {}
-    hooks = [c.register_forward_hook(lambda m, i, o: taps.__setitem__('raw_coarse', o.detach().clone())),
-             f.register_forward_hook(lambda m, i, o: taps.__setitem__('raw_fine', o.detach().clone()))]
-    with torch.no_grad():
-        ref_out = [t.clone() for t in pipe(data)]
-    for h in hooks:
-        h.remove()
-    # the reference's own fp32-vs-fp64 deviation (noise floor) through the bit-identical oracle port in float64
+    torch.save(dict(coarse=c.state_dict(), fine=f.state_dict(), warp=w.state_dict(), steps=STEPS, batch=BATCH), OUT + '.weights')
+    evaluate(ref, c, f, w, pe, de, he, args)
+
+
+VIEWS = {
+    # a TRAINING camera and pose (view k = 3) with an unseen stratified-sampling jitter: what the briefly trained net renders well
+    'seen': dict(h=SIDE, w=SIDE, n_coarse=NC, phi=8.0, theta=108.0, arm_angle_deg=45.0, seed=777, with_colours=True),
+    # unseen camera AND unseen arm angle: 700 steps on 10 views do not interpolate cameras 36 degrees apart (below the all-white score)
+    'heldout': dict(h=SIDE, w=SIDE, n_coarse=NC, phi=10.0, theta=52.0, arm_angle_deg=37.0, seed=999, with_colours=True),
+}
+
+
+def evaluate(ref, c, f, w, pe, de, he, args):
+    """Reference renders of the evaluation views (fp32, reference classes), the intermediates of the bit-identical port, and the
+    reference's own fp32-vs-fp64 deviation with the fine depths teacher-forced (the noise floor parity errors are read against)."""
+    pipe = ref.SmplNerfPipeline(c, f, w, args, pe, de, he)
     c64, f64, w64 = (copy.deepcopy(m).double() for m in (c, f, w))
-    with torch.no_grad():
-        o64 = O.smpl_nerf_forward(c64, f64, w64, pe, de, he, args, [t.double() for t in data])
-    floor = dict(rgb_fine=float((ref_out[1].double() - o64['rgb_fine']).abs().max()),
-                 alpha=float((ref_out[5].double() - o64['alpha_out']).abs().max()),
-                 alpha_p999=float(torch.quantile((ref_out[5].double() - o64['alpha_out']).abs().flatten()[:4000000], 0.999)),
-                 sigma_fine=float((taps['raw_fine'].view(-1, NC + NF, 4)[..., 3].double() - o64['raw_fine'][..., 3]).abs().max()),
-                 sigma_coarse=float((taps['raw_coarse'].view(-1, NC, 4)[..., 3].double() - o64['raw_coarse'][..., 3]).abs().max()))
-    mse = float(torch.mean((ref_out[1].double() - data[-1].double()) ** 2))
-    psnr = -10.0 * np.log10(mse)
-    white = -10.0 * np.log10(float(torch.mean((1.0 - data[-1].double()) ** 2)))
-    print(f'held-out PSNR of the reference render vs ground truth: {psnr:.3f} dB (all-white image: {white:.3f} dB)')
-    print('reference fp32-vs-fp64 floor:', floor)
-    # fp32 run of the (bit-identical) port for the intermediates the reference pipeline does not return
-    with torch.no_grad():
-        o32 = O.smpl_nerf_forward(c, f, w, pe, de, he, args, data)
-    assert torch.equal(o32['rgb_fine'], ref_out[1]) and torch.equal(o32['alpha_out'], ref_out[5]), 'port != reference'
+    out = dict(coarse=c.state_dict(), fine=f.state_dict(), warp=w.state_dict(), n_coarse=NC, n_fine=NF, side=SIDE, steps=STEPS, batch=BATCH,
+               sub_step=8, torch_version=torch.__version__, views={})
     sub = slice(0, None, 8)          # per-sample tensors are stored for every 8th ray only (file size)
-    # the held-out rays are NOT stored (4 MB): scene.make_rays(**held_args) regenerates them bit-for-bit (numpy float64
-    # arithmetic + RandomState(seed)); `data_checksum` guards that
-    held_args = dict(h=SIDE, w=SIDE, n_coarse=NC, phi=10.0, theta=52.0, arm_angle_deg=37.0, seed=999, with_colours=True)
-    torch.save(dict(coarse=c.state_dict(), fine=f.state_dict(), warp=w.state_dict(), n_coarse=NC, n_fine=NF, side=SIDE,
-                    held_args=held_args, data_checksum=[float(t.double().sum()) for t in data],
-                    reference_rgb=ref_out[0], reference_rgb_fine=ref_out[1], sub_step=8,
-                    reference_warped=ref_out[4][sub].clone(),
-                    reference_alpha=ref_out[5][sub].clone(), reference_z_all=o32['z_all'][sub].clone(),
-                    reference_sigma_coarse=taps['raw_coarse'].view(-1, NC, 4)[sub, :, 3].clone(),
-                    reference_sigma_fine=taps['raw_fine'].view(-1, NC + NF, 4)[sub, :, 3].clone(),
-                    reference_psnr=psnr, white_psnr=white, floor=floor, steps=STEPS,
-                    batch=BATCH, torch_version=torch.__version__), OUT)
+    for name, kw in VIEWS.items():
+        rays = scene.make_rays(**kw)
+        data = scene.data_list(rays, 'smpl')
+        with torch.no_grad():
+            ref_out = [t.clone() for t in pipe(data)]
+            o32 = O.smpl_nerf_forward(c, f, w, pe, de, he, args, data)
+            o64 = O.smpl_nerf_forward(c64, f64, w64, pe, de, he, args, [t.double() for t in data], z_all_in=o32['z_all'])
+        assert torch.equal(o32['rgb_fine'], ref_out[1]) and torch.equal(o32['alpha_out'], ref_out[5]), 'port != reference'
+        mask = torch.ones_like(o32['raw_fine'][..., 3], dtype=torch.bool)
+        mask[..., -1] = o32['raw_fine'][..., -1, 3].abs() > 1e-3          # the last sample's alpha is a step function of sigma at 0
+        floor = dict(rgb_fine=float((o32['rgb_fine'].double() - o64['rgb_fine']).abs().max()),
+                     alpha=float((o32['alpha_out'].double() - o64['alpha_out']).abs()[mask].max()),
+                     sigma_fine=float((o32['raw_fine'][..., 3].double() - o64['raw_fine'][..., 3]).abs().max()),
+                     sigma_coarse=float((o32['raw_coarse'][..., 3].double() - o64['raw_coarse'][..., 3]).abs().max()),
+                     max_abs_sigma=float(o32['raw_fine'][..., 3].abs().max()))
+        mse = float(torch.mean((ref_out[1].double() - data[-1].double()) ** 2))
+        psnr = -10.0 * np.log10(mse)
+        white = -10.0 * np.log10(float(torch.mean((1.0 - data[-1].double()) ** 2)))
+        print(f'{name}: reference render vs ground truth {psnr:.3f} dB (all-white image: {white:.3f} dB); fp32-vs-fp64 floor {floor}')
+        v = dict(args=kw, data_checksum=[float(t.double().sum()) for t in data], reference_rgb=ref_out[0], reference_rgb_fine=ref_out[1],
+                 reference_psnr=psnr, white_psnr=white, floor=floor)
+        if name == 'seen':
+            v.update(reference_warped=ref_out[4][sub].clone(), reference_alpha=ref_out[5][sub].clone(), reference_z_all=o32['z_all'][sub].clone(),
+                     reference_sigma_coarse=o32['raw_coarse'][sub, :, 3].clone(), reference_sigma_fine=o32['raw_fine'][sub, :, 3].clone())
+        out['views'][name] = v
+    torch.save(out, OUT)
     print(f'{OUT}: {os.path.getsize(OUT) / 1024:.0f} KB')
 
 
+def evaluate_only():
+    """Re-mint the evaluation part from the weights the training stage left in trained_smpl_d8.ckpt(.weights)."""
+    ref = R.load()
+    src = OUT + '.weights' if os.path.isfile(OUT + '.weights') else OUT
+    ck = torch.load(src, weights_only=False)
+    c, f, w, pe, de, he = O.build_nets('smpl', 41, 'dense', net_cls=ref.RenderRayNet, warp_cls=ref.WarpFieldNet, enc_cls=ref.PositionalEncoder)
+    c.load_state_dict(ck['coarse']); f.load_state_dict(ck['fine']); w.load_state_dict(ck['warp'])
+    torch.set_num_threads(int(os.environ.get('NRF_TRAIN_THREADS', os.cpu_count() or 1)))
+    evaluate(ref, c, f, w, pe, de, he, O.make_args(number_fine_samples=NF))
+
+
 if __name__ == '__main__':
-    main()
+    evaluate_only() if '--eval-only' in sys.argv else main()

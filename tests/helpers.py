@@ -72,5 +72,26 @@ def load_trained():
     return ck, (c, f, None, pe, de, he), args
 
 
+def load_trained_smpl():
+    """The briefly trained SmplNerfPipeline (8 x 256 x 2 + warp net, full fp32 weights) minted by tests/golden/make_trained_smpl.py.
+    Returns (ck, nets, args); ``trained_smpl_view(ck, name)`` regenerates a stored evaluation view's rays."""
+    ck = torch.load(os.path.join(GOLDEN_DIR, 'trained_smpl_d8.ckpt'), weights_only=False)
+    c, f, w, pe, de, he = O.build_nets('smpl', 0, 'default')
+    c.load_state_dict(ck['coarse']); f.load_state_dict(ck['fine']); w.load_state_dict(ck['warp'])
+    for m in (c, f, w):
+        m.eval()
+    return ck, (c, f, w, pe, de, he), O.make_args(number_fine_samples=ck['n_fine'])
+
+
+def trained_smpl_view(ck, name):
+    """Rays of evaluation view ``name`` ('seen' / 'heldout'): regenerated from the stored scene.make_rays arguments (numpy float64 +
+    RandomState: bit-reproducible) and checked against the stored checksums."""
+    from smpl_nerf_b200 import scene
+    v = ck['views'][name]
+    data = scene.data_list(scene.make_rays(**v['args']), 'smpl')
+    assert [float(t.double().sum()) for t in data] == v['data_checksum'], 'the evaluation rays are not reproducible on this machine'
+    return v, data
+
+
 def psnr(img, ref):
     return float(-10.0 * torch.log10(torch.mean((img.double().cpu() - ref.double().cpu()) ** 2)))

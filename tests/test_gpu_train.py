@@ -16,15 +16,39 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-def _planes(x, pad=None):
-    """fp32 [rows, cols] -> (hi, lo) fp16 planes through nrf_split_planes."""
+def _planes(x, pad=None, exact=False):
+    """fp32 [rows, cols] -> (hi, lo[, ll]) planes through nrf_split_planes (fp16 pair, or the exact mode's bfloat16 triple)."""
     L = _lib.lib()
     rows, cols = x.shape
     pad = pad or cols
-    hi = torch.empty(rows, pad, dtype=torch.float16, device=DEV)
-    lo = torch.empty(rows, pad, dtype=torch.float16, device=DEV)
-    _lib.check(L.nrf_split_planes(x.data_ptr(), rows, cols, cols, hi.data_ptr(), lo.data_ptr(), pad, pad, None), 'split')
-    return hi, lo
+    dt = torch.bfloat16 if exact else torch.float16
+    hi, lo = torch.empty(rows, pad, dtype=dt, device=DEV), torch.empty(rows, pad, dtype=dt, device=DEV)
+    ll = torch.empty(rows, pad, dtype=dt, device=DEV) if exact else None
+    _lib.check(L.nrf_split_planes(x.data_ptr(), rows, cols, cols, hi.data_ptr(), lo.data_ptr(), ll.data_ptr() if exact else None, pad, pad, None), 'split')
+    return (hi, lo, ll) if exact else (hi, lo)
+
+
+@pytest.mark.parametrize('S,K,N', [(1000, 256, 256), (300, 576, 512), (77, 64, 128)])
+def test_gemm_exact_mode(S, K, N):
+    """passes = 6 on bfloat16 hi/lo/ll planes: the split is exact (hi + lo + ll == x bit for bit), the product matches fp64 to
+    fp32-accumulation accuracy, also for operands far outside the fp16 range."""
+    L = _lib.lib()
+    torch.manual_seed(S + K)
+    a = torch.randn(S, K, device=DEV) * 3e5
+    w = torch.randn(N, K, device=DEV) / K ** .5 * 1e-5
+    ah, al, aq = _planes(a, exact=True)
+    wh, wl, wq = _planes(w, exact=True)
+    assert torch.equal(ah.float() + al.float() + aq.float(), a) and torch.equal(wh.float() + wl.float() + wq.float(), w)
+    out = torch.empty(S, N, device=DEV)
+    oh, ol, oq = (torch.empty(S, N, dtype=torch.bfloat16, device=DEV) for _ in range(3))
+    _lib.check(L.nrf_gemm_planes(0, ah.data_ptr(), al.data_ptr(), aq.data_ptr(), S, K, wh.data_ptr(), wl.data_ptr(), wq.data_ptr(), N, 6, None, 0,
+                                 out.data_ptr(), oh.data_ptr(), ol.data_ptr(), oq.data_ptr(), None), 'gemm exact')
+    want = a.double() @ w.double().t()
+    err = float((out.double() - want).abs().max())
+    print(f'exact gemm K={K}: max abs err {err:.2e} on outputs of magnitude {float(want.abs().max()):.1f}')
+    assert err <= 3e-6 * max(1.0, (K / 256) ** .5) * float(want.abs().max())
+    assert torch.equal(oh.float() + ol.float() + oq.float(), out)
+    torch.cuda.synchronize()
 
 
 @pytest.mark.parametrize('passes', [3, 1])
@@ -45,8 +69,8 @@ def test_gemm_forward_and_dx(S, K, N, passes):
     out = torch.empty(S, N, device=DEV)
     oh = torch.empty(S, N, dtype=torch.float16, device=DEV)
     ol = torch.empty(S, N, dtype=torch.float16, device=DEV)
-    _lib.check(L.nrf_gemm_planes(0, ah.data_ptr(), al.data_ptr(), S, K, wh.data_ptr(), wl.data_ptr(), N, passes, bias.data_ptr(), 1,
-                                 out.data_ptr(), oh.data_ptr(), ol.data_ptr(), None), 'gemm fwd')
+    _lib.check(L.nrf_gemm_planes(0, ah.data_ptr(), al.data_ptr(), None, S, K, wh.data_ptr(), wl.data_ptr(), None, N, passes, bias.data_ptr(), 1,
+                                 out.data_ptr(), oh.data_ptr(), ol.data_ptr(), None, None), 'gemm fwd')
     want = torch.relu(a.double() @ w.double().t() + bias.double())
     assert float((out.double() - want).abs().max()) <= tol
     assert float(((oh.double() + ol.double()) - out.double()).abs().max()) <= 1e-5 * (1 + float(out.abs().max()))
@@ -54,8 +78,8 @@ def test_gemm_forward_and_dx(S, K, N, passes):
     w2 = torch.randn(K, N, device=DEV) / K ** .5
     w2h, w2l = _planes(w2)
     out2 = torch.empty(S, N, device=DEV)
-    _lib.check(L.nrf_gemm_planes(1, ah.data_ptr(), al.data_ptr(), S, K, w2h.data_ptr(), w2l.data_ptr(), N, passes, None, 0,
-                                 out2.data_ptr(), None, None, None), 'gemm dx')
+    _lib.check(L.nrf_gemm_planes(1, ah.data_ptr(), al.data_ptr(), None, S, K, w2h.data_ptr(), w2l.data_ptr(), None, N, passes, None, 0,
+                                 out2.data_ptr(), None, None, None, None), 'gemm dx')
     assert float((out2.double() - a.double() @ w2.double()).abs().max()) <= tol
     torch.cuda.synchronize()
 
@@ -227,6 +251,53 @@ def test_other_hidden_widths(kind, width):
     print(f'{kind} width {width}: worst relative gradient error {worst:.2e}')
 
 
+@pytest.mark.parametrize('request_scale', [1e5, 1e7])      # activations beyond 65504; at 1e7 the first layer's WEIGHTS too
+def test_exact_mode_beyond_the_fp16_range(request_scale):
+    """precision = 2 (bf16 x 3 planes, six MMA passes, layer by layer): operands are exact fp32 values with fp32's exponent
+    range.  A net whose hidden activations reach 2e5 / 2e7 (first layer x scale, second layer / scale: the same function) trips the
+    fused kernel's fp16 range flag; the exact mode renders it within the parity bars."""
+    scale = request_scale
+    nets = O.build_nets('nerf', 13, 'dense')
+    with torch.no_grad():
+        for net in nets[:2]:
+            net.positions_pose_input.weight.mul_(scale); net.positions_pose_input.bias.mul_(scale)
+            net.positional_net[0].weight.div_(scale)
+    args = O.make_args()
+    data = _rays('nerf', 6, 6, 64, 2)
+    with torch.no_grad():
+        want = H.run_oracle('nerf', nets, args, data)
+    gnets, gdata = H.to_cuda(nets, data)
+    with torch.no_grad():
+        par = engine.render('nerf', gnets[0], gnets[1], None, args, gnets[3], gnets[4], None, gdata, z_all_in=want['z_all'].to(DEV))
+        got = engine.render('nerf', gnets[0], gnets[1], None, args, gnets[3], gnets[4], None, gdata, taps=True,
+                            z_all_in=want['z_all'].to(DEV), precision=2)
+    torch.cuda.synchronize()
+    assert int(par['status'].item()) & 1, 'the fp16 range flag of the fused kernel did not fire'
+    assert int(got['status'].item()) == 0
+    assert float((got['raw_coarse'][..., 3].cpu() - want['raw_coarse'][..., 3]).abs().max()) <= H.TOL_SIGMA * 3     # activations ~1e6: the reference's own fp32 noise is of this order
+    assert float((got['rgb_fine'].cpu() - want['rgb_fine']).abs().max()) <= H.TOL_RGB
+    mask = H.alpha_mask_well_conditioned(want['raw_fine'][..., 3])
+    assert float((got['alpha_out'].cpu() - want['alpha_out']).abs()[mask].max()) <= H.TOL_ALPHA
+
+
+def test_exact_mode_meets_the_literal_sigma_bar_on_trained_weights():
+    """on the trained vanilla-NeRF checkpoint (hidden activations O(100), sigma up to 240) the parity
+    mode's 22-bit operands miss the raw-sigma reading of the 1e-4 bar by up to 7x; the exact mode meets it literally."""
+    ck, nets, args = H.load_trained()
+    with torch.no_grad():
+        want = H.run_oracle('nerf', nets, args, ck['data'])
+    gnets, gdata = H.to_cuda(nets, ck['data'])
+    with torch.no_grad():
+        got = engine.render('nerf', gnets[0], gnets[1], None, args, gnets[3], gnets[4], None, gdata, taps=True,
+                            z_all_in=want['z_all'].to(DEV), precision=2)
+    torch.cuda.synchronize()
+    for k in ('raw_coarse', 'raw_fine'):
+        err = float((got[k][..., 3].cpu() - want[k][..., 3]).abs().max())
+        print(f'exact mode, trained d4 checkpoint: max |sigma - reference| {k} = {err:.2e} (max |sigma| {float(want[k][..., 3].abs().max()):.0f})')
+        assert err <= H.TOL_SIGMA
+    assert float((got['rgb_fine'].cpu() - want['rgb_fine']).abs().max()) <= 1e-5
+
+
 def test_eval_mode_and_no_grad_stay_on_the_fused_kernel():
     """inference.py:247-254 calls the pipeline with eval-mode nets and autograd on; validation uses torch.no_grad():
     both must take the fused inference kernel (graph-less outputs), training-mode nets the differentiable path."""
@@ -244,7 +315,7 @@ def test_eval_mode_and_no_grad_stay_on_the_fused_kernel():
     out = pipe(gdata)
     assert out[0].requires_grad and out[1].requires_grad and not out[2].requires_grad and not out[3].requires_grad
     with pytest.raises(ValueError):
-        engine.render('nerf', gnets[0], gnets[1], None, args, gnets[3], gnets[4], None, gdata, taps=True)
+        engine.render('nerf', gnets[0], gnets[1], None, args, gnets[3], gnets[4], None, gdata, trace_cap=16)
 
 
 @pytest.mark.parametrize('kind', ['nerf', 'append', 'smpl'])
