@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             const uint32_t dst = smem_a + stage * a_stage;
             for (uint32_t p = 0; p < planes; ++p)
               tma_load_2d(dst + p * kATile, &P.a_map[j][p], 64 * lc, static_cast<int32_t>(mt * 128), smem_u32(&bars->a_full[stage]));
+            // the activation planes stream from HBM (hundreds of MB per layer): pull this CTA's tile-after-next into L2 now, so the
+            // 2-3 deep ring is refilled at L2 latency
+            const int64_t pf = mt + 2 * static_cast<int64_t>(gridDim.x);
+            if (pf < n_mt) for (uint32_t p = 0; p < planes; ++p) tma_prefetch_2d(&P.a_map[j][p], 64 * lc, static_cast<int32_t>(pf * 128));
             if (P.b_stream) load_b(j, lc, dst + planes * kATile, smem_u32(&bars->a_full[stage]));
             if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
           }
@@ -164,10 +168,28 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
       const float* bias_row = P.bias ? P.bias + (P.bias_ld ? (row_ok ? row / P.rows_per_ray : 0) * P.bias_ld : 0) : nullptr;
       const float rs = (P.row_scale && row_ok) ? P.row_scale[row * P.row_scale_ld] * s_out : 0.f;
       float l1 = 0.f;
-      float sum[64];            // exact mode: this thread's cols_w (<= 64) columns, K-chunks added with round-to-nearest
-      if (P.bf16) {
+      // this thread's cols_w (<= 64) output columns start from the bias: its global loads (and the ReLU' mask's) are issued
+      // BEFORE the wait for the accumulator, so their latency hides behind the MMAs (loading them per 16-column group after the
+      // TMEM read made the epilogue the bottleneck: long-scoreboard stalls on every group, profiles/r2).  In the exact mode the
+      // K-chunks are then added onto it with round-to-nearest.
+      float sum[64];
+      uint4 mk[8];
+      const int col0 = n0 + half * cols_w;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) sum[i] = 0.f;
+      for (int g = 0; g < 4; ++g) {
+        if (g < cols_w / 16) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b = (bias_row && row_ok) ? __ldg(reinterpret_cast<const float4*>(bias_row + col0 + 16 * g) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sum[16 * g + 4 * i] = b.x; sum[16 * g + 4 * i + 1] = b.y; sum[16 * g + 4 * i + 2] = b.z; sum[16 * g + 4 * i + 3] = b.w;
+          }
+          if (P.mask_hi && row_ok) {
+            const uint4* mp = reinterpret_cast<const uint4*>(P.mask_hi + row * P.mask_ld + col0 + 16 * g);
+            mk[2 * g] = __ldg(mp); mk[2 * g + 1] = __ldg(mp + 1);
+          }
+        }
+      }
+      if (P.bf16) {
         for (int c = 0; c < nk; ++c, ++it) {
           buf = it & 1u;
           mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
@@ -213,12 +235,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 16; ++i) x[i] *= ratio;
         }
-        if (bias_row) {
+        if (!P.bf16) {           // (exact mode: the bias is already inside the running sum)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias_row + col) + i);
-            x[4 * i] += b.x; x[4 * i + 1] += b.y; x[4 * i + 2] += b.z; x[4 * i + 3] += b.w;
-          }
+          for (int i = 0; i < 16; ++i) x[i] += sum[16 * g + i];
         }
         if (P.row_scale) {
 #pragma unroll
@@ -229,8 +248,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
         }
         if (P.mask_hi) {
-          const uint4* mp = reinterpret_cast<const uint4*>(P.mask_hi + row * P.mask_ld + col);
-          const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+          const uint4 m0 = mk[2 * g], m1 = mk[2 * g + 1];
           const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {      // post-ReLU activations are >= 0: "active" = any non-zero bit pattern
@@ -346,6 +364,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
           for (int g = 0; g < 2; ++g) tma_load_2d(da + g * 8192u, p ? &P.a_lo : &P.a_hi, m_tile + 64 * g, s0, full);
           for (int g = 0; g < P.N / 64; ++g) tma_load_2d(db + g * 8192u, p ? &P.b_lo : &P.b_hi, P.n0 + 64 * g, s0, full);
         }
+        const int64_t pf = c + 3 * static_cast<int64_t>(gridDim.y);       // three chunks ahead of the 2-deep ring: into L2
+        if (pf < n_chunks)
+          for (uint32_t p = 0; p < planes; ++p) {
+            for (int g = 0; g < 2; ++g) tma_prefetch_2d(p ? &P.a_lo : &P.a_hi, m_tile + 64 * g, static_cast<int32_t>(pf * 64));
+            for (int g = 0; g < P.N / 64; ++g) tma_prefetch_2d(p ? &P.b_lo : &P.b_hi, P.n0 + 64 * g, static_cast<int32_t>(pf * 64));
+          }
         if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
       }
     }

@@ -253,6 +253,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
                ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
+// the same box, only brought into L2 (no shared-memory destination, no barrier): lets a short shared-memory ring run at L2
+// latency instead of DRAM latency.  SASS: UTMAPF.
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
+}
 // MN-major operand tile, 128-byte swizzle (PTX ISA canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), T = 8 fp16):
 // 64 consecutive M/N elements (128 B) per K row, 8 K rows per 1024-byte swizzle atom; atoms follow each other along K
 // every `sbo` bytes and along M/N every `lbo` bytes.  This is what a SWIZZLE_128B tensor-TMA box of

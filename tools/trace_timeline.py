@@ -16,6 +16,7 @@ warp = warp.to(dev) if warp is not None else None
 args = bench.make_args(w)
 data = [t.to(dev) for t in bench.make_views(w, 0, 1)[0]]
 for _ in range(2):
+  with torch.no_grad():
     out = engine.render(w['kind'], coarse, fine, warp, args, pe, de, he, data, precision=precision, trace_cap=6000)
 torch.cuda.synchronize()
 tr = out['trace'].cpu()
