@@ -45,6 +45,7 @@ __device__ __forceinline__ uint32_t cvt_f16x2_satfinite(float x0, float x1) {
 struct GemmBars { uint64_t b_full, a_full[4], a_empty[4], acc_full[2], acc_empty[2]; uint32_t tmem; uint32_t pad; };
 
 // ------------------------------------------------------------------------------------------------ tile GEMM
+template <bool kExact>
 __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid_constant__ TileGemmParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -54,7 +55,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
   const uint32_t b_bytes = P.b_stream ? 0u : static_cast<uint32_t>(nk) * planes * b_chunk;
   const uint32_t a_stage = planes * kATile + (P.b_stream ? planes * b_chunk : 0u);      // streaming mode: [A planes | B planes] per stage
   const uint32_t smem_b = smem_u32(smem), smem_a = smem_b + b_bytes;
-  GemmBars* bars = reinterpret_cast<GemmBars*>(smem + b_bytes + static_cast<uint32_t>(P.n_stages) * a_stage);
+  const uint32_t out_bytes = P.staged ? static_cast<uint32_t>(P.n_tile) * 256u : 0u;       // one [128 x n_tile] fp16 plane of the output tile
+  const uint32_t smem_o = smem_a + static_cast<uint32_t>(P.n_stages) * a_stage;
+  GemmBars* bars = reinterpret_cast<GemmBars*>(smem + b_bytes + static_cast<uint32_t>(P.n_stages) * a_stage + out_bytes);
   const int n0 = blockIdx.y * P.n_tile;
   const int64_t n_mt = (P.S + 127) / 128;
 
@@ -106,19 +109,19 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_f16_major(128, static_cast<uint32_t>(P.n_tile), 0u, P.b_mn ? 1u : 0u) | (P.bf16 ? ((1u << 7) | (1u << 10)) : 0u);
+    const uint32_t idesc = umma_idesc_f16_major(128, static_cast<uint32_t>(P.n_tile), 0u, P.b_mn ? 1u : 0u) | (kExact ? ((1u << 7) | (1u << 10)) : 0u);
     if (!P.b_stream) mbar_wait(smem_u32(&bars->b_full), 0);
     tc_fence_after_sync();
     uint32_t stage = 0, phase = 0, it = 0;      // it: accumulator hand-offs so far (one per tile; one per K-chunk in the exact mode)
     for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x) {
       uint32_t buf = it & 1u, acc = 0, accumulate = 0;
-      if (!P.bf16) {
+      if (!kExact) {
         mbar_wait(smem_u32(&bars->acc_empty[buf]), ((it >> 1) & 1u) ^ 1u);
         tc_fence_after_sync();
         acc = tmem + buf * static_cast<uint32_t>(P.n_tile);
       }
       for (int c = 0; c < nk; ++c) {
-        if (P.bf16) {
+        if (kExact) {
           // exact mode: the tensor core ROUNDS TOWARD ZERO when it adds into an fp32 accumulator (measured: ~2^-24.5 relative per
           // accumulating instruction, tests/test_gpu_train.py::test_gemm_exact_mode), so long chains drift.  Every K-chunk gets
           // fresh accumulators -- `main` for the 4 hi*hi instructions, `corr` for the 20 small correction products -- and the
@@ -137,8 +140,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           const uint32_t pa = (0x012010u >> (4 * pass)) & 0xFu, pb = (0x210100u >> (4 * pass)) & 0xFu;
           const uint32_t a = a_hi + pa * kATile, b = b_hi + pb * b_chunk;
           const uint64_t ad = umma_desc_sw128(a);
-          const uint32_t dst = (P.bf16 && pass > 0) ? acc + static_cast<uint32_t>(P.n_tile) : acc;
-          if (P.bf16 && pass <= 1) accumulate = 0;       // first instruction into main (pass 0) / corr (pass 1)
+          const uint32_t dst = (kExact && pass > 0) ? acc + static_cast<uint32_t>(P.n_tile) : acc;
+          if (kExact && pass <= 1) accumulate = 0;       // first instruction into main (pass 0) / corr (pass 1)
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks) {
             const uint64_t bd = P.b_mn ? umma_desc_mn_sw128(b + ks * 2048u, 8192u, 1024u) : umma_desc_sw128(b) + 2u * ks;
@@ -148,9 +151,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
         }
         umma_commit_warp(smem_u32(&bars->a_empty[stage]));
         if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
-        if (P.bf16) { umma_commit_warp(smem_u32(&bars->acc_full[buf])); ++it; }
+        if (kExact) { umma_commit_warp(smem_u32(&bars->acc_full[buf])); ++it; }
       }
-      if (!P.bf16) { umma_commit_warp(smem_u32(&bars->acc_full[buf])); ++it; }
+      if (!kExact) { umma_commit_warp(smem_u32(&bars->acc_full[buf])); ++it; }
     }
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -173,8 +176,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
       // TMEM read made the epilogue the bottleneck: long-scoreboard stalls on every group, profiles/r2).  In the exact mode the
       // K-chunks are then added onto it with round-to-nearest.
       float sum[64];
-      uint4 mk[8];
+      uint4 mk[2], mk_next[2];       // ReLU' mask of the current / the next 16-column group (fetched one group ahead)
       const int col0 = n0 + half * cols_w;
+      const uint4* mask_row = (P.mask_hi && row_ok) ? reinterpret_cast<const uint4*>(P.mask_hi + row * P.mask_ld + col0) : nullptr;
+      mk_next[0] = mk_next[1] = make_uint4(0u, 0u, 0u, 0u);
+      if (mask_row) { mk_next[0] = __ldg(mask_row); mk_next[1] = __ldg(mask_row + 1); }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (g < cols_w / 16) {
@@ -183,13 +189,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             const float4 b = (bias_row && row_ok) ? __ldg(reinterpret_cast<const float4*>(bias_row + col0 + 16 * g) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             sum[16 * g + 4 * i] = b.x; sum[16 * g + 4 * i + 1] = b.y; sum[16 * g + 4 * i + 2] = b.z; sum[16 * g + 4 * i + 3] = b.w;
           }
-          if (P.mask_hi && row_ok) {
-            const uint4* mp = reinterpret_cast<const uint4*>(P.mask_hi + row * P.mask_ld + col0 + 16 * g);
-            mk[2 * g] = __ldg(mp); mk[2 * g + 1] = __ldg(mp + 1);
-          }
         }
       }
-      if (P.bf16) {
+      if (kExact) {
         for (int c = 0; c < nk; ++c, ++it) {
           buf = it & 1u;
           mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
@@ -215,11 +217,23 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
         tc_fence_after_sync();
       }
       const uint32_t taddr = tmem + buf * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(half * cols_w);
+      // staged epilogue: the output tile goes through shared memory ([128 rows x 64 cols] SWIZZLE_128B blocks) and leaves as TMA
+      // stores -- a thread owns ONE ROW, so direct 16-byte stores hit 32 different rows per instruction (32 half-used sectors:
+      // the load/store unit, not the tensor pipe, then sets the tile time; profiles/r2)
+      uint32_t lreg[32];
+      const bool e0 = warp == 2 && lane == 0;
+      const int r_t = 32 * q + lane;                      // row inside the tile
+      if (P.staged) {                                     // the previous tile's lo plane has been read out of the staging buffer
+        if (e0) tma_store_wait_read();
+        named_bar_sync(1, 256);
+      }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (g >= cols_w / 16) continue;
+        mk[0] = mk_next[0]; mk[1] = mk_next[1];
+        if (mask_row && g + 1 < cols_w / 16) { mk_next[0] = __ldg(mask_row + 2 * (g + 1)); mk_next[1] = __ldg(mask_row + 2 * (g + 1) + 1); }
         uint32_t v[16];
-        if (!P.bf16) {
+        if (!kExact) {
           tmem_ld16(taddr + 16u * g, v);
           tmem_ld_wait();
         } else {
@@ -235,7 +249,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 16; ++i) x[i] *= ratio;
         }
-        if (!P.bf16) {           // (exact mode: the bias is already inside the running sum)
+        if (!kExact) {           // (exact mode: the bias is already inside the running sum)
 #pragma unroll
           for (int i = 0; i < 16; ++i) x[i] += sum[16 * g + i];
         }
@@ -248,7 +262,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
         }
         if (P.mask_hi) {
-          const uint4 m0 = mk[2 * g], m1 = mk[2 * g + 1];
+          const uint4 m0 = mk[0], m1 = mk[1];
           const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {      // post-ReLU activations are >= 0: "active" = any non-zero bit pattern
@@ -270,7 +284,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           }
         } else {
           uint32_t h[8], l[8], ll[8];
-          if (P.bf16) {
+          if (kExact) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {      // x = hi + lo + ll exactly (3 x 8 significant bits), fp32 exponent range
               float r0 = x[2 * i], r1 = x[2 * i + 1];
@@ -290,13 +304,23 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
               l[i] = cvt_f16x2_satfinite(x[2 * i] - f.x, x[2 * i + 1] - f.y);
             }
           }
-          uint4* ph = reinterpret_cast<uint4*>(P.out_hi + row * P.out_ld + col);
-          ph[0] = make_uint4(h[0], h[1], h[2], h[3]); ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
-          if (P.out_lo) {
-            uint4* pl = reinterpret_cast<uint4*>(P.out_lo + row * P.out_ld + col);
-            pl[0] = make_uint4(l[0], l[1], l[2], l[3]); pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+          if (P.staged) {
+            const int ct = half * cols_w + 16 * g;        // column inside the tile -> 64-column block, 16-byte chunk
+            const uint32_t blk = smem_o + static_cast<uint32_t>(ct >> 6) * 16384u + static_cast<uint32_t>(r_t) * 128u;
+            const uint32_t ch = static_cast<uint32_t>(ct & 63) >> 3;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch) ^ (r_t & 7u)) << 4)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch + 1u) ^ (r_t & 7u)) << 4)), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i) lreg[8 * g + i] = l[i];
+          } else {
+            uint4* ph = reinterpret_cast<uint4*>(P.out_hi + row * P.out_ld + col);
+            ph[0] = make_uint4(h[0], h[1], h[2], h[3]); ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            if (P.out_lo) {
+              uint4* pl = reinterpret_cast<uint4*>(P.out_lo + row * P.out_ld + col);
+              pl[0] = make_uint4(l[0], l[1], l[2], l[3]); pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+            }
           }
-          if (P.bf16 && P.out_ll) {
+          if (kExact && P.out_ll) {
             uint4* pq = reinterpret_cast<uint4*>(P.out_ll + row * P.out_ld + col);
             pq[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]); pq[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
           }
@@ -308,13 +332,42 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
         }
       }
       l1_run = fmaxf(l1_run, l1);
-      if (!P.bf16) {
+      if (!kExact) {
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
         ++it;
       }
+      if (P.staged) {
+        const int32_t r0 = static_cast<int32_t>(mt * 128);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);                            // hi plane of the tile is in the staging buffer
+        if (e0) {
+          for (int b = 0; b < P.n_tile / 64; ++b) tma_store_2d(&P.o_map[0], n0 + 64 * b, r0, smem_o + static_cast<uint32_t>(b) * 16384u);
+          tma_store_commit();
+          if (P.out_lo) tma_store_wait_read();
+        }
+        if (P.out_lo) {
+          named_bar_sync(1, 256);                          // ... and has been read: the lo plane takes its place
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g >= cols_w / 16) continue;
+            const int ct = half * cols_w + 16 * g;
+            const uint32_t blk = smem_o + static_cast<uint32_t>(ct >> 6) * 16384u + static_cast<uint32_t>(r_t) * 128u;
+            const uint32_t ch = static_cast<uint32_t>(ct & 63) >> 3;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch) ^ (r_t & 7u)) << 4)), "r"(lreg[8 * g]), "r"(lreg[8 * g + 1]), "r"(lreg[8 * g + 2]), "r"(lreg[8 * g + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch + 1u) ^ (r_t & 7u)) << 4)), "r"(lreg[8 * g + 4]), "r"(lreg[8 * g + 5]), "r"(lreg[8 * g + 6]), "r"(lreg[8 * g + 7]) : "memory");
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 256);
+          if (e0) {
+            for (int b = 0; b < P.n_tile / 64; ++b) tma_store_2d(&P.o_map[1], n0 + 64 * b, r0, smem_o + static_cast<uint32_t>(b) * 16384u);
+            tma_store_commit();
+          }
+        }
+      }
     }
+    if (P.staged && warp == 2 && lane == 0) tma_store_wait_all();
     if (P.l1max) {
       l1_run *= (P.epi == GEPI_F32 ? 1.f : inv_out) * static_cast<float>(gridDim.y * 2);     // real units; 2 column segments per slice
 #pragma unroll
@@ -488,7 +541,16 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
     a_stage += planes * P.n_tile * 128u;
     b_bytes = 0;
   }
-  int stages = static_cast<int>((kGemmSmemLimit - 256 - b_bytes) / a_stage);
+  // staged epilogue (fp16 planes out through shared memory + TMA stores) whenever the ring keeps >= 2 stages beside it
+  uint32_t out_bytes = 0;
+  if (a.epi == GEPI_PLANES && a.passes != 6 && a.out.hi && !(reinterpret_cast<uintptr_t>(a.out.hi) & 15u) && !(a.out.ld & 7) &&
+      (!a.out.lo || !(reinterpret_cast<uintptr_t>(a.out.lo) & 15u)) && b_bytes + 2 * a_stage + static_cast<uint32_t>(P.n_tile) * 256u + 256 <= kGemmSmemLimit) {
+    P.staged = 1;
+    out_bytes = static_cast<uint32_t>(P.n_tile) * 256u;
+    if ((rc = encode_planes_map(&P.o_map[0], a.out.hi, S, a.N, a.out.ld, 64, 128)) != NRF_OK) return rc;
+    if (a.out.lo && (rc = encode_planes_map(&P.o_map[1], a.out.lo, S, a.N, a.out.ld, 64, 128)) != NRF_OK) return rc;
+  }
+  int stages = static_cast<int>((kGemmSmemLimit - 256 - b_bytes - out_bytes) / a_stage);
   P.n_stages = stages > 4 ? 4 : stages;
   P.epi = a.epi; P.relu = a.relu; P.bias = a.bias; P.bias_ld = a.bias_ld; P.rows_per_ray = a.rows_per_ray > 0 ? a.rows_per_ray : 1;
   P.out_hi = a.out.hi; P.out_lo = a.out.lo; P.out_ll = a.out.ll; P.out_ld = a.out.ld; P.out_f32 = a.out_f32; P.out_f32_ld = a.out_f32_ld; P.accumulate = a.accumulate;
@@ -501,10 +563,12 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
   const int slices = a.N / P.n_tile;
   const int64_t n_mt = (S + 127) / 128;
   int gx = sms / slices; if (gx < 1) gx = 1; if (gx > n_mt) gx = static_cast<int>(n_mt);
-  const uint32_t smem_bytes = b_bytes + static_cast<uint32_t>(P.n_stages) * a_stage + 256;
-  cudaError_t e = cudaFuncSetAttribute(tile_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit));
+  const uint32_t smem_bytes = b_bytes + static_cast<uint32_t>(P.n_stages) * a_stage + out_bytes + 256;
+  cudaError_t e = P.bf16 ? cudaFuncSetAttribute(tile_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit))
+                         : cudaFuncSetAttribute(tile_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tile_gemm)");
-  tile_gemm_kernel<<<dim3(gx, slices), kTileThreads, smem_bytes, stream>>>(P);
+  if (P.bf16) tile_gemm_kernel<true><<<dim3(gx, slices), kTileThreads, smem_bytes, stream>>>(P);
+  else tile_gemm_kernel<false><<<dim3(gx, slices), kTileThreads, smem_bytes, stream>>>(P);
   ++g_train_launches;
   e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "tile_gemm_kernel launch");

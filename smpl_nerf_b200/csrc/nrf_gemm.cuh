@@ -33,6 +33,8 @@ struct TileGemmParams {
   int32_t kc[2];
   int32_t n_src, b_mn, n_tile, passes, n_stages;
   int32_t bf16;                   // 1: the planes hold bfloat16 (exact mode: 3 planes = 24 significant bits, fp32 range), else fp16
+  CUtensorMap o_map[2];           // staged epilogue: output planes hi / lo as [S, N], box {64, 128}, written by TMA stores
+  int32_t staged;                 // 1: the epilogue stages the fp16 output planes through shared memory (coalesced TMA stores)
   int32_t b_stream;               // 1: K too large for a resident weight slice -- the B chunk travels with every A chunk through the ring
   int64_t S;
   int32_t epi, relu;

@@ -258,6 +258,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
 __device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
 }
+// shared -> global 2-D tensor store (bulk async group; rows / columns outside the tensor are clipped).  SASS: UTMASTG.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int32_t c0, int32_t c1, uint32_t src_smem) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(src_smem) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources may be overwritten
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // MN-major operand tile, 128-byte swizzle (PTX ISA canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), T = 8 fp16):
 // 64 consecutive M/N elements (128 B) per K row, 8 K rows per 1024-byte swizzle atom; atoms follow each other along K
 // every `sbo` bytes and along M/N every `lbo` bytes.  This is what a SWIZZLE_128B tensor-TMA box of
