@@ -141,6 +141,74 @@ def test_render_argument_errors_are_reported_without_a_gpu(L):
     assert L.nrf_generate_rays(0, 4, 1.0, None, None, None, None, 8, None, None, None, None, None) == -1
 
 
+def test_training_entry_points_validate_without_a_gpu(L):
+    """nrf_train_* / nrf_ssim / nrf_generate_rays_range / nrf_ray_bias check shapes, pointers and workspace sizes before any launch."""
+    c, f, w, pe, de, he = O.build_nets('smpl', 0)
+    dc, dw = engine.raynet_desc(c, pe, de, True), engine.warpnet_desc(w, pe, 40, True)
+    pipe = _lib.PipelineDesc()
+    pipe.kind, pipe.n_coarse, pipe.n_fine, pipe.run_fine, pipe.white_background = 1, 64, 128, 1, 1
+    pipe.pose_freqs, pipe.pose_identity, pipe.pose_encoded, pipe.pose_stride, pipe.pose_col0, pipe.pose_col1 = 10, 0, 1, 69, 38, 41
+    small = L.nrf_train_workspace_bytes(C.byref(pipe), C.byref(dc), C.byref(dc), C.byref(dw), 64)
+    big = L.nrf_train_workspace_bytes(C.byref(pipe), C.byref(dc), C.byref(dc), C.byref(dw), 1024)
+    # ~17 KB of saved activations / gradient planes per sample (256 samples per ray) + fixed buffers
+    assert 0 < small < big and 2.5e9 < big < 6e9
+    pipe.precision = 1          # one-pass mode keeps no lo planes
+    assert L.nrf_train_workspace_bytes(C.byref(pipe), C.byref(dc), C.byref(dc), C.byref(dw), 1024) < 0.8 * big
+    pipe.precision = 0
+    dbad = engine.raynet_desc(c, pe, de, True); dbad.width = 192
+    assert L.nrf_train_workspace_bytes(C.byref(pipe), C.byref(dbad), C.byref(dc), C.byref(dw), 64) == 0
+    assert b'width' in L.nrf_last_error()
+    d128 = engine.raynet_desc(c, pe, de, True); d128.width = 128      # 128 / 512 are planned by the layer-by-layer path
+    assert L.nrf_train_workspace_bytes(C.byref(pipe), C.byref(d128), C.byref(d128), C.byref(dw), 64) > 0
+    pipe.pose_encoded = 0
+    assert L.nrf_train_workspace_bytes(C.byref(pipe), C.byref(dc), C.byref(dc), C.byref(dw), 64) == 0
+    assert b'human_pose_encoding' in L.nrf_last_error()
+    pipe.pose_encoded = 1
+    io = _lib.RenderIO()
+    PP = C.POINTER(C.c_void_p)
+    tab = (C.c_void_p * 26)(*([1024] * 26))
+    tw = (C.c_void_p * 4)(*([1024] * 4))
+    args = (C.byref(pipe), C.byref(dc), tab, 26, C.byref(dc), tab, 26, C.byref(dw), tw, 4)
+    assert L.nrf_train_forward(*args, None, 8, C.c_void_p(4096), big, 0, None) == -1 and b'io is NULL' in L.nrf_last_error()
+    assert L.nrf_train_forward(*args, C.byref(io), 8, None, big, 0, None) == -1 and b'workspace' in L.nrf_last_error()
+    assert L.nrf_train_forward(*args, C.byref(io), 8, C.c_void_p(4096), 1024, 0, None) == -1 and b'too small' in L.nrf_last_error()
+    assert L.nrf_train_forward(C.byref(pipe), C.byref(dc), tab, 25, C.byref(dc), tab, 26, C.byref(dw), tw, 4, C.byref(io), 8, C.c_void_p(4096), big, 0,
+                               None) == -1 and b'parameter tensors' in L.nrf_last_error()
+    assert L.nrf_train_forward(*args, C.byref(io), 8, C.c_void_p(4096), big, 0, None) == -1 and b'ray inputs' in L.nrf_last_error()
+    # image metrics / ray windows / per-ray bias
+    assert L.nrf_ssim(C.c_void_p(16), C.c_void_p(16), 3, 32, 32, C.c_void_p(16), 10, 1e-4, 9e-4, C.c_void_p(16), C.c_void_p(16), None, None) == -1
+    assert L.nrf_ssim(C.c_void_p(16), C.c_void_p(16), 3, 8, 32, C.c_void_p(16), 11, 1e-4, 9e-4, C.c_void_p(16), C.c_void_p(16), None, None) == -1
+    assert b"Kernel size can't be greater" in L.nrf_last_error()            # the reference's message (util/scores.py:147-149)
+    assert L.nrf_ssim_partial_floats(3, 64, 64, 11) == 3 * 2 * 16
+    cam = (C.c_double * 16)(*([0.0] * 16))
+    ptr = C.c_void_p(16)
+    assert L.nrf_generate_rays_range(8, 8, 1.0, cam, ptr, ptr, ptr, 4, 60, 8, ptr, ptr, ptr, ptr, None) == -1 and b'window' in L.nrf_last_error()
+    ca, fa, *_ = O.build_nets('append_full', 0)
+    dfull = engine.raynet_desc(ca, pe, de, False, True)
+    assert L.nrf_raynet_ext_slots(C.byref(dfull)) == 2
+    # fp16 hi/lo planes of 4096 feature rows and of two 256-row weight blocks, K = 1380 padded to 1408
+    assert L.nrf_ray_bias_workspace_bytes(C.byref(dfull), 4096) >= (4096 + 2 * 256) * 1408 * 4
+    assert L.nrf_train_launch_count(1) >= 0 and L.nrf_train_launch_count(0) == 0
+
+
+def test_grad_mode_routing_rule():
+    """train.needs_grad: differentiable path iff autograd records AND a net is in training mode AND a parameter requires grad."""
+    from smpl_nerf_b200 import train
+    c, f, w, *_ = O.build_nets('smpl', 0)          # build_nets leaves the nets in eval mode
+    assert not train.needs_grad(c, f, w)
+    c.train()
+    assert train.needs_grad(c, f, w) and train.needs_grad(c, None, None)
+    with torch.no_grad():
+        assert not train.needs_grad(c, f, w)
+    for p in c.parameters():
+        p.requires_grad_(False)
+    assert train.needs_grad(c, f, w)               # fine / warp parameters still require grad
+    for m in (f, w):
+        for p in m.parameters():
+            p.requires_grad_(False)
+    assert not train.needs_grad(c, f, w)
+
+
 def test_product_does_not_import_oracle():
     """The product package must never reach into oracle/ (only tests, smoke() and bench's CPU legs may)."""
     pkg = os.path.join(ROOT, 'smpl_nerf_b200')

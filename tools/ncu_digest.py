@@ -15,7 +15,7 @@ for h, u, v in zip(hdr, units, vals):
         if 'stalled' in h and float(v or 0) < 0.05: continue
         print(f'{h} [{u}] = {v}')
 rows = list(csv.reader(open(sass)))
-hdr = rows[1]; data = rows[2:]
+hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr) and r[hdr.index('# Samples')].isdigit()]
 iS = hdr.index('# Samples'); iSrc = hdr.index('Source'); iEx = hdr.index('Instructions Executed')
 tot = sum(int(r[iS]) for r in data)
 print('total samples', tot, 'static instrs', len(data), 'executed warp-instrs', sum(int(r[iEx]) for r in data))
