@@ -254,8 +254,8 @@ def run_reference(a, w, rank, world):
     cores = os.cpu_count() or 1
     line = {
         'impl': 'reference', 'device': a.device, 'metric': 'rays/sec', 'value': rps, 'unit': 'rays/s', 'n_gpus': a.gpus, 'steps': a.steps,
-        'warmup': a.warmup, 'ms_per_step': 1e3 * statistics.median(times), 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'warmup': a.warmup, 'ms_per_step': 1e3 * statistics.median(times), 'higher_is_better': True,
+        'scaling': 'strong' if w.get('strong') else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': w['text'], 'rays_per_step': batch, 'timing': 'time.perf_counter, median over steps'},
         'cpu_baseline': {'value': rps, 'unit': 'rays/s', 'cores': cores, 'kind': 'port', 'cpu': cpu_model(),
                          'sample': f'{a.steps} steps x {batch} rays of the workload, torch {torch.__version__} CPU, '
