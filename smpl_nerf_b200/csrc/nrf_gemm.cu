@@ -388,16 +388,23 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
   const uint32_t planes = P.passes == 3 ? 2u : 1u;
   const uint32_t a_bytes = 16384u, b_bytes = static_cast<uint32_t>(P.N) * 128u;       // one plane of one 64-sample stage
   const uint32_t stage_bytes = planes * (a_bytes + b_bytes);
-  GemmBars* bars = reinterpret_cast<GemmBars*>(smem + static_cast<uint32_t>(P.n_stages) * stage_bytes);
+  const uint32_t ones_bytes = P.colsum_partial ? 8192u : 0u;                            // [64 samples x 128 B] of fp16 1.0
+  const uint32_t smem_ones = smem_u32(smem) + static_cast<uint32_t>(P.n_stages) * stage_bytes;
+  GemmBars* bars = reinterpret_cast<GemmBars*>(smem + static_cast<uint32_t>(P.n_stages) * stage_bytes + ones_bytes);
   const int64_t n_chunks = (P.S + 63) / 64;
   const int m_tile = P.m0 + 128 * blockIdx.x;
+  if (P.colsum_partial) {      // every 16-byte chunk is the same, so the 128-byte swizzle leaves the tile unchanged
+    for (uint32_t i = threadIdx.x; i < 8192u / 16u; i += blockDim.x)
+      *reinterpret_cast<uint4*>(smem + static_cast<uint32_t>(P.n_stages) * stage_bytes + 16u * i) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&bars->a_full[s]), 1); mbar_init(smem_u32(&bars->a_empty[s]), 1); }
     mbar_init(smem_u32(&bars->acc_full[0]), 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<256>(smem_u32(&bars->tmem));
+  if (warp == 1) tmem_alloc<512>(smem_u32(&bars->tmem));      // columns [0, N): dW tile; [256, 272): column sums
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -428,6 +435,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     const uint32_t idesc = umma_idesc_f16_major(128, static_cast<uint32_t>(P.N), 1u, 1u);
+    const uint32_t idesc_cs = umma_idesc_f16_major(128, 16u, 1u, 1u);
     uint32_t stage = 0, phase = 0, accumulate = 0;
     for (int64_t c = blockIdx.y; c < n_chunks; c += gridDim.y) {
       mbar_wait(smem_u32(&bars->a_full[stage]), phase);
@@ -442,6 +450,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
           accumulate = 1;
         }
       }
+      if (P.colsum_partial) {      // bias gradient: (dY_hi + dY_lo)^T . ones, N = 16 (only column 0 is read back)
+        for (uint32_t pl = 0; pl < planes; ++pl) {
+          const uint32_t a = pl ? a_lo : a_hi;
+#pragma unroll
+          for (uint32_t ks = 0; ks < 4; ++ks)
+            umma_f16_ss_warp(tmem + 256u, umma_desc_mn_sw128(a + ks * 2048u, 8192u, 1024u), umma_desc_mn_sw128(smem_ones + ks * 2048u, 8192u, 1024u), idesc_cs,
+                             (c != static_cast<int64_t>(blockIdx.y) || pl || ks) ? 1u : 0u);
+        }
+      }
       umma_commit_warp(smem_u32(&bars->a_empty[stage]));
       if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
     }
@@ -453,6 +470,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
     tc_fence_after_sync();
     const int m = 128 * blockIdx.x + 32 * q + lane;
     float* dst = P.partial + (static_cast<size_t>(blockIdx.y) * P.M_total + m) * P.N;
+    if (P.colsum_partial) {
+      uint32_t v[16];
+      tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + 256u, v);
+      tmem_ld_wait();
+      P.colsum_partial[static_cast<size_t>(blockIdx.y) * P.M_total + m] = any ? __uint_as_float(v[0]) : 0.f;
+    }
     for (int g = 0; g < P.N / 16; ++g) {
       uint32_t v[16];
       tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + 16u * g, v);
@@ -465,7 +488,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem);
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -582,7 +605,7 @@ int dw_gemm_max_split(int n_sms, int M) {
 }
 
 int launch_dw_gemm(const Planes& a, int m0, int M, const Planes& b, int n0, int N, int passes, float* partial, int max_split,
-                   int* n_split_out, int n_sms, cudaStream_t stream) {
+                   int* n_split_out, int n_sms, cudaStream_t stream, float* colsum_partial) {
   static thread_local DwGemmParams P;
   memset(&P, 0, sizeof(P));
   if (passes != 1 && passes != 3) { set_error("dw_gemm: passes must be 1 or 3"); return NRF_E_INVALID; }
@@ -597,10 +620,11 @@ int launch_dw_gemm(const Planes& a, int m0, int M, const Planes& b, int n0, int 
     if ((rc = encode_planes_map(&P.a_lo, a.lo, a.rows, a.cols, a.ld, 64, 64)) != NRF_OK) return rc;
     if ((rc = encode_planes_map(&P.b_lo, b.lo, b.rows, b.cols, b.ld, 64, 64)) != NRF_OK) return rc;
   }
-  P.m0 = m0; P.n0 = n0; P.N = N; P.passes = passes; P.S = a.rows; P.partial = partial; P.M_total = M;
+  P.m0 = m0; P.n0 = n0; P.N = N; P.passes = passes; P.S = a.rows; P.partial = partial; P.M_total = M; P.colsum_partial = colsum_partial;
   const uint32_t planes = passes == 3 ? 2u : 1u;
   const uint32_t stage_bytes = planes * (16384u + static_cast<uint32_t>(N) * 128u);
-  int stages = static_cast<int>((kGemmSmemLimit - 256) / stage_bytes);
+  const uint32_t ones_bytes = colsum_partial ? 8192u : 0u;
+  int stages = static_cast<int>((kGemmSmemLimit - 256 - ones_bytes) / stage_bytes);
   P.n_stages = stages > 4 ? 4 : stages;
   const int64_t n_chunks = (a.rows + 63) / 64;
   int split = dw_gemm_max_split(n_sms, M);
@@ -610,7 +634,7 @@ int launch_dw_gemm(const Planes& a, int m0, int M, const Planes& b, int n0, int 
   *n_split_out = split;
   cudaError_t e = cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dw_gemm)");
-  dw_gemm_kernel<<<dim3(M / 128, split), kDwThreads, static_cast<uint32_t>(P.n_stages) * stage_bytes + 256, stream>>>(P);
+  dw_gemm_kernel<<<dim3(M / 128, split), kDwThreads, static_cast<uint32_t>(P.n_stages) * stage_bytes + ones_bytes + 256, stream>>>(P);
   ++g_train_launches;
   e = cudaGetLastError();
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "dw_gemm_kernel launch");

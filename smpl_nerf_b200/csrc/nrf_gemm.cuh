@@ -58,6 +58,8 @@ struct DwGemmParams {
   int64_t S;
   float* partial;                 // [n_split][M_total][N]
   int32_t M_total;
+  float* colsum_partial;          // optional [n_split][M_total]: sum over this CTA's samples of (hi + lo)[s, m] -- the bias gradient --
+                                  // from two extra N = 16 MMAs per K-step against a constant tile of ones (no extra pass over dY)
 };
 
 // host helpers (nrf_gemm.cu).  All return NRF_OK or an error code with the message set.
@@ -82,7 +84,7 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream);
 
 // dW[M, N] = sum_s A[s, m0 + m] * B[s, n0 + n]: partial sums per CTA into `partial` ([n_split][M][N] floats, n_split returned)
 int launch_dw_gemm(const Planes& a, int m0, int M, const Planes& b, int n0, int N, int passes, float* partial, int max_split,
-                   int* n_split_out, int n_sms, cudaStream_t stream);
+                   int* n_split_out, int n_sms, cudaStream_t stream, float* colsum_partial = nullptr);
 int dw_gemm_max_split(int n_sms, int M);
 
 }  // namespace nrf

@@ -89,7 +89,7 @@ struct TrainWs {
   PassWs pass[2];
   float *pose_feat, *dir_feat, *ray_norm, *weights_c, *alpha_c, *z_all, *pts_fine, *warp_pose_feat;
   Planes dy[2];
-  float *dysum, *g_encx, *g_encd, *g_warp, *partial;
+  float *dysum, *g_encx, *g_encd, *g_warp, *partial, *cs_partial;
   float* sc;               // [kScaleSlots][2]: {s, 1/s} of every gradient plane tensor of the backward chain
   unsigned int* mx;        // [kScaleSlots]: row-L1 bounds (float bits); mx[0] = max |d raw| over both passes
   unsigned int* wmax;      // [kWmaxSlots]: max |W| per (net, layer) activation block and per head (float bits; written by the forward)
@@ -147,6 +147,7 @@ static void layout_ws(Bump& m, const TrainCfg& c, const TNet net[2], TrainWs* ws
   if (c.smpl) { ws->g_encx = m.take<float>(static_cast<size_t>(Smax) * 64); ws->g_encd = m.take<float>(static_cast<size_t>(Smax) * 64);
                 ws->g_warp = m.take<float>(static_cast<size_t>(Smax) * 3); }
   ws->partial = m.take<float>(static_cast<size_t>(148) * 128 * 256);     // split x M x N <= (148 / (M / 128)) x M x 256
+  ws->cs_partial = m.take<float>(static_cast<size_t>(148) * 512);
   ws->sc = m.take<float>(2 * kScaleSlots);
   ws->mx = reinterpret_cast<unsigned int*>(m.take<float>(kScaleSlots));
   ws->wmax = reinterpret_cast<unsigned int*>(m.take<float>(kWmaxSlots));
@@ -402,7 +403,8 @@ static int forward_all(TrainCtx& t) {
 // ------------------------------------------------------------------------------ backward
 struct Grads { float* const* g[3]; };
 
-static int dw_into(TrainCtx& t, const Planes& dy, const float* sc, int M, const Planes& x, int n0, int N, int cols, float* dst, int ld, int col0) {
+static int dw_into(TrainCtx& t, const Planes& dy, const float* sc, int M, const Planes& x, int n0, int N, int cols, float* dst, int ld, int col0,
+                   float* db = nullptr) {
   // dW[M, cols] += dY^T X[:, n0 : n0 + N], in blocks of at most 256 X columns (one TMEM accumulator); M < 128 (the 64-wide layers of
   // a width-128 net) runs as one 128-row tile whose upper half multiplies zero-filled (out-of-bounds) dY columns and is dropped
   const int Mp = (M + 127) & ~127;
@@ -411,9 +413,14 @@ static int dw_into(TrainCtx& t, const Planes& dy, const float* sc, int M, const 
     const int cb = cols - nb < Nb ? cols - nb : Nb;
     if (cb <= 0) break;
     int split = 0;
-    TRY(launch_dw_gemm(dy, 0, Mp, x, n0 + nb, Nb, t.c.passes, t.ws.partial, 148, &split, t.n_sms, t.st));
+    const bool with_db = db != nullptr && nb == 0;       // the bias gradient rides on the first block: (dY_hi + dY_lo)^T . ones
+    TRY(launch_dw_gemm(dy, 0, Mp, x, n0 + nb, Nb, t.c.passes, t.ws.partial, 148, &split, t.n_sms, t.st, with_db ? t.ws.cs_partial : nullptr));
     dw_reduce_kernel<<<grid1(static_cast<int64_t>(M) * cb, 256), 256, 0, t.st>>>(t.ws.partial, split, Mp, M, Nb, cb, sc, dst, ld, col0 + nb);
     LAUNCH_CHECK("dw_reduce_kernel");
+    if (with_db) {
+      colsum_reduce_kernel<<<(M + 127) / 128, 128, 0, t.st>>>(t.ws.cs_partial, split, Mp, M, sc, db);
+      LAUNCH_CHECK("colsum_reduce_kernel");
+    }
   }
   return NRF_OK;
 }
@@ -474,10 +481,14 @@ static int backward_pass(TrainCtx& t, int p, const Grads& G) {
     const float* sc = SC(slot);
     dy = view(t.ws.dy[cur], L.n_out, w.S);
     // parameter gradients
-    if (L.in_act) TRY(dw_into(t, dy, sc, L.n_out, w.act[l - 1], 0, L.in_act, L.in_act, dW, L.ld, L.col_act));
-    if (L.aux) TRY(dw_into(t, dy, sc, L.n_out, L.aux == 1 ? w.encx : w.encd, 0, 64, L.aux_cols, dW, L.ld, L.col_aux));
-    TRY(colsum_and_bias(t, dy, sc, L.n_out, w.n, db));
-    if (L.ray_src) TRY(rayfeat_dw(t, sc, L.ray_src == 1 ? t.ws.pose_feat : t.ws.dir_feat, L.n_out, L.ray_k, dW, L.ld, L.col_ray));
+    // (the bias gradient comes out of the first dW GEMM of the layer; layers with per-ray inputs need the per-ray sums of dY anyway)
+    float* db_gemm = L.ray_src ? nullptr : db;
+    if (L.in_act) { TRY(dw_into(t, dy, sc, L.n_out, w.act[l - 1], 0, L.in_act, L.in_act, dW, L.ld, L.col_act, db_gemm)); db_gemm = nullptr; }
+    if (L.aux) TRY(dw_into(t, dy, sc, L.n_out, L.aux == 1 ? w.encx : w.encd, 0, 64, L.aux_cols, dW, L.ld, L.col_aux, db_gemm));
+    if (L.ray_src) {
+      TRY(colsum_and_bias(t, dy, sc, L.n_out, w.n, db));
+      TRY(rayfeat_dw(t, sc, L.ray_src == 1 ? t.ws.pose_feat : t.ws.dir_feat, L.n_out, L.ray_k, dW, L.ld, L.col_ray));
+    }
     // gradient of the encodings (only the SMPL pipeline differentiates them: they are functions of the warp net); REAL units
     if (c.smpl && L.aux) {
       TileGemmArgs a{};

@@ -391,6 +391,14 @@ __global__ void rayfeat_dw_kernel(const float* __restrict__ dysum, const float* 
   }
   if (k < K && n < n_out) dW[static_cast<size_t>(n) * ld + col0 + k] += acc * __ldg(scale2 + 1);
 }
+// db[m] += inv_scale * sum_split colsum_partial[split][m]      (the ones-column of dw_gemm)
+__global__ void colsum_reduce_kernel(const float* __restrict__ partial, int n_split, int Mp, int M, const float* __restrict__ scale2, float* __restrict__ db) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float acc = 0.f;
+  for (int s = 0; s < n_split; ++s) acc += partial[static_cast<size_t>(s) * Mp + m];
+  db[m] += acc * __ldg(scale2 + 1);
+}
 // dst[m, col0 + c] += inv_scale * sum_split partial[split][m][c]        (m < M <= Mp rows of the partials, c < cols <= N)
 __global__ void dw_reduce_kernel(const float* __restrict__ partial, int n_split, int Mp, int M, int N, int cols, const float* __restrict__ scale2,
                                  float* __restrict__ dst, int ld, int col0) {
