@@ -441,8 +441,8 @@ static int rayfeat_dw(TrainCtx& t, const float* sc, const float* feat, int n_out
 
 static int head_bwd(TrainCtx& t, const float* x, int64_t S, int K, const float* g, int g_ld, int c0, int nh, const float* W, const float* sc_out,
                     int relu_mask, float* dW, float* db, const Planes* dy, unsigned int* l1max) {
-  const int rows = 128;
-  head_bwd_kernel<<<static_cast<unsigned>((S + rows - 1) / rows), K < 32 ? 32 : K, 0, t.st>>>(x, S, K, g, g_ld, c0, nh, W, sc_out, relu_mask, dW, db,
+  const int rows = 256;           // K in {64, 128, 256, 512}: 256 threads = 1024 / K rows in flight
+  head_bwd_kernel<<<static_cast<unsigned>((S + rows - 1) / rows), 256, 0, t.st>>>(x, S, K, g, g_ld, c0, nh, W, sc_out, relu_mask, dW, db,
                                                                                   dy ? dy->hi : nullptr, dy ? dy->lo : nullptr, dy ? dy->ld : 0, rows, l1max);
   LAUNCH_CHECK("head_bwd_kernel");
   return NRF_OK;

@@ -193,49 +193,88 @@ __global__ void heads_kernel(const float* __restrict__ x, int64_t S, int K, cons
   }
 }
 
-// Backward of a head over a block of rows: thread = input feature k.
+// Backward of a head over a block of rows.  thread = 4 consecutive input features of one row group (K / 4 threads per row,
+// 1024 / K rows in flight per CTA): 16-byte loads of x, 8-byte stores of the gradient planes.
 //   dW[c, k] += sum_s g[s, c] x[s, k]      db[c] += sum_s g[s, c]      dY[s, k] = sum_c g[s, c] W[c, k]   (-> planes, masked by x > 0)
-// g is the upstream gradient in REAL units (fp32); the planes are written as real * sc_out[0].  l1max: see TileGemmParams.
-__global__ void head_bwd_kernel(const float* __restrict__ x, int64_t S, int K, const float* __restrict__ g, int g_ld, int c0, int nh,
-                                const float* __restrict__ W, const float* __restrict__ sc_out, int relu_mask,
-                                float* __restrict__ dW, float* __restrict__ db, __half* __restrict__ dy_hi, __half* __restrict__ dy_lo, int dy_ld,
-                                int rows_per_block, unsigned int* __restrict__ l1max) {
-  const int k = threadIdx.x;
+// g is the upstream gradient in REAL units (fp32); the planes are written as real * sc_out[0].  l1max: see TileGemmParams (here the
+// row segment is a warp's 128 columns).
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ x, int64_t S, int K, const float* __restrict__ g, int g_ld, int c0, int nh,
+                                                       const float* __restrict__ W, const float* __restrict__ sc_out, int relu_mask,
+                                                       float* __restrict__ dW, float* __restrict__ db, __half* __restrict__ dy_hi,
+                                                       __half* __restrict__ dy_lo, int dy_ld, int rows_per_block, unsigned int* __restrict__ l1max) {
+  __shared__ float red[3][1024];
+  const int tpr = K >> 2;                                 // threads per row
+  const int rg = threadIdx.x / tpr, n_rg = blockDim.x / tpr, k4 = (threadIdx.x - rg * tpr) * 4;
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   const float sc = sc_out ? __ldg(sc_out) : 1.f;
-  float l1_run = 0.f;
-  float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-  if (k < K) { w0 = W[k]; if (nh > 1) { w1 = W[K + k]; w2 = W[2 * K + k]; } }
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-  for (int64_t s = r0; s < r0 + rows_per_block && s < S; ++s) {
-    const float g0 = g[s * g_ld + c0], g1 = nh > 1 ? g[s * g_ld + c0 + 1] : 0.f, g2 = nh > 1 ? g[s * g_ld + c0 + 2] : 0.f;
+  float4 w0 = *reinterpret_cast<const float4*>(W + k4), w1 = make_float4(0.f, 0.f, 0.f, 0.f), w2 = w1;
+  if (nh > 1) { w1 = *reinterpret_cast<const float4*>(W + K + k4); w2 = *reinterpret_cast<const float4*>(W + 2 * K + k4); }
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+  float b0 = 0.f, b1 = 0.f, b2 = 0.f, l1_run = 0.f;
+  for (int it = 0; it * n_rg < rows_per_block; ++it) {      // uniform trip count: the warp shuffles below need every lane
+    const int64_t s = r0 + static_cast<int64_t>(it) * n_rg + rg;
+    const bool ok = s < r0 + rows_per_block && s < S;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+      g0 = g[s * g_ld + c0];
+      if (nh > 1) { g1 = g[s * g_ld + c0 + 1]; g2 = g[s * g_ld + c0 + 2]; }
+      xv = *reinterpret_cast<const float4*>(x + s * K + k4);
+    }
     b0 += g0; b1 += g1; b2 += g2;
-    float dy = 0.f;
-    if (k < K) {
-      const float xv = x[s * K + k];
-      a0 = fmaf(g0, xv, a0); a1 = fmaf(g1, xv, a1); a2 = fmaf(g2, xv, a2);
-      if (dy_hi) {
-        dy = fmaf(g0, w0, fmaf(g1, w1, g2 * w2));
-        if (relu_mask && !(xv > 0.f)) dy = 0.f;
-        split_store(dy * sc, dy_hi + s * dy_ld + k, dy_lo ? dy_lo + s * dy_ld + k : nullptr);
+    a0.x = fmaf(g0, xv.x, a0.x); a0.y = fmaf(g0, xv.y, a0.y); a0.z = fmaf(g0, xv.z, a0.z); a0.w = fmaf(g0, xv.w, a0.w);
+    if (nh > 1) {
+      a1.x = fmaf(g1, xv.x, a1.x); a1.y = fmaf(g1, xv.y, a1.y); a1.z = fmaf(g1, xv.z, a1.z); a1.w = fmaf(g1, xv.w, a1.w);
+      a2.x = fmaf(g2, xv.x, a2.x); a2.y = fmaf(g2, xv.y, a2.y); a2.z = fmaf(g2, xv.z, a2.z); a2.w = fmaf(g2, xv.w, a2.w);
+    }
+    if (dy_hi) {
+      float d[4] = {fmaf(g0, w0.x, fmaf(g1, w1.x, g2 * w2.x)), fmaf(g0, w0.y, fmaf(g1, w1.y, g2 * w2.y)),
+                    fmaf(g0, w0.z, fmaf(g1, w1.z, g2 * w2.z)), fmaf(g0, w0.w, fmaf(g1, w1.w, g2 * w2.w))};
+      if (relu_mask) {
+        if (!(xv.x > 0.f)) d[0] = 0.f;
+        if (!(xv.y > 0.f)) d[1] = 0.f;
+        if (!(xv.z > 0.f)) d[2] = 0.f;
+        if (!(xv.w > 0.f)) d[3] = 0.f;
+      }
+      __align__(8) __half h[4];
+      __align__(8) __half l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_store(d[i] * sc, &h[i], &l[i]);
+      if (ok) {
+        *reinterpret_cast<uint2*>(dy_hi + s * dy_ld + k4) = *reinterpret_cast<const uint2*>(h);
+        if (dy_lo) *reinterpret_cast<uint2*>(dy_lo + s * dy_ld + k4) = *reinterpret_cast<const uint2*>(l);
+      }
+      if (l1max) {          // L1 norm of this warp's 128 columns of the row (real units); a warp never straddles two rows (K >= 128) ...
+        float a = fabsf(d[0]) + fabsf(d[1]) + fabsf(d[2]) + fabsf(d[3]);
+        const int span = tpr < 32 ? tpr : 32;          // ... and for K = 64 a row is 16 lanes
+        for (int o = span >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        l1_run = fmaxf(l1_run, a);
       }
     }
-    if (l1max) {          // L1 norm of this warp's 32 columns of the row (real units)
-      float a = fabsf(dy);
+  }
+  if (l1max && isfinite(l1_run)) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      l1_run = fmaxf(l1_run, a);
-    }
+    for (int o = 16; o > 0; o >>= 1) l1_run = fmaxf(l1_run, __shfl_xor_sync(0xffffffffu, l1_run, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(l1max, __float_as_uint(l1_run * static_cast<float>((K + 127) / 128)));
   }
-  if (l1max && (threadIdx.x & 31) == 0 && isfinite(l1_run)) atomicMax(l1max, __float_as_uint(l1_run * static_cast<float>((K + 31) / 32)));
-  const float f = 1.f;
-  if (k < K) {
-    atomicAdd(dW + k, a0 * f);
-    if (nh > 1) { atomicAdd(dW + K + k, a1 * f); atomicAdd(dW + 2 * K + k, a2 * f); }
+  // fold the row groups of the CTA, then one atomic per (head, feature)
+  float* ra[3] = {red[0], red[1], red[2]};
+  const float4 acc[3] = {a0, a1, a2};
+  for (int c = 0; c < nh; ++c) *reinterpret_cast<float4*>(ra[c] + rg * K + k4) = acc[c];
+  __syncthreads();
+  for (int i = threadIdx.x; i < nh * K; i += blockDim.x) {
+    const int c = i / K, k = i - c * K;
+    float t = 0.f;
+    for (int r = 0; r < n_rg; ++r) t += ra[c][r * K + k];
+    atomicAdd(dW + c * K + k, t);
   }
-  if (k == 0) {
-    atomicAdd(db, b0 * f);
-    if (nh > 1) { atomicAdd(db + 1, b1 * f); atomicAdd(db + 2, b2 * f); }
+  __syncthreads();
+  if (k4 == 0) { red[0][rg] = b0; red[1][rg] = b1; red[2][rg] = b2; }
+  __syncthreads();
+  if (threadIdx.x < nh) {
+    float t = 0.f;
+    for (int r = 0; r < n_rg; ++r) t += red[threadIdx.x][r];
+    atomicAdd(db + threadIdx.x, t);
   }
 }
 
