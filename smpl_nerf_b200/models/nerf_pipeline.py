@@ -37,7 +37,7 @@ class NerfPipeline(SmplPipeline):
         """Raise if an activation of the LAST call left the fp16 range (|x| > 65504): the fp16 hi/lo operand split
         saturates there, so the result would silently deviate from the fp32 reference.  Synchronises the device."""
         st = getattr(self, '_status', None)
-        if st is not None and int(st.item()) & 1:
+        if st is not None and int(st.item()) & 3:          # bit 0: fused kernel (activation or packed weight), bit 1: layer-by-layer path
             raise FloatingPointError('smpl_nerf_b200: a hidden activation exceeded the fp16 range (65504), which the fp16 hi/lo '
                                      'operand split cannot represent -- set pipeline.precision = 2 (exact mode: bf16 x 3 planes '
                                      'with fp32\'s exponent range) for this net')
