@@ -13,6 +13,7 @@
 // Warp roles: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (converged warp, elected lane), the rest = epilogue
 // (TMEM lane quarter = warp % 4).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_bf16.h>
@@ -45,75 +46,98 @@ __device__ __forceinline__ uint32_t cvt_f16x2_satfinite(float x0, float x1) {
 struct GemmBars { uint64_t b_full, a_full[4], a_empty[4], acc_full[2], acc_empty[2]; uint32_t tmem; uint32_t pad; };
 
 // ------------------------------------------------------------------------------------------------ tile GEMM
-template <bool kExact>
+// kExact: bf16 x 3 planes, six passes, per-chunk accumulators (see below).  kPair: the CTA runs as one half of a CTA PAIR
+// (cluster of 2, tcgen05 cta_group::2): every MMA is M = 256 -- 128 sample rows of each CTA -- by N = n_tile (128 or 256), each CTA
+// keeps only ITS half of the weight slice resident and streams only its own rows of A.  Per byte of A streamed the pair does twice
+// the MMA work of a single CTA with a 128-column slice (1,536 instead of 768 tensor cycles per 32 KB chunk), which is what lets a
+// 2-stage ring keep up with the L2 latency; A is also read once instead of once per 128-column slice.
+template <bool kExact, bool kPair>
 __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid_constant__ TileGemmParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const uint32_t planes = P.passes == 6 ? 3u : (P.passes == 3 ? 2u : 1u);
   const int nk = P.kc[0] + (P.n_src > 1 ? P.kc[1] : 0);
-  const uint32_t b_chunk = static_cast<uint32_t>(P.n_tile) * 128u;
+  const int n_cta = kPair ? P.n_tile / 2 : P.n_tile;                    // weight rows (output features) staged by THIS CTA
+  const uint32_t b_chunk = static_cast<uint32_t>(n_cta) * 128u;
   const uint32_t b_bytes = P.b_stream ? 0u : static_cast<uint32_t>(nk) * planes * b_chunk;
   const uint32_t a_stage = planes * kATile + (P.b_stream ? planes * b_chunk : 0u);      // streaming mode: [A planes | B planes] per stage
   const uint32_t smem_b = smem_u32(smem), smem_a = smem_b + b_bytes;
-  const uint32_t out_bytes = P.staged ? static_cast<uint32_t>(P.n_tile) * 256u : 0u;       // one [128 x n_tile] fp16 plane of the output tile
+  const int cols_pass = P.n_tile < 128 ? P.n_tile : 128;                // the epilogue walks the accumulator in passes of <= 128 columns
+  const int n_cpass = P.n_tile / cols_pass;
+  const uint32_t out_bytes = P.staged ? static_cast<uint32_t>(cols_pass) * 256u : 0u;    // one [128 x cols_pass] fp16 plane of the output tile
   const uint32_t smem_o = smem_a + static_cast<uint32_t>(P.n_stages) * a_stage;
   GemmBars* bars = reinterpret_cast<GemmBars*>(smem + b_bytes + static_cast<uint32_t>(P.n_stages) * a_stage + out_bytes);
   const int n0 = blockIdx.y * P.n_tile;
-  const int64_t n_mt = (P.S + 127) / 128;
+  const int rows_tile = kPair ? 256 : 128;
+  const int64_t n_mt = (P.S + rows_tile - 1) / rows_tile;
+  const int64_t mt0 = kPair ? (blockIdx.x >> 1) : blockIdx.x, mt_step = kPair ? (gridDim.x >> 1) : gridDim.x;
 
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bars->b_full), 1);
     for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&bars->a_full[s]), 1); mbar_init(smem_u32(&bars->a_empty[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bars->acc_full[b]), 1); mbar_init(smem_u32(&bars->acc_empty[b]), 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bars->acc_full[b]), 1); mbar_init(smem_u32(&bars->acc_empty[b]), kPair ? 16 : 8); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(smem_u32(&bars->tmem));      // exact mode: 2 buffers x (main, correction) x n_tile columns
+  if (warp == 1) { if (kPair) tmem_alloc2<512>(smem_u32(&bars->tmem)); else tmem_alloc<512>(smem_u32(&bars->tmem)); }
   tc_fence_before_sync();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();       // pair: both CTAs' barriers exist before any remote arrival
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem;
 
   if (warp == 0) {
     if (lane == 0) {
+      // pair: both CTAs' bytes are credited to the barrier of the ISSUING (rank 0) CTA, whose producer announces the total
+      auto bar_of = [&](uint64_t* b) { return kPair ? mapa_shared(smem_u32(b), 0) : smem_u32(b); };
+      auto load = [&](uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+        if (kPair) tma2_load_2d(dst, map, c0, c1, bar); else tma_load_2d(dst, map, c0, c1, bar);
+      };
+      const int nb0 = n0 + static_cast<int>(rank) * n_cta;             // first output feature of this CTA's weight rows
       auto load_b = [&](int j, int lc, uint32_t dst0, uint32_t bar) {
         for (uint32_t p = 0; p < planes; ++p) {
           const CUtensorMap* map = &P.b_map[j][p];
           const uint32_t dst = dst0 + p * b_chunk;
-          if (!P.b_mn) tma_load_2d(dst, map, 64 * lc, n0, bar);
-          else for (int g = 0; g < P.n_tile / 64; ++g) tma_load_2d(dst + g * 8192u, map, n0 + 64 * g, 64 * lc, bar);
+          if (!P.b_mn) load(dst, map, 64 * lc, nb0, bar);
+          else for (int g = 0; g < n_cta / 64; ++g) load(dst + g * 8192u, map, nb0 + 64 * g, 64 * lc, bar);
         }
       };
+      const uint32_t mult = kPair ? 2u : 1u;
       // ---- resident weight slice
       if (!P.b_stream) {
-        mbar_arrive_expect_tx(smem_u32(&bars->b_full), b_bytes);
+        if (rank == 0) mbar_arrive_expect_tx(smem_u32(&bars->b_full), mult * b_bytes);
         int c = 0;
         for (int j = 0; j < P.n_src; ++j)
-          for (int lc = 0; lc < P.kc[j]; ++lc, ++c) load_b(j, lc, smem_b + static_cast<uint32_t>(c) * planes * b_chunk, smem_u32(&bars->b_full));
+          for (int lc = 0; lc < P.kc[j]; ++lc, ++c) load_b(j, lc, smem_b + static_cast<uint32_t>(c) * planes * b_chunk, bar_of(&bars->b_full));
       }
       // ---- sample tiles
       uint32_t stage = 0, phase = 0;
-      for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x)
+      for (int64_t mt = mt0; mt < n_mt; mt += mt_step)
         for (int j = 0; j < P.n_src; ++j)
           for (int lc = 0; lc < P.kc[j]; ++lc) {
             mbar_wait(smem_u32(&bars->a_empty[stage]), phase ^ 1);
-            mbar_arrive_expect_tx(smem_u32(&bars->a_full[stage]), a_stage);
+            if (rank == 0) mbar_arrive_expect_tx(smem_u32(&bars->a_full[stage]), mult * a_stage);
             const uint32_t dst = smem_a + stage * a_stage;
-            for (uint32_t p = 0; p < planes; ++p)
-              tma_load_2d(dst + p * kATile, &P.a_map[j][p], 64 * lc, static_cast<int32_t>(mt * 128), smem_u32(&bars->a_full[stage]));
+            const int32_t r0 = static_cast<int32_t>(mt * rows_tile + rank * 128);
+            for (uint32_t p = 0; p < planes; ++p) load(dst + p * kATile, &P.a_map[j][p], 64 * lc, r0, bar_of(&bars->a_full[stage]));
             // the activation planes stream from HBM (hundreds of MB per layer): pull this CTA's tile-after-next into L2 now, so the
             // 2-3 deep ring is refilled at L2 latency
-            const int64_t pf = mt + 2 * static_cast<int64_t>(gridDim.x);
-            if (pf < n_mt) for (uint32_t p = 0; p < planes; ++p) tma_prefetch_2d(&P.a_map[j][p], 64 * lc, static_cast<int32_t>(pf * 128));
-            if (P.b_stream) load_b(j, lc, dst + planes * kATile, smem_u32(&bars->a_full[stage]));
+            const int64_t pf = mt + 2 * mt_step;
+            if (pf < n_mt) for (uint32_t p = 0; p < planes; ++p) tma_prefetch_2d(&P.a_map[j][p], 64 * lc, static_cast<int32_t>(pf * rows_tile + rank * 128));
+            if (P.b_stream) load_b(j, lc, dst + planes * kATile, bar_of(&bars->a_full[stage]));
             if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
           }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_f16_major(128, static_cast<uint32_t>(P.n_tile), 0u, P.b_mn ? 1u : 0u) | (kExact ? ((1u << 7) | (1u << 10)) : 0u);
+    if (rank == 0) {      // (the issuer warp of the odd CTA of a pair idles)
+    const uint32_t idesc = umma_idesc_f16_major(kPair ? 256u : 128u, static_cast<uint32_t>(P.n_tile), 0u, P.b_mn ? 1u : 0u) | (kExact ? ((1u << 7) | (1u << 10)) : 0u);
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc_flag) {
+      if (kPair) umma2_f16_ss_warp(d, ad, bd, idesc, acc_flag); else umma_f16_ss_warp(d, ad, bd, idesc, acc_flag);
+    };
+    auto commit = [&](uint64_t* b) { if (kPair) umma2_commit_warp(smem_u32(b)); else umma_commit_warp(smem_u32(b)); };
     if (!P.b_stream) mbar_wait(smem_u32(&bars->b_full), 0);
     tc_fence_after_sync();
     uint32_t stage = 0, phase = 0, it = 0;      // it: accumulator hand-offs so far (one per tile; one per K-chunk in the exact mode)
-    for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x) {
+    for (int64_t mt = mt0; mt < n_mt; mt += mt_step) {
       uint32_t buf = it & 1u, acc = 0, accumulate = 0;
       if (!kExact) {
         mbar_wait(smem_u32(&bars->acc_empty[buf]), ((it >> 1) & 1u) ^ 1u);
@@ -145,39 +169,46 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks) {
             const uint64_t bd = P.b_mn ? umma_desc_mn_sw128(b + ks * 2048u, 8192u, 1024u) : umma_desc_sw128(b) + 2u * ks;
-            umma_f16_ss_warp(dst, ad + 2u * ks, bd, idesc, accumulate);
+            mma(dst, ad + 2u * ks, bd, accumulate);
             accumulate = 1;
           }
         }
-        umma_commit_warp(smem_u32(&bars->a_empty[stage]));
+        commit(&bars->a_empty[stage]);
         if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
-        if (kExact) { umma_commit_warp(smem_u32(&bars->acc_full[buf])); ++it; }
+        if (kExact) { commit(&bars->acc_full[buf]); ++it; }
       }
-      if (!kExact) { umma_commit_warp(smem_u32(&bars->acc_full[buf])); ++it; }
+      if (!kExact) { commit(&bars->acc_full[buf]); ++it; }
+    }
     }
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const int cols_w = P.n_tile / 2;
+    const int cols_w = cols_pass / 2;
     const float s_out = P.sc_out ? __ldg(P.sc_out) : 1.f, inv_out = P.sc_out ? __ldg(P.sc_out + 1) : 1.f;
     const float ratio = (P.epi == GEPI_F32 ? 1.f : s_out) * (P.sc_in ? __ldg(P.sc_in + 1) : 1.f);     // stored-in -> stored-out (or real)
     const bool rescale = P.sc_in != nullptr || P.sc_out != nullptr;
     float l1_run = 0.f;
     bool saturated = false;
     uint32_t it = 0;
-    for (int64_t mt = blockIdx.x; mt < n_mt; mt += gridDim.x) {
+    const bool e0 = warp == 2 && lane == 0;
+    const int r_t = 32 * q + lane;                        // row inside this CTA's 128 rows of the tile
+    int tr_n = 0;
+    auto TR = [&](int ev) { if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && e0 && tr_n < 600) { P.trace[2 * tr_n] = ev; P.trace[2 * tr_n + 1] = clock64(); ++tr_n; } };
+    for (int64_t mt = mt0; mt < n_mt; mt += mt_step) {
       uint32_t buf = it & 1u;
-      const int64_t row = mt * 128 + 32 * q + lane;
+      TR(0);
+      const int64_t row = mt * rows_tile + rank * 128 + r_t;
       const bool row_ok = row < P.S;
       const float* bias_row = P.bias ? P.bias + (P.bias_ld ? (row_ok ? row / P.rows_per_ray : 0) * P.bias_ld : 0) : nullptr;
       const float rs = (P.row_scale && row_ok) ? P.row_scale[row * P.row_scale_ld] * s_out : 0.f;
       float l1 = 0.f;
+      for (int cp = 0; cp < n_cpass; ++cp) {
       // this thread's cols_w (<= 64) output columns start from the bias: its global loads (and the ReLU' mask's) are issued
       // BEFORE the wait for the accumulator, so their latency hides behind the MMAs (loading them per 16-column group after the
       // TMEM read made the epilogue the bottleneck: long-scoreboard stalls on every group, profiles/r2).  In the exact mode the
       // K-chunks are then added onto it with round-to-nearest.
       float sum[64];
       uint4 mk[2], mk_next[2];       // ReLU' mask of the current / the next 16-column group (fetched one group ahead)
-      const int col0 = n0 + half * cols_w;
+      const int col0 = n0 + cp * cols_pass + half * cols_w;
       const uint4* mask_row = (P.mask_hi && row_ok) ? reinterpret_cast<const uint4*>(P.mask_hi + row * P.mask_ld + col0) : nullptr;
       mk_next[0] = mk_next[1] = make_uint4(0u, 0u, 0u, 0u);
       if (mask_row) { mk_next[0] = __ldg(mask_row); mk_next[1] = __ldg(mask_row + 1); }
@@ -212,21 +243,21 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
         }
-      } else {
+      } else if (cp == 0) {
         mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
         tc_fence_after_sync();
       }
-      const uint32_t taddr = tmem + buf * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(half * cols_w);
+      TR(1);
+      const uint32_t taddr = tmem + buf * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(cp * cols_pass + half * cols_w);
       // staged epilogue: the output tile goes through shared memory ([128 rows x 64 cols] SWIZZLE_128B blocks) and leaves as TMA
       // stores -- a thread owns ONE ROW, so direct 16-byte stores hit 32 different rows per instruction (32 half-used sectors:
       // the load/store unit, not the tensor pipe, then sets the tile time; profiles/r2)
       uint32_t lreg[32];
-      const bool e0 = warp == 2 && lane == 0;
-      const int r_t = 32 * q + lane;                      // row inside the tile
-      if (P.staged) {                                     // the previous tile's lo plane has been read out of the staging buffer
+      if (P.staged) {                                     // the previous plane has been read out of the staging buffer
         if (e0) tma_store_wait_read();
         named_bar_sync(1, 256);
       }
+      TR(2);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (g >= cols_w / 16) continue;
@@ -241,7 +272,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(sum[16 * g + i]);
         }
         if (!row_ok) continue;
-        const int col = n0 + half * cols_w + 16 * g;
+        const int col = col0 + 16 * g;
         float x[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
@@ -305,7 +336,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             }
           }
           if (P.staged) {
-            const int ct = half * cols_w + 16 * g;        // column inside the tile -> 64-column block, 16-byte chunk
+            const int ct = half * cols_w + 16 * g;        // column inside the pass -> 64-column block, 16-byte chunk
             const uint32_t blk = smem_o + static_cast<uint32_t>(ct >> 6) * 16384u + static_cast<uint32_t>(r_t) * 128u;
             const uint32_t ch = static_cast<uint32_t>(ct & 63) >> 3;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch) ^ (r_t & 7u)) << 4)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
@@ -331,24 +362,28 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           }
         }
       }
-      l1_run = fmaxf(l1_run, l1);
-      if (!kExact) {
+      if (!kExact && cp == n_cpass - 1) {                  // the accumulator has been read completely: hand it back to the issuer
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
+        if (lane == 0) { if (kPair && rank != 0) mbar_arrive_cluster_relaxed(smem_u32(&bars->acc_empty[buf]), 0); else mbar_arrive(smem_u32(&bars->acc_empty[buf])); }
         ++it;
       }
       if (P.staged) {
-        const int32_t r0 = static_cast<int32_t>(mt * 128);
+        const int32_t r0 = static_cast<int32_t>(mt * rows_tile + rank * 128);
+        const int32_t c0 = n0 + cp * cols_pass;
+        TR(3);
         fence_proxy_async_smem();
-        named_bar_sync(1, 256);                            // hi plane of the tile is in the staging buffer
+        named_bar_sync(1, 256);                            // hi plane of this pass is in the staging buffer
+        TR(4);
         if (e0) {
-          for (int b = 0; b < P.n_tile / 64; ++b) tma_store_2d(&P.o_map[0], n0 + 64 * b, r0, smem_o + static_cast<uint32_t>(b) * 16384u);
+          for (int b = 0; b < cols_pass / 64; ++b) tma_store_2d(&P.o_map[0], c0 + 64 * b, r0, smem_o + static_cast<uint32_t>(b) * 16384u);
           tma_store_commit();
           if (P.out_lo) tma_store_wait_read();
         }
+        TR(5);
         if (P.out_lo) {
           named_bar_sync(1, 256);                          // ... and has been read: the lo plane takes its place
+          TR(6);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (g >= cols_w / 16) continue;
@@ -358,18 +393,23 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch) ^ (r_t & 7u)) << 4)), "r"(lreg[8 * g]), "r"(lreg[8 * g + 1]), "r"(lreg[8 * g + 2]), "r"(lreg[8 * g + 3]) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch + 1u) ^ (r_t & 7u)) << 4)), "r"(lreg[8 * g + 4]), "r"(lreg[8 * g + 5]), "r"(lreg[8 * g + 6]), "r"(lreg[8 * g + 7]) : "memory");
           }
+          TR(7);
           fence_proxy_async_smem();
           named_bar_sync(1, 256);
+          TR(8);
           if (e0) {
-            for (int b = 0; b < P.n_tile / 64; ++b) tma_store_2d(&P.o_map[1], n0 + 64 * b, r0, smem_o + static_cast<uint32_t>(b) * 16384u);
+            for (int b = 0; b < cols_pass / 64; ++b) tma_store_2d(&P.o_map[1], c0 + 64 * b, r0, smem_o + static_cast<uint32_t>(b) * 16384u);
             tma_store_commit();
           }
         }
       }
+      }   // column passes
+      l1_run = fmaxf(l1_run, l1);
     }
-    if (P.staged && warp == 2 && lane == 0) tma_store_wait_all();
+    if (P.staged && e0) tma_store_wait_all();
     if (P.l1max) {
-      l1_run *= (P.epi == GEPI_F32 ? 1.f : inv_out) * static_cast<float>(gridDim.y * 2);     // real units; 2 column segments per slice
+      // real units; a row's L1 norm is bounded by (number of column segments it is split into) x the largest segment sum
+      l1_run *= (P.epi == GEPI_F32 ? 1.f : inv_out) * static_cast<float>(gridDim.y * 2);       // two column halves (warp groups) per slice
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) l1_run = fmaxf(l1_run, __shfl_xor_sync(0xffffffffu, l1_run, o));
       if (lane == 0 && isfinite(l1_run)) atomicMax(P.l1max, __float_as_uint(l1_run));
@@ -377,8 +417,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
     if (saturated && P.status) atomicOr(P.status, 2);
   }
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem);
+  if (kPair) cluster_sync_all(); else __syncthreads();       // pair: neither CTA may exit (or free TMEM) while its peer can still address it
+  if (warp == 1) { if (kPair) tmem_dealloc2<512>(tmem); else tmem_dealloc<512>(tmem); }
 }
 
 // ------------------------------------------------------------------------------------------------ dW GEMM (split-K over samples)
@@ -537,16 +577,36 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
   if (a.N < 64 || (a.N & 63)) { set_error("tile_gemm: N = %d must be a multiple of 64", a.N); return NRF_E_INVALID; }
   const int64_t S = a.a[0].rows;
   if (S <= 0) return NRF_OK;
-  P.n_tile = (a.N % 128 == 0) ? 128 : 64;
+  int rc, sms;
+  if ((rc = device_sms(n_sms, &sms)) != NRF_OK) return rc;
+  int nk = 0;
+  for (int j = 0; j < a.n_src; ++j) {
+    if (a.a[j].cols < 64 || (a.a[j].cols & 63) || a.a[j].rows != S) { set_error("tile_gemm: A source %d has %d columns / %lld rows", j, a.a[j].cols, (long long)a.a[j].rows); return NRF_E_INVALID; }
+    nk += a.a[j].cols / 64;
+  }
+  const uint32_t planes = static_cast<uint32_t>(n_planes);
+  const uint32_t a_plane_stage = planes * kATile;
+  // CTA pairs (cta_group::2, M = 256) whenever the output is 128 / 256 columns wide (or a multiple of 256), the weight half-slice
+  // fits beside a 2-stage ring, and this is not the exact mode (whose per-chunk accumulators need all of TMEM for 128 columns)
+  // (same-box A/B of the whole training step, 20 steps each, twice: 13.59 ms never paired, 13.01 ms large launches only, 12.95 ms whenever
+  //  possible; a 393k x 256 x 256 layer alone: 187 us against 203 us, with half the L2 -> SMEM traffic)
+  static int pair_mode = -1;      // NRF_GEMM_PAIR=0 / 1 / 2: never / large launches only / whenever possible (default); developer A/B
+  if (pair_mode < 0) pair_mode = getenv("NRF_GEMM_PAIR") ? atoi(getenv("NRF_GEMM_PAIR")) : 2;
+  bool pair = pair_mode > 0 && a.passes != 6 && sms >= 2 && (a.N == 128 || a.N % 256 == 0) && (pair_mode == 2 || (nk >= 4 && S >= 65536));
+  if (pair) {
+    const int nt = a.N == 128 ? 128 : 256;
+    if (static_cast<uint32_t>(nk) * planes * (nt / 2) * 128u + 2 * a_plane_stage + 256 > kGemmSmemLimit) pair = false;
+    else P.n_tile = nt;
+  }
+  if (!pair) P.n_tile = (a.N % 128 == 0) ? 128 : 64;
+  const int n_cta = pair ? P.n_tile / 2 : P.n_tile;
   P.n_src = a.n_src; P.b_mn = a.b_mn ? 1 : 0; P.passes = a.passes; P.S = S;
-  int nk = 0, rc;
   for (int j = 0; j < a.n_src; ++j) {
     const Planes& A = a.a[j]; const Planes& B = a.b[j];
-    if (A.cols < 64 || (A.cols & 63) || A.rows != S) { set_error("tile_gemm: A source %d has %d columns / %lld rows", j, A.cols, (long long)A.rows); return NRF_E_INVALID; }
     const __half* ap[3] = {A.hi, A.lo, A.ll};
     const __half* bp[3] = {B.hi, B.lo, B.ll};
     for (int q = 0; q < n_planes; ++q) if (!ap[q] || !bp[q]) { set_error("tile_gemm: %d passes need %d planes per operand", a.passes, n_planes); return NRF_E_INVALID; }
-    P.kc[j] = A.cols / 64; nk += P.kc[j];
+    P.kc[j] = A.cols / 64;
     if (!a.b_mn) {      // B[N, K]: rows = output features
       if (B.rows != a.N || B.cols != A.cols) { set_error("tile_gemm: B source %d is [%lld x %d], expected [%d x %d]", j, (long long)B.rows, B.cols, a.N, A.cols); return NRF_E_INVALID; }
     } else {            // B[K, N]: rows = reduction index
@@ -554,22 +614,22 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
     }
     for (int q = 0; q < n_planes; ++q) {
       if ((rc = encode_planes_map(&P.a_map[j][q], ap[q], S, A.cols, A.ld, 64, 128)) != NRF_OK) return rc;
-      if ((rc = encode_planes_map(&P.b_map[j][q], bp[q], B.rows, B.cols, B.ld, 64, a.b_mn ? 64 : P.n_tile)) != NRF_OK) return rc;
+      if ((rc = encode_planes_map(&P.b_map[j][q], bp[q], B.rows, B.cols, B.ld, 64, a.b_mn ? 64 : n_cta)) != NRF_OK) return rc;
     }
   }
-  const uint32_t planes = static_cast<uint32_t>(n_planes);
-  uint32_t b_bytes = static_cast<uint32_t>(nk) * planes * P.n_tile * 128u, a_stage = planes * kATile;
+  uint32_t b_bytes = static_cast<uint32_t>(nk) * planes * n_cta * 128u, a_stage = a_plane_stage;
   if (b_bytes + 2 * a_stage + 256 > kGemmSmemLimit) {      // K too large for a resident weight slice: stream the B chunks with the A chunks
     P.b_stream = 1;
-    a_stage += planes * P.n_tile * 128u;
+    a_stage += planes * n_cta * 128u;
     b_bytes = 0;
   }
   // staged epilogue (fp16 planes out through shared memory + TMA stores) whenever the ring keeps >= 2 stages beside it
+  const uint32_t cols_pass = P.n_tile < 128 ? P.n_tile : 128;
   uint32_t out_bytes = 0;
   if (a.epi == GEPI_PLANES && a.passes != 6 && a.out.hi && !(reinterpret_cast<uintptr_t>(a.out.hi) & 15u) && !(a.out.ld & 7) &&
-      (!a.out.lo || !(reinterpret_cast<uintptr_t>(a.out.lo) & 15u)) && b_bytes + 2 * a_stage + static_cast<uint32_t>(P.n_tile) * 256u + 256 <= kGemmSmemLimit) {
+      (!a.out.lo || !(reinterpret_cast<uintptr_t>(a.out.lo) & 15u)) && b_bytes + 2 * a_stage + cols_pass * 256u + 256 <= kGemmSmemLimit) {
     P.staged = 1;
-    out_bytes = static_cast<uint32_t>(P.n_tile) * 256u;
+    out_bytes = cols_pass * 256u;
     if ((rc = encode_planes_map(&P.o_map[0], a.out.hi, S, a.N, a.out.ld, 64, 128)) != NRF_OK) return rc;
     if (a.out.lo && (rc = encode_planes_map(&P.o_map[1], a.out.lo, S, a.N, a.out.ld, 64, 128)) != NRF_OK) return rc;
   }
@@ -581,19 +641,53 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
   P.sc_in = a.sc_in; P.sc_out = a.sc_out; P.l1max = a.l1max; P.status = a.status;
   if (a.epi == GEPI_PLANES && !a.out.hi) { set_error("tile_gemm: planes epilogue without an output"); return NRF_E_INVALID; }
   if (a.epi == GEPI_F32 && !a.out_f32) { set_error("tile_gemm: fp32 epilogue without an output"); return NRF_E_INVALID; }
-  int sms;
-  if ((rc = device_sms(n_sms, &sms)) != NRF_OK) return rc;
   const int slices = a.N / P.n_tile;
-  const int64_t n_mt = (S + 127) / 128;
-  int gx = sms / slices; if (gx < 1) gx = 1; if (gx > n_mt) gx = static_cast<int>(n_mt);
+  const int rows_tile = pair ? 256 : 128;
+  const int64_t n_mt = (S + rows_tile - 1) / rows_tile;
+  int gx = sms / slices;
+  if (pair) gx /= 2;                                      // pairs per slice
+  if (gx < 1) gx = 1;
+  if (gx > n_mt) gx = static_cast<int>(n_mt);
+  if (pair) gx *= 2;
   const uint32_t smem_bytes = b_bytes + static_cast<uint32_t>(P.n_stages) * a_stage + out_bytes + 256;
-  cudaError_t e = P.bf16 ? cudaFuncSetAttribute(tile_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit))
-                         : cudaFuncSetAttribute(tile_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit));
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tile_gemm)");
-  if (P.bf16) tile_gemm_kernel<true><<<dim3(gx, slices), kTileThreads, smem_bytes, stream>>>(P);
-  else tile_gemm_kernel<false><<<dim3(gx, slices), kTileThreads, smem_bytes, stream>>>(P);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(gx, slices); cfg.blockDim = dim3(kTileThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  static long long* dbg_trace = nullptr;
+  static int dbg_left = -1;
+  if (dbg_left < 0) dbg_left = getenv("NRF_GEMM_TRACE") ? atoi(getenv("NRF_GEMM_TRACE")) : 0;
+  const bool tracing = dbg_left > 0 && S > 300000 && a.N == 256 && a.epi == GEPI_PLANES;
+  if (tracing) {
+    if (!dbg_trace) cudaMalloc(&dbg_trace, 1200 * sizeof(long long));
+    cudaMemsetAsync(dbg_trace, 0, 1200 * sizeof(long long), stream);
+    P.trace = dbg_trace;
+  }
+  cudaError_t e;
+  if (P.bf16) {
+    e = cudaFuncSetAttribute(tile_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit));
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, tile_gemm_kernel<true, false>, P);
+  } else if (pair) {
+    e = cudaFuncSetAttribute(tile_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit));
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, tile_gemm_kernel<false, true>, P);
+  } else {
+    e = cudaFuncSetAttribute(tile_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemLimit));
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, tile_gemm_kernel<false, false>, P);
+  }
   ++g_train_launches;
-  e = cudaGetLastError();
+  if (tracing && e == cudaSuccess) {       // developer tap: print CTA 0's epilogue timeline of this launch (synchronises!)
+    --dbg_left;
+    static long long host[1200];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(host, dbg_trace, sizeof(host), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tile_gemm trace] pair=%d staged=%d stages=%d mask=%d b_mn=%d\n", pair ? 1 : 0, P.staged, P.n_stages, a.mask_hi ? 1 : 0, P.b_mn);
+    long long t0 = host[1];
+    for (int i = 0; i < 600 && host[2 * i + 1]; ++i) { fprintf(stderr, "%lld:%lld ", host[2 * i], host[2 * i + 1] - t0); if (host[2 * i] == 8 || (i + 1 < 600 && host[2 * (i + 1)] == 0)) fprintf(stderr, "\n"); }
+    fprintf(stderr, "\n");
+  }
   return e == cudaSuccess ? NRF_OK : cuda_fail(e, "tile_gemm_kernel launch");
 }
 
