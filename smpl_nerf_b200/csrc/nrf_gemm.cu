@@ -54,6 +54,7 @@ struct GemmBars { uint64_t b_full, a_full[4], a_empty[4], acc_full[2], acc_empty
 template <bool kExact, bool kPair>
 __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid_constant__ TileGemmParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const int getenv_pf_dist = P.pf_dist;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const uint32_t planes = P.passes == 6 ? 3u : (P.passes == 3 ? 2u : 1u);
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
   const uint32_t smem_b = smem_u32(smem), smem_a = smem_b + b_bytes;
   const int cols_pass = P.n_tile < 128 ? P.n_tile : 128;                // the epilogue walks the accumulator in passes of <= 128 columns
   const int n_cpass = P.n_tile / cols_pass;
-  const uint32_t out_bytes = P.staged ? static_cast<uint32_t>(cols_pass) * 256u : 0u;    // one [128 x cols_pass] fp16 plane of the output tile
+  const uint32_t out_bytes = P.staged ? 32768u : 0u;                    // staging: [128 x 64] fp16 hi block | lo block of one 64-column unit
   const uint32_t smem_o = smem_a + static_cast<uint32_t>(P.n_stages) * a_stage;
   GemmBars* bars = reinterpret_cast<GemmBars*>(smem + b_bytes + static_cast<uint32_t>(P.n_stages) * a_stage + out_bytes);
   const int n0 = blockIdx.y * P.n_tile;
@@ -119,9 +120,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             const uint32_t dst = smem_a + stage * a_stage;
             const int32_t r0 = static_cast<int32_t>(mt * rows_tile + rank * 128);
             for (uint32_t p = 0; p < planes; ++p) load(dst + p * kATile, &P.a_map[j][p], 64 * lc, r0, bar_of(&bars->a_full[stage]));
-            // the activation planes stream from HBM (hundreds of MB per layer): pull this CTA's tile-after-next into L2 now, so the
-            // 2-3 deep ring is refilled at L2 latency
-            const int64_t pf = mt + 2 * mt_step;
+            // the activation planes stream from HBM (hundreds of MB per layer): pull this CTA's NEXT tile into L2 now, so the 2-3 deep
+            // ring is refilled at L2 latency (two tiles ahead was measured worse: 290 MB of a 402 MB operand were evicted by the
+            // output stream before use and read twice)
+            const int64_t pf = mt + (getenv_pf_dist > 0 ? getenv_pf_dist : 1) * mt_step;
             if (pf < n_mt) for (uint32_t p = 0; p < planes; ++p) tma_prefetch_2d(&P.a_map[j][p], 64 * lc, static_cast<int32_t>(pf * rows_tile + rank * 128));
             if (P.b_stream) load_b(j, lc, dst + planes * kATile, bar_of(&bars->a_full[stage]));
             if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
@@ -180,7 +182,173 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
       if (!kExact) { commit(&bars->acc_full[buf]); ++it; }
     }
     }
+  } else if (!kExact) {
+    // ------------------------------------------------------------ epilogue warps (parity / fast modes)
+    // The accumulator is drained in UNITS of 64 columns: warp = 32 rows (TMEM lane quarter q) x 32 columns (cg), so a thread holds only
+    // 2 x 16 values at a time.  Both planes of a unit are staged together ([128 x 64] hi block | lo block, SWIZZLE_128B) and leave as
+    // TMA stores; the wait for the previous unit's stores to have read the staging buffer comes AFTER the next unit's values are in
+    // registers, so it overlaps the arithmetic (staging hi and lo of 128 columns one after the other serialised on that wait).
+    const int q = warp & 3, cg = (warp - 2) >> 2;
+    const int n_units = P.n_tile / 64;
+    const float s_out = P.sc_out ? __ldg(P.sc_out) : 1.f, inv_out = P.sc_out ? __ldg(P.sc_out + 1) : 1.f;
+    const float ratio = (P.epi == GEPI_F32 ? 1.f : s_out) * (P.sc_in ? __ldg(P.sc_in + 1) : 1.f);     // stored-in -> stored-out (or real)
+    const bool rescale = P.sc_in != nullptr || P.sc_out != nullptr;
+    float l1_run = 0.f;
+    bool saturated = false;
+    uint32_t it = 0;
+    const bool e0 = warp == 2 && lane == 0;
+    const int r_t = 32 * q + lane;                        // row inside this CTA's 128 rows of the tile
+    int tr_n = 0;
+    auto TR = [&](int ev) { if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && e0 && tr_n < 600) { P.trace[2 * tr_n] = ev; P.trace[2 * tr_n + 1] = clock64(); ++tr_n; } };
+    for (int64_t mt = mt0; mt < n_mt; mt += mt_step, ++it) {
+      const uint32_t buf = it & 1u;
+      TR(0);
+      const int64_t row = mt * rows_tile + rank * 128 + r_t;
+      const bool row_ok = row < P.S;
+      const float* bias_row = (P.bias && row_ok) ? P.bias + (P.bias_ld ? (row / P.rows_per_ray) * P.bias_ld : 0) : nullptr;
+      const float rs = (P.row_scale && row_ok) ? P.row_scale[row * P.row_scale_ld] * s_out : 0.f;
+      const int32_t r0 = static_cast<int32_t>(mt * rows_tile + rank * 128);
+      float l1 = 0.f;
+      for (int u = 0; u < n_units; ++u) {
+        const int col0 = n0 + 64 * u + 32 * cg;           // this thread's 32 columns of the unit
+        // bias and ReLU' mask of the unit: global loads issued before the accumulator / the TMEM reads are waited for
+        float bias[32];
+        uint4 mk[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = bias_row ? __ldg(reinterpret_cast<const float4*>(bias_row + col0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          bias[4 * i] = b.x; bias[4 * i + 1] = b.y; bias[4 * i + 2] = b.z; bias[4 * i + 3] = b.w;
+        }
+        if (P.mask_hi && row_ok) {
+          const uint4* mp = reinterpret_cast<const uint4*>(P.mask_hi + row * P.mask_ld + col0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mk[i] = __ldg(mp + i);
+        }
+        if (u == 0) {
+          mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
+          tc_fence_after_sync();
+          TR(1);
+        }
+        const uint32_t taddr = tmem + buf * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(64 * u + 32 * cg);
+        uint32_t v[32];
+        tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_ld16(taddr + 16u, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        tmem_ld_wait();
+        if (u == n_units - 1) {                              // the accumulator has been read completely: hand it back to the issuer
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) { if (kPair && rank != 0) mbar_arrive_cluster_relaxed(smem_u32(&bars->acc_empty[buf]), 0); else mbar_arrive(smem_u32(&bars->acc_empty[buf])); }
+        }
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+        if (rescale) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] *= ratio;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] += bias[i];
+        if (P.row_scale) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = fmaf(rs, __ldg(P.col_vec + col0 + i), x[i]);
+        }
+        if (P.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
+        }
+        if (P.mask_hi && row_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {      // post-ReLU activations are >= 0: "active" = any non-zero bit pattern
+            const uint32_t mw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if ((mw[j] & 0x7FFFu) == 0u) x[8 * i + 2 * j] = 0.f;
+              if ((mw[j] & 0x7FFF0000u) == 0u) x[8 * i + 2 * j + 1] = 0.f;
+            }
+          }
+        }
+        if (P.l1max && row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) l1 += fabsf(x[i]);
+        }
+        if (P.epi == GEPI_F32) {
+          if (row_ok) {
+            float4* op = reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 o = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+              if (P.accumulate) { const float4 t = op[i]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              op[i] = o;
+            }
+          }
+          continue;
+        }
+        uint32_t h[16], l[16];
+        __half2 amax2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          h[i] = cvt_f16x2_satfinite(x[2 * i], x[2 * i + 1]);
+          const __half2 hh = *reinterpret_cast<const __half2*>(&h[i]);
+          amax2 = __hmax2(amax2, __habs2(hh));
+          const float2 f = __half22float2(hh);
+          l[i] = cvt_f16x2_satfinite(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+        }
+        {
+          const uint32_t am = *reinterpret_cast<const uint32_t*>(&amax2);
+          saturated |= (am & 0xFFFFu) >= 0x7BFFu || (am >> 16) >= 0x7BFFu;
+        }
+        if (P.out_f32 && row_ok) {
+          float4* op = reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) op[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        }
+        if (!P.staged) {
+          if (row_ok) {
+            uint4* ph = reinterpret_cast<uint4*>(P.out_hi + row * P.out_ld + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ph[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+            if (P.out_lo) {
+              uint4* pl = reinterpret_cast<uint4*>(P.out_lo + row * P.out_ld + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) pl[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+            }
+          }
+          continue;
+        }
+        TR(2);
+        if (e0) tma_store_wait_read();                     // the previous unit's stores have read the staging buffer ...
+        named_bar_sync(1, 256);
+        TR(3);
+        const uint32_t rowb = smem_o + static_cast<uint32_t>(r_t) * 128u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                      // ... this unit takes its place: 16-byte chunks 4 cg + i of the row, swizzled
+          const uint32_t ofs = ((static_cast<uint32_t>(4 * cg + i)) ^ (r_t & 7u)) << 4;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ofs), "r"(h[4 * i]), "r"(h[4 * i + 1]), "r"(h[4 * i + 2]), "r"(h[4 * i + 3]) : "memory");
+          if (P.out_lo)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + 16384u + ofs), "r"(l[4 * i]), "r"(l[4 * i + 1]), "r"(l[4 * i + 2]), "r"(l[4 * i + 3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);
+        TR(4);
+        if (e0) {
+          tma_store_2d(&P.o_map[0], n0 + 64 * u, r0, smem_o);
+          if (P.out_lo) tma_store_2d(&P.o_map[1], n0 + 64 * u, r0, smem_o + 16384u);
+          tma_store_commit();
+        }
+      }
+      l1_run = fmaxf(l1_run, l1);
+    }
+    if (P.staged && e0) tma_store_wait_all();
+    if (P.l1max) {
+      // real units; a row's L1 norm is bounded by (number of column segments it is split into) x the largest segment sum
+      l1_run *= (P.epi == GEPI_F32 ? 1.f : inv_out) * static_cast<float>(gridDim.y * 2);       // two column groups (warp sets) per slice
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) l1_run = fmaxf(l1_run, __shfl_xor_sync(0xffffffffu, l1_run, o));
+      if (lane == 0 && isfinite(l1_run)) atomicMax(P.l1max, __float_as_uint(l1_run));
+    }
+    if (saturated && P.status) atomicOr(P.status, 2);
   } else {
+    // ------------------------------------------------------------ epilogue warps, exact mode (single CTA, 128-column slice, unstaged)
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int cols_w = cols_pass / 2;
     const float s_out = P.sc_out ? __ldg(P.sc_out) : 1.f, inv_out = P.sc_out ? __ldg(P.sc_out + 1) : 1.f;
@@ -624,12 +792,12 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
     b_bytes = 0;
   }
   // staged epilogue (fp16 planes out through shared memory + TMA stores) whenever the ring keeps >= 2 stages beside it
-  const uint32_t cols_pass = P.n_tile < 128 ? P.n_tile : 128;
+  const uint32_t stage_out = 32768u;       // [128 x 64] fp16 block of the hi plane | the same of the lo plane
   uint32_t out_bytes = 0;
   if (a.epi == GEPI_PLANES && a.passes != 6 && a.out.hi && !(reinterpret_cast<uintptr_t>(a.out.hi) & 15u) && !(a.out.ld & 7) &&
-      (!a.out.lo || !(reinterpret_cast<uintptr_t>(a.out.lo) & 15u)) && b_bytes + 2 * a_stage + cols_pass * 256u + 256 <= kGemmSmemLimit) {
+      (!a.out.lo || !(reinterpret_cast<uintptr_t>(a.out.lo) & 15u)) && b_bytes + 2 * a_stage + stage_out + 256 <= kGemmSmemLimit) {
     P.staged = 1;
-    out_bytes = cols_pass * 256u;
+    out_bytes = stage_out;
     if ((rc = encode_planes_map(&P.o_map[0], a.out.hi, S, a.N, a.out.ld, 64, 128)) != NRF_OK) return rc;
     if (a.out.lo && (rc = encode_planes_map(&P.o_map[1], a.out.lo, S, a.N, a.out.ld, 64, 128)) != NRF_OK) return rc;
   }
@@ -657,6 +825,9 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  static int pf_dist = -1;
+  if (pf_dist < 0) pf_dist = getenv("NRF_GEMM_PF") ? atoi(getenv("NRF_GEMM_PF")) : 1;
+  P.pf_dist = pf_dist;
   static long long* dbg_trace = nullptr;
   static int dbg_left = -1;
   if (dbg_left < 0) dbg_left = getenv("NRF_GEMM_TRACE") ? atoi(getenv("NRF_GEMM_TRACE")) : 0;

@@ -49,6 +49,7 @@ struct TileGemmParams {
   // norm, from which the host derives the next layer's scale (|dX| <= |dY row|_1 max|W|).
   const float* sc_in; const float* sc_out; unsigned int* l1max;
   int32_t* status;                                                 // bit 1: an output saturated the fp16 range
+  int32_t pf_dist;                                                 // L2 prefetch distance in tiles (developer A/B: NRF_GEMM_PF; default 1)
   long long* trace;                                                // developer tap (NRF_GEMM_TRACE): CTA 0's epilogue timeline, SM clocks
 };
 
