@@ -25,7 +25,7 @@
 namespace nrf {
 
 constexpr uint32_t kGemmSmemLimit = 232448;
-constexpr int kTileThreads = 320;     // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kTileThreads = 352;     // TMA warp, MMA warp, 8 epilogue warps, store warp
 constexpr int kDwThreads = 192;       // TMA warp, MMA warp, 4 epilogue warps
 constexpr uint32_t kATile = 16384;    // [128 x 64] fp16
 
@@ -182,6 +182,38 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
       if (!kExact) { commit(&bars->acc_full[buf]); ++it; }
     }
     }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------ store warp: staged output units -> TMA stores
+    // consumer of barrier 1 ("unit staged", 256 epilogue threads arrive), producer of barrier 2 ("staging buffer free again")
+    if (!kExact && P.staged) {
+      named_bar_arrive(2, 288);                            // the buffer starts out free
+      for (int64_t mt = mt0; mt < n_mt; mt += mt_step) {
+        const int32_t r0 = static_cast<int32_t>(mt * rows_tile + rank * 128);
+        for (int u = 0; u < P.n_tile / 64; ++u) {
+          if (P.f32_staged) {                              // round A: the unit's fp32 copy (columns as 16-bit element indices)
+            named_bar_sync(1, 288);
+            if (lane == 0) {
+              tma_store_2d(&P.f_map, 2 * (n0 + 64 * u), r0, smem_o);
+              tma_store_2d(&P.f_map, 2 * (n0 + 64 * u) + 64, r0, smem_o + 16384u);
+              tma_store_commit();
+              tma_store_wait_read();
+            }
+            __syncwarp();
+            named_bar_arrive(2, 288);
+          }
+          named_bar_sync(1, 288);
+          if (lane == 0) {
+            tma_store_2d(&P.o_map[0], n0 + 64 * u, r0, smem_o);
+            if (P.out_lo) tma_store_2d(&P.o_map[1], n0 + 64 * u, r0, smem_o + 16384u);
+            tma_store_commit();
+            tma_store_wait_read();
+          }
+          __syncwarp();
+          named_bar_arrive(2, 288);
+        }
+      }
+      if (lane == 0) tma_store_wait_all();
+    }
   } else if (!kExact) {
     // ------------------------------------------------------------ epilogue warps (parity / fast modes)
     // The accumulator is drained in UNITS of 64 columns: warp = 32 rows (TMEM lane quarter q) x 32 columns (cg), so a thread holds only
@@ -200,30 +232,40 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
     const int r_t = 32 * q + lane;                        // row inside this CTA's 128 rows of the tile
     int tr_n = 0;
     auto TR = [&](int ev) { if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && e0 && tr_n < 600) { P.trace[2 * tr_n] = ev; P.trace[2 * tr_n + 1] = clock64(); ++tr_n; } };
+    // bias and ReLU' mask of a unit are global loads with an L2 round trip: they are issued ONE UNIT AHEAD (for the first unit of a
+    // tile: during the last unit of the previous tile) into the registers the current unit has just finished with, so the round trip
+    // hides behind the conversion + staging of the current unit instead of stalling every unit (profiles/r2 timeline).
+    float bias[32];
+    uint4 mk[4];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mk[i] = make_uint4(0u, 0u, 0u, 0u);
+    auto aux_load = [&](int64_t mt_l, int u_l) {
+      const int64_t row_l = mt_l * rows_tile + rank * 128 + r_t;
+      const bool ok = row_l < P.S;
+      const int c0 = n0 + 64 * u_l + 32 * cg;
+      if (P.bias) {
+        const float4* bp = reinterpret_cast<const float4*>(P.bias + (P.bias_ld ? (ok ? row_l / P.rows_per_ray : 0) * P.bias_ld : 0) + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float4 b = __ldg(bp + i); bias[4 * i] = b.x; bias[4 * i + 1] = b.y; bias[4 * i + 2] = b.z; bias[4 * i + 3] = b.w; }
+      }
+      if (P.mask_hi && ok) {
+        const uint4* mp = reinterpret_cast<const uint4*>(P.mask_hi + row_l * P.mask_ld + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mk[i] = __ldg(mp + i);
+      }
+    };
+    if (mt0 < n_mt) aux_load(mt0, 0);
     for (int64_t mt = mt0; mt < n_mt; mt += mt_step, ++it) {
       const uint32_t buf = it & 1u;
       TR(0);
       const int64_t row = mt * rows_tile + rank * 128 + r_t;
       const bool row_ok = row < P.S;
-      const float* bias_row = (P.bias && row_ok) ? P.bias + (P.bias_ld ? (row / P.rows_per_ray) * P.bias_ld : 0) : nullptr;
       const float rs = (P.row_scale && row_ok) ? P.row_scale[row * P.row_scale_ld] * s_out : 0.f;
-      const int32_t r0 = static_cast<int32_t>(mt * rows_tile + rank * 128);
       float l1 = 0.f;
       for (int u = 0; u < n_units; ++u) {
         const int col0 = n0 + 64 * u + 32 * cg;           // this thread's 32 columns of the unit
-        // bias and ReLU' mask of the unit: global loads issued before the accumulator / the TMEM reads are waited for
-        float bias[32];
-        uint4 mk[4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = bias_row ? __ldg(reinterpret_cast<const float4*>(bias_row + col0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          bias[4 * i] = b.x; bias[4 * i + 1] = b.y; bias[4 * i + 2] = b.z; bias[4 * i + 3] = b.w;
-        }
-        if (P.mask_hi && row_ok) {
-          const uint4* mp = reinterpret_cast<const uint4*>(P.mask_hi + row * P.mask_ld + col0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) mk[i] = __ldg(mp + i);
-        }
         if (u == 0) {
           mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
           tc_fence_after_sync();
@@ -234,6 +276,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
         tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
         tmem_ld16(taddr + 16u, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
         tmem_ld_wait();
+        TR(5);
         if (u == n_units - 1) {                              // the accumulator has been read completely: hand it back to the issuer
           tc_fence_before_sync();
           __syncwarp();
@@ -267,6 +310,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             }
           }
         }
+        TR(6);
+        if (u + 1 < n_units) aux_load(mt, u + 1);          // the next unit's bias / mask (see above)
+        else if (mt + mt_step < n_mt) aux_load(mt + mt_step, 0);
         if (P.l1max && row_ok) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) l1 += fabsf(x[i]);
@@ -283,6 +329,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           }
           continue;
         }
+        if (P.f32_staged) {                                // fp32 copy of the unit: box cg, row r_t, 16-byte chunks swizzled
+          named_bar_sync(2, 288);
+          const uint32_t rowf = smem_o + static_cast<uint32_t>(cg) * 16384u + static_cast<uint32_t>(r_t) * 128u;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowf + ((static_cast<uint32_t>(i) ^ (r_t & 7u)) << 4)), "f"(x[4 * i]), "f"(x[4 * i + 1]),
+                         "f"(x[4 * i + 2]), "f"(x[4 * i + 3]) : "memory");
+          fence_proxy_async_smem();
+          named_bar_arrive(1, 288);
+        }
         uint32_t h[16], l[16];
         __half2 amax2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
@@ -297,7 +353,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           const uint32_t am = *reinterpret_cast<const uint32_t*>(&amax2);
           saturated |= (am & 0xFFFFu) >= 0x7BFFu || (am >> 16) >= 0x7BFFu;
         }
-        if (P.out_f32 && row_ok) {
+        if (P.out_f32 && !P.f32_staged && row_ok) {
           float4* op = reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) op[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
@@ -316,8 +372,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           continue;
         }
         TR(2);
-        if (e0) tma_store_wait_read();                     // the previous unit's stores have read the staging buffer ...
-        named_bar_sync(1, 256);
+        named_bar_sync(2, 288);                            // the previous unit's stores have read the staging buffer (store warp) ...
         TR(3);
         const uint32_t rowb = smem_o + static_cast<uint32_t>(r_t) * 128u;
 #pragma unroll
@@ -328,17 +383,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + 16384u + ofs), "r"(l[4 * i]), "r"(l[4 * i + 1]), "r"(l[4 * i + 2]), "r"(l[4 * i + 3]) : "memory");
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 256);
+        named_bar_arrive(1, 288);                          // ... hand the unit to the store warp and go on with the next one
         TR(4);
-        if (e0) {
-          tma_store_2d(&P.o_map[0], n0 + 64 * u, r0, smem_o);
-          if (P.out_lo) tma_store_2d(&P.o_map[1], n0 + 64 * u, r0, smem_o + 16384u);
-          tma_store_commit();
-        }
       }
       l1_run = fmaxf(l1_run, l1);
     }
-    if (P.staged && e0) tma_store_wait_all();
     if (P.l1max) {
       // real units; a row's L1 norm is bounded by (number of column segments it is split into) x the largest segment sum
       l1_run *= (P.epi == GEPI_F32 ? 1.f : inv_out) * static_cast<float>(gridDim.y * 2);       // two column groups (warp sets) per slice
@@ -800,6 +849,12 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
     out_bytes = stage_out;
     if ((rc = encode_planes_map(&P.o_map[0], a.out.hi, S, a.N, a.out.ld, 64, 128)) != NRF_OK) return rc;
     if (a.out.lo && (rc = encode_planes_map(&P.o_map[1], a.out.lo, S, a.N, a.out.ld, 64, 128)) != NRF_OK) return rc;
+    if (a.out_f32 && !(reinterpret_cast<uintptr_t>(a.out_f32) & 15u) && !(a.out_f32_ld & 3)) {
+      // the fp32 copy (read by the scalar heads) takes the same route: a thread's 32 floats are one 128-byte row of a [128 x 32] box;
+      // written straight from registers they were 8 x 16-byte stores into 32 different lines per warp (+130 us on a 250 us layer)
+      P.f32_staged = 1;
+      if ((rc = encode_planes_map(&P.f_map, a.out_f32, S, 2 * static_cast<uint64_t>(a.N), 2 * static_cast<uint64_t>(a.out_f32_ld), 64, 128)) != NRF_OK) return rc;
+    }
   }
   int stages = static_cast<int>((kGemmSmemLimit - 256 - b_bytes - out_bytes) / a_stage);
   P.n_stages = stages > 4 ? 4 : stages;

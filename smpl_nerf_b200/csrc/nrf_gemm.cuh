@@ -35,6 +35,8 @@ struct TileGemmParams {
   int32_t bf16;                   // 1: the planes hold bfloat16 (exact mode: 3 planes = 24 significant bits, fp32 range), else fp16
   CUtensorMap o_map[2];           // staged epilogue: output planes hi / lo as [S, N], box {64, 128}, written by TMA stores
   int32_t staged;                 // 1: the epilogue stages the fp16 output planes through shared memory (coalesced TMA stores)
+  CUtensorMap f_map;              // staged fp32 copy (out_f32 beside the planes): [S, N] floats seen as [S, 2N] 16-bit elements, box {64, 128}
+  int32_t f32_staged;             // 1: the fp32 copy of a unit also leaves through the staging buffer (two [128 x 32] float boxes)
   int32_t b_stream;               // 1: K too large for a resident weight slice -- the B chunk travels with every A chunk through the ring
   int64_t S;
   int32_t epi, relu;

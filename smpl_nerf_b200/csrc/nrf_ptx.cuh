@@ -58,6 +58,9 @@ __device__ __forceinline__ void tc_fence_after_sync() {
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {      // producer side of a producer / consumer barrier
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // ------------------------------------------------------------------------------ TMA (1-D bulk)
 // global -> shared, completion counted in bytes on an mbarrier.  SASS: UBLKCP.
