@@ -25,7 +25,9 @@
 namespace nrf {
 
 constexpr uint32_t kGemmSmemLimit = 232448;
-constexpr int kTileThreads = 352;     // TMA warp, MMA warp, 8 epilogue warps, store warp
+constexpr int kCT = 32;                                  // accumulator columns a thread drains per 64-column unit
+constexpr int kEpiWarps = 4 * (64 / kCT);                // 4 TMEM lane quarters x 2 column groups
+constexpr int kTileThreads = 32 * (2 + kEpiWarps);       // TMA warp, MMA warp, epilogue warps
 constexpr int kDwThreads = 192;       // TMA warp, MMA warp, 4 epilogue warps
 constexpr uint32_t kATile = 16384;    // [128 x 64] fp16
 
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bars->b_full), 1);
     for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&bars->a_full[s]), 1); mbar_init(smem_u32(&bars->a_empty[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bars->acc_full[b]), 1); mbar_init(smem_u32(&bars->acc_empty[b]), kPair ? 16 : 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bars->acc_full[b]), 1); mbar_init(smem_u32(&bars->acc_empty[b]), kExact ? 8 : (kPair ? 2 * kEpiWarps : kEpiWarps)); }
     fence_mbar_init();
   }
   if (warp == 1) { if (kPair) tmem_alloc2<512>(smem_u32(&bars->tmem)); else tmem_alloc<512>(smem_u32(&bars->tmem)); }
@@ -182,44 +184,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
       if (!kExact) { commit(&bars->acc_full[buf]); ++it; }
     }
     }
-  } else if (warp == 10) {
-    // ------------------------------------------------------------ store warp: staged output units -> TMA stores
-    // consumer of barrier 1 ("unit staged", 256 epilogue threads arrive), producer of barrier 2 ("staging buffer free again")
-    if (!kExact && P.staged) {
-      named_bar_arrive(2, 288);                            // the buffer starts out free
-      for (int64_t mt = mt0; mt < n_mt; mt += mt_step) {
-        const int32_t r0 = static_cast<int32_t>(mt * rows_tile + rank * 128);
-        for (int u = 0; u < P.n_tile / 64; ++u) {
-          if (P.f32_staged) {                              // round A: the unit's fp32 copy (columns as 16-bit element indices)
-            named_bar_sync(1, 288);
-            if (lane == 0) {
-              tma_store_2d(&P.f_map, 2 * (n0 + 64 * u), r0, smem_o);
-              tma_store_2d(&P.f_map, 2 * (n0 + 64 * u) + 64, r0, smem_o + 16384u);
-              tma_store_commit();
-              tma_store_wait_read();
-            }
-            __syncwarp();
-            named_bar_arrive(2, 288);
-          }
-          named_bar_sync(1, 288);
-          if (lane == 0) {
-            tma_store_2d(&P.o_map[0], n0 + 64 * u, r0, smem_o);
-            if (P.out_lo) tma_store_2d(&P.o_map[1], n0 + 64 * u, r0, smem_o + 16384u);
-            tma_store_commit();
-            tma_store_wait_read();
-          }
-          __syncwarp();
-          named_bar_arrive(2, 288);
-        }
-      }
-      if (lane == 0) tma_store_wait_all();
-    }
   } else if (!kExact) {
     // ------------------------------------------------------------ epilogue warps (parity / fast modes)
-    // The accumulator is drained in UNITS of 64 columns: warp = 32 rows (TMEM lane quarter q) x 32 columns (cg), so a thread holds only
-    // 2 x 16 values at a time.  Both planes of a unit are staged together ([128 x 64] hi block | lo block, SWIZZLE_128B) and leave as
-    // TMA stores; the wait for the previous unit's stores to have read the staging buffer comes AFTER the next unit's values are in
-    // registers, so it overlaps the arithmetic (staging hi and lo of 128 columns one after the other serialised on that wait).
+    // The accumulator is drained in UNITS of 64 columns: warp = 32 rows (TMEM lane quarter q) x kCT columns (cg), so a thread holds only
+    // kCT values at a time.  Every warp owns a PRIVATE 4 KB staging block ([32 x 32] hi | lo, 64-byte rows, SWIZZLE_64B; or one
+    // [32 x 32] fp32 block, SWIZZLE_128B) and issues its own TMA stores: lane 0 waits for the warp's previous stores to have read the
+    // block just before the next unit overwrites it (~a unit later, so the wait is free) and NO barrier joins the epilogue warps.
+    // (CTA-wide staging with two named barriers per unit kept all warps in lock step -- TMEM read, arithmetic and st.shared phases
+    // queued on the same unit one after the other instead of overlapping; a unit took 2.3k cycles whatever the instruction count.)
     const int q = warp & 3, cg = (warp - 2) >> 2;
     const int n_units = P.n_tile / 64;
     const float s_out = P.sc_out ? __ldg(P.sc_out) : 1.f, inv_out = P.sc_out ? __ldg(P.sc_out + 1) : 1.f;
@@ -231,29 +203,34 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
     const bool e0 = warp == 2 && lane == 0;
     const int r_t = 32 * q + lane;                        // row inside this CTA's 128 rows of the tile
     int tr_n = 0;
+#ifdef NRF_GEMM_TRACE_BUILD      // developer timeline (build with -DNRF_GEMM_TRACE_BUILD, run with NRF_GEMM_TRACE=n): ~70 issued instructions per unit
     auto TR = [&](int ev) { if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && e0 && tr_n < 600) { P.trace[2 * tr_n] = ev; P.trace[2 * tr_n + 1] = clock64(); ++tr_n; } };
+#else
+    auto TR = [&](int) {};
+    (void)e0; (void)tr_n;
+#endif
     // bias and ReLU' mask of a unit are global loads with an L2 round trip: they are issued ONE UNIT AHEAD (for the first unit of a
     // tile: during the last unit of the previous tile) into the registers the current unit has just finished with, so the round trip
     // hides behind the conversion + staging of the current unit instead of stalling every unit (profiles/r2 timeline).
-    float bias[32];
-    uint4 mk[4];
+    float bias[kCT];
+    uint4 mk[kCT / 8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) bias[i] = 0.f;
+    for (int i = 0; i < kCT; ++i) bias[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mk[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < kCT / 8; ++i) mk[i] = make_uint4(0u, 0u, 0u, 0u);
     auto aux_load = [&](int64_t mt_l, int u_l) {
       const int64_t row_l = mt_l * rows_tile + rank * 128 + r_t;
       const bool ok = row_l < P.S;
-      const int c0 = n0 + 64 * u_l + 32 * cg;
+      const int c0 = n0 + 64 * u_l + kCT * cg;
       if (P.bias) {
         const float4* bp = reinterpret_cast<const float4*>(P.bias + (P.bias_ld ? (ok ? row_l / P.rows_per_ray : 0) * P.bias_ld : 0) + c0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float4 b = __ldg(bp + i); bias[4 * i] = b.x; bias[4 * i + 1] = b.y; bias[4 * i + 2] = b.z; bias[4 * i + 3] = b.w; }
+        for (int i = 0; i < kCT / 4; ++i) { const float4 b = __ldg(bp + i); bias[4 * i] = b.x; bias[4 * i + 1] = b.y; bias[4 * i + 2] = b.z; bias[4 * i + 3] = b.w; }
       }
       if (P.mask_hi && ok) {
         const uint4* mp = reinterpret_cast<const uint4*>(P.mask_hi + row_l * P.mask_ld + c0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mk[i] = __ldg(mp + i);
+        for (int i = 0; i < kCT / 8; ++i) mk[i] = __ldg(mp + i);
       }
     };
     if (mt0 < n_mt) aux_load(mt0, 0);
@@ -265,16 +242,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
       const float rs = (P.row_scale && row_ok) ? P.row_scale[row * P.row_scale_ld] * s_out : 0.f;
       float l1 = 0.f;
       for (int u = 0; u < n_units; ++u) {
-        const int col0 = n0 + 64 * u + 32 * cg;           // this thread's 32 columns of the unit
+        const int col0 = n0 + 64 * u + kCT * cg;          // this thread's kCT columns of the unit
         if (u == 0) {
           mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
           tc_fence_after_sync();
           TR(1);
         }
-        const uint32_t taddr = tmem + buf * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(64 * u + 32 * cg);
-        uint32_t v[32];
-        tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        tmem_ld16(taddr + 16u, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        const uint32_t taddr = tmem + buf * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(64 * u + kCT * cg);
+        uint32_t v[kCT];
+#pragma unroll
+        for (int g = 0; g < kCT / 16; ++g) tmem_ld16(taddr + 16u * g, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * g]));
         tmem_ld_wait();
         TR(5);
         if (u == n_units - 1) {                              // the accumulator has been read completely: hand it back to the issuer
@@ -282,26 +259,26 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           __syncwarp();
           if (lane == 0) { if (kPair && rank != 0) mbar_arrive_cluster_relaxed(smem_u32(&bars->acc_empty[buf]), 0); else mbar_arrive(smem_u32(&bars->acc_empty[buf])); }
         }
-        float x[32];
+        float x[kCT];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+        for (int i = 0; i < kCT; ++i) x[i] = __uint_as_float(v[i]);
         if (rescale) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] *= ratio;
+          for (int i = 0; i < kCT; ++i) x[i] *= ratio;
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] += bias[i];
+        for (int i = 0; i < kCT; ++i) x[i] += bias[i];
         if (P.row_scale) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = fmaf(rs, __ldg(P.col_vec + col0 + i), x[i]);
+          for (int i = 0; i < kCT; ++i) x[i] = fmaf(rs, __ldg(P.col_vec + col0 + i), x[i]);
         }
         if (P.relu) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
+          for (int i = 0; i < kCT; ++i) x[i] = fmaxf(x[i], 0.f);
         }
         if (P.mask_hi && row_ok) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {      // post-ReLU activations are >= 0: "active" = any non-zero bit pattern
+          for (int i = 0; i < kCT / 8; ++i) {      // post-ReLU activations are >= 0: "active" = any non-zero bit pattern
             const uint32_t mw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -315,13 +292,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
         else if (mt + mt_step < n_mt) aux_load(mt + mt_step, 0);
         if (P.l1max && row_ok) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) l1 += fabsf(x[i]);
+          for (int i = 0; i < kCT; ++i) l1 += fabsf(x[i]);
         }
         if (P.epi == GEPI_F32) {
           if (row_ok) {
             float4* op = reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < kCT / 4; ++i) {
               float4 o = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
               if (P.accumulate) { const float4 t = op[i]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
               op[i] = o;
@@ -329,20 +306,24 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           }
           continue;
         }
-        if (P.f32_staged) {                                // fp32 copy of the unit: box cg, row r_t, 16-byte chunks swizzled
-          named_bar_sync(2, 288);
-          const uint32_t rowf = smem_o + static_cast<uint32_t>(cg) * 16384u + static_cast<uint32_t>(r_t) * 128u;
+        const uint32_t st_w = smem_o + static_cast<uint32_t>(warp - 2) * 4096u;           // this warp's staging block
+        const int32_t r0w = static_cast<int32_t>(mt * rows_tile + rank * 128 + 32 * q);    // first row of the warp's 32
+        if (P.f32_staged) {                                // fp32 copy of the unit: [32 rows x 32 floats], 128-byte rows, SWIZZLE_128B
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+          const uint32_t rowf = st_w + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowf + ((static_cast<uint32_t>(i) ^ (r_t & 7u)) << 4)), "f"(x[4 * i]), "f"(x[4 * i + 1]),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowf + ((static_cast<uint32_t>(i) ^ (lane & 7u)) << 4)), "f"(x[4 * i]), "f"(x[4 * i + 1]),
                          "f"(x[4 * i + 2]), "f"(x[4 * i + 3]) : "memory");
           fence_proxy_async_smem();
-          named_bar_arrive(1, 288);
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&P.f_map, 2 * col0, r0w, st_w); tma_store_commit(); }
         }
-        uint32_t h[16], l[16];
+        uint32_t h[kCT / 2], l[kCT / 2];
         __half2 amax2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < kCT / 2; ++i) {
           h[i] = cvt_f16x2_satfinite(x[2 * i], x[2 * i + 1]);
           const __half2 hh = *reinterpret_cast<const __half2*>(&h[i]);
           amax2 = __hmax2(amax2, __habs2(hh));
@@ -356,46 +337,53 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
         if (P.out_f32 && !P.f32_staged && row_ok) {
           float4* op = reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) op[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          for (int i = 0; i < kCT / 4; ++i) op[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
         }
         if (!P.staged) {
           if (row_ok) {
             uint4* ph = reinterpret_cast<uint4*>(P.out_hi + row * P.out_ld + col0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) ph[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+            for (int i = 0; i < kCT / 8; ++i) ph[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
             if (P.out_lo) {
               uint4* pl = reinterpret_cast<uint4*>(P.out_lo + row * P.out_ld + col0);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) pl[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+              for (int i = 0; i < kCT / 8; ++i) pl[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
             }
           }
           continue;
         }
         TR(2);
-        named_bar_sync(2, 288);                            // the previous unit's stores have read the staging buffer (store warp) ...
+        if (lane == 0) tma_store_wait_read();              // the warp's previous stores have read its staging block ...
+        __syncwarp();
         TR(3);
-        const uint32_t rowb = smem_o + static_cast<uint32_t>(r_t) * 128u;
+        const uint32_t rowb = st_w + static_cast<uint32_t>(lane) * 64u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                      // ... this unit takes its place: 16-byte chunks 4 cg + i of the row, swizzled
-          const uint32_t ofs = ((static_cast<uint32_t>(4 * cg + i)) ^ (r_t & 7u)) << 4;
+        for (int i = 0; i < 4; ++i) {                      // ... this unit takes its place: 64-byte rows, 16-byte chunks swizzled (SWIZZLE_64B)
+          const uint32_t ofs = (static_cast<uint32_t>(i) ^ ((lane >> 1) & 3u)) << 4;
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ofs), "r"(h[4 * i]), "r"(h[4 * i + 1]), "r"(h[4 * i + 2]), "r"(h[4 * i + 3]) : "memory");
           if (P.out_lo)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + 16384u + ofs), "r"(l[4 * i]), "r"(l[4 * i + 1]), "r"(l[4 * i + 2]), "r"(l[4 * i + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + 2048u + ofs), "r"(l[4 * i]), "r"(l[4 * i + 1]), "r"(l[4 * i + 2]), "r"(l[4 * i + 3]) : "memory");
         }
         fence_proxy_async_smem();
-        named_bar_arrive(1, 288);                          // ... hand the unit to the store warp and go on with the next one
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&P.o_map[0], col0, r0w, st_w);
+          if (P.out_lo) tma_store_2d(&P.o_map[1], col0, r0w, st_w + 2048u);
+          tma_store_commit();
+        }
         TR(4);
       }
       l1_run = fmaxf(l1_run, l1);
     }
     if (P.l1max) {
       // real units; a row's L1 norm is bounded by (number of column segments it is split into) x the largest segment sum
-      l1_run *= (P.epi == GEPI_F32 ? 1.f : inv_out) * static_cast<float>(gridDim.y * 2);       // two column groups (warp sets) per slice
+      l1_run *= (P.epi == GEPI_F32 ? 1.f : inv_out) * static_cast<float>(gridDim.y * (64 / kCT));       // 64 / kCT column groups (warp sets) per slice
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) l1_run = fmaxf(l1_run, __shfl_xor_sync(0xffffffffu, l1_run, o));
       if (lane == 0 && isfinite(l1_run)) atomicMax(P.l1max, __float_as_uint(l1_run));
     }
     if (saturated && P.status) atomicOr(P.status, 2);
+    if (P.staged && lane == 0) tma_store_wait_all();
   } else {
     // ------------------------------------------------------------ epilogue warps, exact mode (single CTA, 128-column slice, unstaged)
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -409,7 +397,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
     const bool e0 = warp == 2 && lane == 0;
     const int r_t = 32 * q + lane;                        // row inside this CTA's 128 rows of the tile
     int tr_n = 0;
+#ifdef NRF_GEMM_TRACE_BUILD      // developer timeline (build with -DNRF_GEMM_TRACE_BUILD, run with NRF_GEMM_TRACE=n): ~70 issued instructions per unit
     auto TR = [&](int ev) { if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && e0 && tr_n < 600) { P.trace[2 * tr_n] = ev; P.trace[2 * tr_n + 1] = clock64(); ++tr_n; } };
+#else
+    auto TR = [&](int) {};
+    (void)e0; (void)tr_n;
+#endif
     for (int64_t mt = mt0; mt < n_mt; mt += mt_step) {
       uint32_t buf = it & 1u;
       TR(0);
@@ -753,7 +746,7 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int encode_planes_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows) {
+int encode_planes_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
   static EncodeTiledFn2 fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -768,7 +761,7 @@ int encode_planes_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for a [%llu x %llu] plane", static_cast<int>(r), (unsigned long long)rows, (unsigned long long)cols); return NRF_E_CUDA; }
   return NRF_OK;
 }
@@ -847,13 +840,13 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
       (!a.out.lo || !(reinterpret_cast<uintptr_t>(a.out.lo) & 15u)) && b_bytes + 2 * a_stage + stage_out + 256 <= kGemmSmemLimit) {
     P.staged = 1;
     out_bytes = stage_out;
-    if ((rc = encode_planes_map(&P.o_map[0], a.out.hi, S, a.N, a.out.ld, 64, 128)) != NRF_OK) return rc;
-    if (a.out.lo && (rc = encode_planes_map(&P.o_map[1], a.out.lo, S, a.N, a.out.ld, 64, 128)) != NRF_OK) return rc;
+    if ((rc = encode_planes_map(&P.o_map[0], a.out.hi, S, a.N, a.out.ld, 32, 32, 64)) != NRF_OK) return rc;
+    if (a.out.lo && (rc = encode_planes_map(&P.o_map[1], a.out.lo, S, a.N, a.out.ld, 32, 32, 64)) != NRF_OK) return rc;
     if (a.out_f32 && !(reinterpret_cast<uintptr_t>(a.out_f32) & 15u) && !(a.out_f32_ld & 3)) {
       // the fp32 copy (read by the scalar heads) takes the same route: a thread's 32 floats are one 128-byte row of a [128 x 32] box;
       // written straight from registers they were 8 x 16-byte stores into 32 different lines per warp (+130 us on a 250 us layer)
       P.f32_staged = 1;
-      if ((rc = encode_planes_map(&P.f_map, a.out_f32, S, 2 * static_cast<uint64_t>(a.N), 2 * static_cast<uint64_t>(a.out_f32_ld), 64, 128)) != NRF_OK) return rc;
+      if ((rc = encode_planes_map(&P.f_map, a.out_f32, S, 2 * static_cast<uint64_t>(a.N), 2 * static_cast<uint64_t>(a.out_f32_ld), 64, 32)) != NRF_OK) return rc;
     }
   }
   int stages = static_cast<int>((kGemmSmemLimit - 256 - b_bytes - out_bytes) / a_stage);

@@ -33,10 +33,10 @@ struct TileGemmParams {
   int32_t kc[2];
   int32_t n_src, b_mn, n_tile, passes, n_stages;
   int32_t bf16;                   // 1: the planes hold bfloat16 (exact mode: 3 planes = 24 significant bits, fp32 range), else fp16
-  CUtensorMap o_map[2];           // staged epilogue: output planes hi / lo as [S, N], box {64, 128}, written by TMA stores
+  CUtensorMap o_map[2];           // staged epilogue: output planes hi / lo as [S, N], box {32, 32} (one warp's share of a unit, SWIZZLE_64B), TMA stores
   int32_t staged;                 // 1: the epilogue stages the fp16 output planes through shared memory (coalesced TMA stores)
-  CUtensorMap f_map;              // staged fp32 copy (out_f32 beside the planes): [S, N] floats seen as [S, 2N] 16-bit elements, box {64, 128}
-  int32_t f32_staged;             // 1: the fp32 copy of a unit also leaves through the staging buffer (two [128 x 32] float boxes)
+  CUtensorMap f_map;              // staged fp32 copy (out_f32 beside the planes): [S, N] floats seen as [S, 2N] 16-bit elements, box {64, 32}
+  int32_t f32_staged;             // 1: the fp32 copy of a unit also leaves through the staging buffer (one [32 x 32] float box per warp)
   int32_t b_stream;               // 1: K too large for a resident weight slice -- the B chunk travels with every A chunk through the ring
   int64_t S;
   int32_t epi, relu;
@@ -67,7 +67,8 @@ struct DwGemmParams {
 };
 
 // host helpers (nrf_gemm.cu).  All return NRF_OK or an error code with the message set.
-int encode_planes_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows);
+int encode_planes_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows,
+                      int swizzle_bytes = 128);
 
 // cols: logical feature count (multiple of 64).  ll: third plane of the exact mode (bf16 x 3), NULL otherwise; the element type of the
 // storage is 16-bit either way (fp16 or, in the exact mode, bfloat16 bit patterns).
