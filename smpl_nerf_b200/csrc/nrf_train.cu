@@ -284,7 +284,7 @@ static int heads(TrainCtx& t, const float* x, int64_t S, int K, const float* W, 
 }
 
 static int encode(TrainCtx& t, const float* x, int64_t S, int freqs, int identity, const Planes& dst) {
-  encode_planes_kernel<<<grid1(S * 8, 256), 256, 0, t.st>>>(x, S, freqs, identity, dst.hi, dst.lo, dst.ll);
+  encode_planes_kernel<<<static_cast<unsigned>((S + kEncRows - 1) / kEncRows), 256, 0, t.st>>>(x, S, freqs, identity, dst.hi, dst.lo, dst.ll);
   LAUNCH_CHECK("encode_planes_kernel");
   return NRF_OK;
 }
@@ -415,12 +415,10 @@ static int dw_into(TrainCtx& t, const Planes& dy, const float* sc, int M, const 
     int split = 0;
     const bool with_db = db != nullptr && nb == 0;       // the bias gradient rides on the first block: (dY_hi + dY_lo)^T . ones
     TRY(launch_dw_gemm(dy, 0, Mp, x, n0 + nb, Nb, t.c.passes, t.ws.partial, 148, &split, t.n_sms, t.st, with_db ? t.ws.cs_partial : nullptr));
-    dw_reduce_kernel<<<grid1(static_cast<int64_t>(M) * cb, 256), 256, 0, t.st>>>(t.ws.partial, split, Mp, M, Nb, cb, sc, dst, ld, col0 + nb);
+    const int main_blocks = (M * cb + 63) / 64;      // + the bias gradient's blocks (same launch)
+    dw_reduce_kernel<<<main_blocks + (with_db ? (M + 63) / 64 : 0), kDwReduceThreads, 0, t.st>>>(t.ws.partial, split, Mp, M, Nb, cb, sc, dst, ld, col0 + nb,
+                                                                                                main_blocks, with_db ? t.ws.cs_partial : nullptr, db);
     LAUNCH_CHECK("dw_reduce_kernel");
-    if (with_db) {
-      colsum_reduce_kernel<<<(M + 127) / 128, 128, 0, t.st>>>(t.ws.cs_partial, split, Mp, M, sc, db);
-      LAUNCH_CHECK("colsum_reduce_kernel");
-    }
   }
   return NRF_OK;
 }
@@ -701,7 +699,8 @@ extern "C" int nrf_gemm_dw(const void* a_hi, const void* a_lo, int32_t M, const 
   const float one[2] = {1.f, 1.f};
   cudaError_t e = cudaMemcpyAsync(scale2, one, sizeof(one), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(scale)");
-  dw_reduce_kernel<<<grid1(static_cast<int64_t>(M) * N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, split, M, M, N, N, scale2, out, N, 0);
+  dw_reduce_kernel<<<(M * N + 63) / 64, kDwReduceThreads, 0, static_cast<cudaStream_t>(stream)>>>(partial, split, M, M, N, N, scale2, out, N, 0, (M * N + 63) / 64,
+                                                                                                        nullptr, nullptr);
   LAUNCH_CHECK("dw_reduce_kernel");
   return NRF_OK;
 }

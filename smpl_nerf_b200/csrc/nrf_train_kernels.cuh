@@ -64,34 +64,53 @@ __global__ void absmax_kernel(const float* __restrict__ x, int n, unsigned int* 
 // ---------------------------------------------------------------------------------- positional encoding -> planes
 // utils.py:127-131 in REFERENCE feature order ([x?] ++ for k: sin(2^k x), cos(2^k x), each over the 3 components), zero
 // padded to 64 features, as fp16 hi/lo planes [S, 64]: the K-chunk an MLP layer multiplies with its xyz / direction columns.
-__global__ void encode_planes_kernel(const float* __restrict__ x, int64_t S, int freqs, int identity, __half* __restrict__ hi,
-                                     __half* __restrict__ lo, __half* __restrict__ ll) {
-  const int64_t total = S * 8;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t s = idx >> 3;
-    const int f0 = static_cast<int>(idx & 7) * 8;
-    const float v[3] = {x[s * 3], x[s * 3 + 1], x[s * 3 + 2]};
-    const int n_id = identity ? 3 : 0, width = n_id + 6 * freqs;
-    __align__(16) __half h[8];
-    __align__(16) __half l[8];
-    __align__(16) __half q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int f = f0 + i;
-      float val = 0.f;
-      if (f < n_id) val = v[f];
-      else if (f < width) {
-        const int j = f - n_id, k = j / 6, rem = j - 6 * k;
-        float sv, cv;
-        sincos_pe(v[rem % 3] * __int_as_float((127 + k) << 23), sv, cv);
-        val = rem < 3 ? sv : cv;
-      }
-      if (ll) split_store_bf16x3(val, &h[i], &l[i], &q[i]);
-      else split_store(val, &h[i], &l[i]);
+// A block encodes 32 samples: one work item = (sample, frequency, component) -> ONE sincos whose two results are the sin and the cos
+// feature of that (frequency, component) (a thread per feature evaluated every angle twice; the kernel is bound by the range-reduced
+// sincos, 64 us for 393k samples); the [32 x 64] tiles are assembled in shared memory and leave as 16-byte row-contiguous stores.
+constexpr int kEncRows = 32;
+__global__ void __launch_bounds__(256) encode_planes_kernel(const float* __restrict__ x, int64_t S, int freqs, int identity, __half* __restrict__ hi,
+                                                            __half* __restrict__ lo, __half* __restrict__ ll) {
+  __shared__ __align__(16) __half th[kEncRows][64];
+  __shared__ __align__(16) __half tl[kEncRows][64];
+  __shared__ __align__(16) __half tq[kEncRows][64];
+  __shared__ float xs[kEncRows][3];
+  const int64_t s0 = static_cast<int64_t>(blockIdx.x) * kEncRows;
+  const int tid = threadIdx.x;
+  if (tid < kEncRows * 3) { const int64_t i = s0 * 3 + tid; xs[tid / 3][tid % 3] = i < S * 3 ? x[i] : 0.f; }
+  for (int i = tid; i < kEncRows * 64 / 8; i += 256) {      // zero: padding features (and rows past S, never stored)
+    reinterpret_cast<uint4*>(&th[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(&tl[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(&tq[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  const int n_id = identity ? 3 : 0;
+  auto put = [&](int r, int f, float val) {
+    if (ll) split_store_bf16x3(val, &th[r][f], &tl[r][f], &tq[r][f]);
+    else split_store(val, &th[r][f], &tl[r][f]);
+  };
+  const int per = 3 * freqs + n_id;                         // work items per sample: (k, comp) pairs, then the identity components
+  for (int w = tid; w < kEncRows * per; w += 256) {
+    const int r = w / per, j = w - r * per;
+    if (j < 3 * freqs) {
+      const int k = j / 3, comp = j - 3 * k;
+      float sv, cv;
+      sincos_pe(xs[r][comp] * __int_as_float((127 + k) << 23), sv, cv);
+      put(r, n_id + 6 * k + comp, sv);
+      put(r, n_id + 6 * k + 3 + comp, cv);
+    } else {
+      const int comp = j - 3 * freqs;
+      put(r, comp, xs[r][comp]);
     }
-    *reinterpret_cast<uint4*>(hi + s * 64 + f0) = *reinterpret_cast<const uint4*>(h);
-    if (lo) *reinterpret_cast<uint4*>(lo + s * 64 + f0) = *reinterpret_cast<const uint4*>(l);
-    if (ll) *reinterpret_cast<uint4*>(ll + s * 64 + f0) = *reinterpret_cast<const uint4*>(q);
+  }
+  __syncthreads();
+  {
+    const int r = tid >> 3, c8 = (tid & 7) * 8;             // 256 threads = 32 rows x 8 chunks of 8 features
+    const int64_t srow = s0 + r;
+    if (srow < S) {
+      *reinterpret_cast<uint4*>(hi + srow * 64 + c8) = *reinterpret_cast<const uint4*>(&th[r][c8]);
+      if (lo) *reinterpret_cast<uint4*>(lo + srow * 64 + c8) = *reinterpret_cast<const uint4*>(&tl[r][c8]);
+      if (ll) *reinterpret_cast<uint4*>(ll + srow * 64 + c8) = *reinterpret_cast<const uint4*>(&tq[r][c8]);
+    }
   }
 }
 
@@ -430,23 +449,35 @@ __global__ void rayfeat_dw_kernel(const float* __restrict__ dysum, const float* 
   }
   if (k < K && n < n_out) dW[static_cast<size_t>(n) * ld + col0 + k] += acc * __ldg(scale2 + 1);
 }
-// db[m] += inv_scale * sum_split colsum_partial[split][m]      (the ones-column of dw_gemm)
-__global__ void colsum_reduce_kernel(const float* __restrict__ partial, int n_split, int Mp, int M, const float* __restrict__ scale2, float* __restrict__ db) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  float acc = 0.f;
-  for (int s = 0; s < n_split; ++s) acc += partial[static_cast<size_t>(s) * Mp + m];
-  db[m] += acc * __ldg(scale2 + 1);
-}
 // dst[m, col0 + c] += inv_scale * sum_split partial[split][m][c]        (m < M <= Mp rows of the partials, c < cols <= N)
-__global__ void dw_reduce_kernel(const float* __restrict__ partial, int n_split, int Mp, int M, int N, int cols, const float* __restrict__ scale2,
-                                 float* __restrict__ dst, int ld, int col0) {
-  const int total = M * cols;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int m = idx / cols, c = idx - m * cols;
-    float acc = 0.f;
-    for (int s = 0; s < n_split; ++s) acc += partial[(static_cast<size_t>(s) * Mp + m) * N + c];
-    dst[static_cast<size_t>(m) * ld + col0 + c] += acc * __ldg(scale2 + 1);
+// and, in the blocks past the first `main_blocks`, db[m] += inv_scale * sum_split cs_partial[split][m] (the ones-column of dw_gemm).
+// A block owns 64 consecutive outputs; its 4 thread groups each add every 4th split (independent, unrolled loads -- one thread walking
+// all ~74 splits serially was latency bound: 25-45 us for 20 MB) and the 4 sums are combined in a fixed order (deterministic).
+constexpr int kDwReduceThreads = 256;
+__global__ void __launch_bounds__(kDwReduceThreads) dw_reduce_kernel(const float* __restrict__ partial, int n_split, int Mp, int M, int N, int cols,
+                                                                      const float* __restrict__ scale2, float* __restrict__ dst, int ld, int col0,
+                                                                      int main_blocks, const float* __restrict__ cs_partial, float* __restrict__ db) {
+  __shared__ float part[4][64];
+  const int e = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const bool bias_part = static_cast<int>(blockIdx.x) >= main_blocks;
+  const int idx = (bias_part ? blockIdx.x - main_blocks : blockIdx.x) * 64 + e;
+  const bool ok = idx < (bias_part ? M : M * cols);
+  const int m = ok ? (bias_part ? idx : idx / cols) : 0, c = (ok && !bias_part) ? idx - m * cols : 0;
+  const float* src = bias_part ? cs_partial + m : partial + static_cast<size_t>(m) * N + c;
+  const size_t stride = bias_part ? static_cast<size_t>(Mp) : static_cast<size_t>(Mp) * N;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int s = g;
+  if (ok) {
+    for (; s + 12 < n_split; s += 16) {
+      a0 += __ldg(src + s * stride); a1 += __ldg(src + (s + 4) * stride); a2 += __ldg(src + (s + 8) * stride); a3 += __ldg(src + (s + 12) * stride);
+    }
+    for (; s < n_split; s += 4) a0 += __ldg(src + s * stride);
+  }
+  part[g][e] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (g == 0 && ok) {
+    const float v = ((part[0][e] + part[1][e]) + (part[2][e] + part[3][e])) * __ldg(scale2 + 1);
+    if (bias_part) db[m] += v; else dst[static_cast<size_t>(m) * ld + col0 + c] += v;
   }
 }
 
