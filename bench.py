@@ -399,7 +399,7 @@ def run_train(a, w, rank, world, local_rank):
     def step(data):
         out = pipe(data)
         loss = torch.mean((out[0] - data[-1]) ** 2) + torch.mean((out[1] - data[-1]) ** 2)
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad()
         loss.backward()
         if world > 1:
             flat = torch.cat([p.grad.flatten() for p in params])

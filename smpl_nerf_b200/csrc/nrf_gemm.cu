@@ -66,8 +66,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
   const uint32_t b_bytes = P.b_stream ? 0u : static_cast<uint32_t>(nk) * planes * b_chunk;
   const uint32_t a_stage = planes * kATile + (P.b_stream ? planes * b_chunk : 0u);      // streaming mode: [A planes | B planes] per stage
   const uint32_t smem_b = smem_u32(smem), smem_a = smem_b + b_bytes;
-  const int cols_pass = P.n_tile < 128 ? P.n_tile : 128;                // the epilogue walks the accumulator in passes of <= 128 columns
-  const int n_cpass = P.n_tile / cols_pass;
   const uint32_t out_bytes = P.staged ? 32768u : 0u;                    // staging: [128 x 64] fp16 hi block | lo block of one 64-column unit
   const uint32_t smem_o = smem_a + static_cast<uint32_t>(P.n_stages) * a_stage;
   GemmBars* bars = reinterpret_cast<GemmBars*>(smem + b_bytes + static_cast<uint32_t>(P.n_stages) * a_stage + out_bytes);
@@ -213,11 +211,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
     // tile: during the last unit of the previous tile) into the registers the current unit has just finished with, so the round trip
     // hides behind the conversion + staging of the current unit instead of stalling every unit (profiles/r2 timeline).
     float bias[kCT];
-    uint4 mk[kCT / 8];
+    uint32_t mk = 0u;                                     // ReLU' bit mask of the unit's kCT = 32 columns (one word per thread)
 #pragma unroll
     for (int i = 0; i < kCT; ++i) bias[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < kCT / 8; ++i) mk[i] = make_uint4(0u, 0u, 0u, 0u);
     auto aux_load = [&](int64_t mt_l, int u_l) {
       const int64_t row_l = mt_l * rows_tile + rank * 128 + r_t;
       const bool ok = row_l < P.S;
@@ -227,11 +223,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
 #pragma unroll
         for (int i = 0; i < kCT / 4; ++i) { const float4 b = __ldg(bp + i); bias[4 * i] = b.x; bias[4 * i + 1] = b.y; bias[4 * i + 2] = b.z; bias[4 * i + 3] = b.w; }
       }
-      if (P.mask_hi && ok) {
-        const uint4* mp = reinterpret_cast<const uint4*>(P.mask_hi + row_l * P.mask_ld + c0);
-#pragma unroll
-        for (int i = 0; i < kCT / 8; ++i) mk[i] = __ldg(mp + i);
-      }
+      if (P.mask_bits && ok) mk = __ldg(P.mask_bits + row_l * P.bits_ld + (c0 >> 5));
     };
     if (mt0 < n_mt) aux_load(mt0, 0);
     for (int64_t mt = mt0; mt < n_mt; mt += mt_step, ++it) {
@@ -276,16 +268,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < kCT; ++i) x[i] = fmaxf(x[i], 0.f);
         }
-        if (P.mask_hi && row_ok) {
+        if (P.mask_bits && row_ok) {
 #pragma unroll
-          for (int i = 0; i < kCT / 8; ++i) {      // post-ReLU activations are >= 0: "active" = any non-zero bit pattern
-            const uint32_t mw[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+          for (int i = 0; i < kCT; ++i) x[i] = (mk >> i) & 1u ? x[i] : 0.f;
+        }
+        if (P.bits_out && row_ok) {
+          // ReLU' mask for the backward: bit i <=> the fp16 hi half of column i is non-zero (the value the next layer's GEMM sees as
+          // "active"); round-to-nearest-even sends exactly the values <= 2^-25 to zero.  32 x fewer bytes for dX to read than the hi plane.
+          uint32_t wd = 0u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if ((mw[j] & 0x7FFFu) == 0u) x[8 * i + 2 * j] = 0.f;
-              if ((mw[j] & 0x7FFF0000u) == 0u) x[8 * i + 2 * j + 1] = 0.f;
-            }
-          }
+          for (int i = 0; i < kCT; ++i) wd |= x[i] > 2.98023223876953125e-8f ? (1u << i) : 0u;
+          P.bits_out[row * P.bits_ld + (col0 >> 5)] = wd;
         }
         TR(6);
         if (u + 1 < n_units) aux_load(mt, u + 1);          // the next unit's bias / mask (see above)
@@ -385,136 +378,53 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
     if (saturated && P.status) atomicOr(P.status, 2);
     if (P.staged && lane == 0) tma_store_wait_all();
   } else {
-    // ------------------------------------------------------------ epilogue warps, exact mode (single CTA, 128-column slice, unstaged)
+    // ------------------------------------------------------------ epilogue warps, exact mode (inference only: single CTA, one slice of
+    // <= 128 columns, direct stores; no ReLU' mask, no gradient scaling).  The tensor core ROUNDS TOWARD ZERO when it adds into an fp32
+    // accumulator, so every K-chunk arrives in fresh `main` / `corr` accumulators and is added here with round-to-nearest fp32 adds,
+    // starting from the bias.
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const int cols_w = cols_pass / 2;
-    const float s_out = P.sc_out ? __ldg(P.sc_out) : 1.f, inv_out = P.sc_out ? __ldg(P.sc_out + 1) : 1.f;
-    const float ratio = (P.epi == GEPI_F32 ? 1.f : s_out) * (P.sc_in ? __ldg(P.sc_in + 1) : 1.f);     // stored-in -> stored-out (or real)
-    const bool rescale = P.sc_in != nullptr || P.sc_out != nullptr;
-    float l1_run = 0.f;
-    bool saturated = false;
+    const int cols_w = P.n_tile / 2;                      // 64 or 32 columns per thread
+    const int r_t = 32 * q + lane;
     uint32_t it = 0;
-    const bool e0 = warp == 2 && lane == 0;
-    const int r_t = 32 * q + lane;                        // row inside this CTA's 128 rows of the tile
-    int tr_n = 0;
-#ifdef NRF_GEMM_TRACE_BUILD      // developer timeline (build with -DNRF_GEMM_TRACE_BUILD, run with NRF_GEMM_TRACE=n): ~70 issued instructions per unit
-    auto TR = [&](int ev) { if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && e0 && tr_n < 600) { P.trace[2 * tr_n] = ev; P.trace[2 * tr_n + 1] = clock64(); ++tr_n; } };
-#else
-    auto TR = [&](int) {};
-    (void)e0; (void)tr_n;
-#endif
     for (int64_t mt = mt0; mt < n_mt; mt += mt_step) {
-      uint32_t buf = it & 1u;
-      TR(0);
-      const int64_t row = mt * rows_tile + rank * 128 + r_t;
+      const int64_t row = mt * rows_tile + r_t;
       const bool row_ok = row < P.S;
-      const float* bias_row = P.bias ? P.bias + (P.bias_ld ? (row_ok ? row / P.rows_per_ray : 0) * P.bias_ld : 0) : nullptr;
-      const float rs = (P.row_scale && row_ok) ? P.row_scale[row * P.row_scale_ld] * s_out : 0.f;
-      float l1 = 0.f;
-      for (int cp = 0; cp < n_cpass; ++cp) {
-      // this thread's cols_w (<= 64) output columns start from the bias: its global loads (and the ReLU' mask's) are issued
-      // BEFORE the wait for the accumulator, so their latency hides behind the MMAs (loading them per 16-column group after the
-      // TMEM read made the epilogue the bottleneck: long-scoreboard stalls on every group, profiles/r2).  In the exact mode the
-      // K-chunks are then added onto it with round-to-nearest.
+      const int col0 = n0 + half * cols_w;
+      const float* bias_row = (P.bias && row_ok) ? P.bias + (P.bias_ld ? (row / P.rows_per_ray) * P.bias_ld : 0) + col0 : nullptr;
       float sum[64];
-      uint4 mk[2], mk_next[2];       // ReLU' mask of the current / the next 16-column group (fetched one group ahead)
-      const int col0 = n0 + cp * cols_pass + half * cols_w;
-      const uint4* mask_row = (P.mask_hi && row_ok) ? reinterpret_cast<const uint4*>(P.mask_hi + row * P.mask_ld + col0) : nullptr;
-      mk_next[0] = mk_next[1] = make_uint4(0u, 0u, 0u, 0u);
-      if (mask_row) { mk_next[0] = __ldg(mask_row); mk_next[1] = __ldg(mask_row + 1); }
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (g < cols_w / 16) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b = (bias_row && row_ok) ? __ldg(reinterpret_cast<const float4*>(bias_row + col0 + 16 * g) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            sum[16 * g + 4 * i] = b.x; sum[16 * g + 4 * i + 1] = b.y; sum[16 * g + 4 * i + 2] = b.z; sum[16 * g + 4 * i + 3] = b.w;
-          }
-        }
+      for (int i = 0; i < 16; ++i) {
+        const float4 b = (bias_row && 4 * i < cols_w) ? __ldg(reinterpret_cast<const float4*>(bias_row) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sum[4 * i] = b.x; sum[4 * i + 1] = b.y; sum[4 * i + 2] = b.z; sum[4 * i + 3] = b.w;
       }
-      if (kExact) {
-        for (int c = 0; c < nk; ++c, ++it) {
-          buf = it & 1u;
-          mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
-          tc_fence_after_sync();
-          const uint32_t ta = tmem + buf * 2u * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(half * cols_w);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g < cols_w / 16) {
-              uint32_t vm[16], vc[16];
-              tmem_ld16(ta + 16u * g, vm);
-              tmem_ld16(ta + static_cast<uint32_t>(P.n_tile) + 16u * g, vc);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) sum[16 * g + i] = __fadd_rn(sum[16 * g + i], __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
-            }
-          }
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
-        }
-      } else if (cp == 0) {
+      for (int c = 0; c < nk; ++c, ++it) {
+        const uint32_t buf = it & 1u;
         mbar_wait(smem_u32(&bars->acc_full[buf]), (it >> 1) & 1u);
         tc_fence_after_sync();
+        const uint32_t ta = tmem + buf * 2u * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(half * cols_w);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (16 * g < cols_w) {
+            uint32_t vm[16], vc[16];
+            tmem_ld16(ta + 16u * g, vm);
+            tmem_ld16(ta + static_cast<uint32_t>(P.n_tile) + 16u * g, vc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sum[16 * g + i] = __fadd_rn(sum[16 * g + i], __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
       }
-      TR(1);
-      const uint32_t taddr = tmem + buf * static_cast<uint32_t>(P.n_tile) + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(cp * cols_pass + half * cols_w);
-      // staged epilogue: the output tile goes through shared memory ([128 rows x 64 cols] SWIZZLE_128B blocks) and leaves as TMA
-      // stores -- a thread owns ONE ROW, so direct 16-byte stores hit 32 different rows per instruction (32 half-used sectors:
-      // the load/store unit, not the tensor pipe, then sets the tile time; profiles/r2)
-      uint32_t lreg[32];
-      if (P.staged) {                                     // the previous plane has been read out of the staging buffer
-        if (e0) tma_store_wait_read();
-        named_bar_sync(1, 256);
-      }
-      TR(2);
+      if (!row_ok) continue;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        if (g >= cols_w / 16) continue;
-        mk[0] = mk_next[0]; mk[1] = mk_next[1];
-        if (mask_row && g + 1 < cols_w / 16) { mk_next[0] = __ldg(mask_row + 2 * (g + 1)); mk_next[1] = __ldg(mask_row + 2 * (g + 1) + 1); }
-        uint32_t v[16];
-        if (!kExact) {
-          tmem_ld16(taddr + 16u * g, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(sum[16 * g + i]);
-        }
-        if (!row_ok) continue;
+        if (16 * g >= cols_w) continue;
         const int col = col0 + 16 * g;
         float x[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
-        if (rescale) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] *= ratio;
-        }
-        if (!kExact) {           // (exact mode: the bias is already inside the running sum)
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] += sum[16 * g + i];
-        }
-        if (P.row_scale) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = fmaf(rs, __ldg(P.col_vec + col + i), x[i]);
-        }
-        if (P.relu) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
-        }
-        if (P.mask_hi) {
-          const uint4 m0 = mk[0], m1 = mk[1];
-          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {      // post-ReLU activations are >= 0: "active" = any non-zero bit pattern
-            if ((mw[i] & 0x7FFFu) == 0u) x[2 * i] = 0.f;
-            if ((mw[i] & 0x7FFF0000u) == 0u) x[2 * i + 1] = 0.f;
-          }
-        }
-        if (P.l1max) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) l1 += fabsf(x[i]);
-        }
+        for (int i = 0; i < 16; ++i) x[i] = P.relu ? fmaxf(sum[16 * g + i], 0.f) : sum[16 * g + i];
         if (P.epi == GEPI_F32) {
           float4* op = reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col);
 #pragma unroll
@@ -523,108 +433,36 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             if (P.accumulate) { const float4 t = op[i]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
             op[i] = o;
           }
-        } else {
-          uint32_t h[8], l[8], ll[8];
-          if (kExact) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {      // x = hi + lo + ll exactly (3 x 8 significant bits), fp32 exponent range
-              float r0 = x[2 * i], r1 = x[2 * i + 1];
-              const __nv_bfloat162 b0 = __floats2bfloat162_rn(r0, r1);
-              r0 -= __low2float(b0); r1 -= __high2float(b0);
-              const __nv_bfloat162 b1 = __floats2bfloat162_rn(r0, r1);
-              r0 -= __low2float(b1); r1 -= __high2float(b1);
-              const __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
-              h[i] = *reinterpret_cast<const uint32_t*>(&b0); l[i] = *reinterpret_cast<const uint32_t*>(&b1); ll[i] = *reinterpret_cast<const uint32_t*>(&b2);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              saturated |= fabsf(x[2 * i]) > 65504.f || fabsf(x[2 * i + 1]) > 65504.f;
-              h[i] = cvt_f16x2_satfinite(x[2 * i], x[2 * i + 1]);
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
-              l[i] = cvt_f16x2_satfinite(x[2 * i] - f.x, x[2 * i + 1] - f.y);
-            }
-          }
-          if (P.staged) {
-            const int ct = half * cols_w + 16 * g;        // column inside the pass -> 64-column block, 16-byte chunk
-            const uint32_t blk = smem_o + static_cast<uint32_t>(ct >> 6) * 16384u + static_cast<uint32_t>(r_t) * 128u;
-            const uint32_t ch = static_cast<uint32_t>(ct & 63) >> 3;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch) ^ (r_t & 7u)) << 4)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch + 1u) ^ (r_t & 7u)) << 4)), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
-#pragma unroll
-            for (int i = 0; i < 8; ++i) lreg[8 * g + i] = l[i];
-          } else {
-            uint4* ph = reinterpret_cast<uint4*>(P.out_hi + row * P.out_ld + col);
-            ph[0] = make_uint4(h[0], h[1], h[2], h[3]); ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
-            if (P.out_lo) {
-              uint4* pl = reinterpret_cast<uint4*>(P.out_lo + row * P.out_ld + col);
-              pl[0] = make_uint4(l[0], l[1], l[2], l[3]); pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
-            }
-          }
-          if (kExact && P.out_ll) {
-            uint4* pq = reinterpret_cast<uint4*>(P.out_ll + row * P.out_ld + col);
-            pq[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]); pq[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
-          }
-          if (P.out_f32) {
-            float4* op = reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) op[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-          }
+          continue;
         }
-      }
-      if (!kExact && cp == n_cpass - 1) {                  // the accumulator has been read completely: hand it back to the issuer
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) { if (kPair && rank != 0) mbar_arrive_cluster_relaxed(smem_u32(&bars->acc_empty[buf]), 0); else mbar_arrive(smem_u32(&bars->acc_empty[buf])); }
-        ++it;
-      }
-      if (P.staged) {
-        const int32_t r0 = static_cast<int32_t>(mt * rows_tile + rank * 128);
-        const int32_t c0 = n0 + cp * cols_pass;
-        TR(3);
-        fence_proxy_async_smem();
-        named_bar_sync(1, 256);                            // hi plane of this pass is in the staging buffer
-        TR(4);
-        if (e0) {
-          for (int b = 0; b < cols_pass / 64; ++b) tma_store_2d(&P.o_map[0], c0 + 64 * b, r0, smem_o + static_cast<uint32_t>(b) * 16384u);
-          tma_store_commit();
-          if (P.out_lo) tma_store_wait_read();
+        uint32_t h[8], l[8], ll[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {      // x = hi + lo + ll exactly (3 x 8 significant bits), fp32 exponent range
+          float r0 = x[2 * i], r1 = x[2 * i + 1];
+          const __nv_bfloat162 b0 = __floats2bfloat162_rn(r0, r1);
+          r0 -= __low2float(b0); r1 -= __high2float(b0);
+          const __nv_bfloat162 b1 = __floats2bfloat162_rn(r0, r1);
+          r0 -= __low2float(b1); r1 -= __high2float(b1);
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
+          h[i] = *reinterpret_cast<const uint32_t*>(&b0); l[i] = *reinterpret_cast<const uint32_t*>(&b1); ll[i] = *reinterpret_cast<const uint32_t*>(&b2);
         }
-        TR(5);
+        uint4* ph = reinterpret_cast<uint4*>(P.out_hi + row * P.out_ld + col);
+        ph[0] = make_uint4(h[0], h[1], h[2], h[3]); ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
         if (P.out_lo) {
-          named_bar_sync(1, 256);                          // ... and has been read: the lo plane takes its place
-          TR(6);
+          uint4* pl = reinterpret_cast<uint4*>(P.out_lo + row * P.out_ld + col);
+          pl[0] = make_uint4(l[0], l[1], l[2], l[3]); pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+        }
+        if (P.out_ll) {
+          uint4* pq = reinterpret_cast<uint4*>(P.out_ll + row * P.out_ld + col);
+          pq[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]); pq[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+        }
+        if (P.out_f32) {
+          float4* op = reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g >= cols_w / 16) continue;
-            const int ct = half * cols_w + 16 * g;
-            const uint32_t blk = smem_o + static_cast<uint32_t>(ct >> 6) * 16384u + static_cast<uint32_t>(r_t) * 128u;
-            const uint32_t ch = static_cast<uint32_t>(ct & 63) >> 3;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch) ^ (r_t & 7u)) << 4)), "r"(lreg[8 * g]), "r"(lreg[8 * g + 1]), "r"(lreg[8 * g + 2]), "r"(lreg[8 * g + 3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch + 1u) ^ (r_t & 7u)) << 4)), "r"(lreg[8 * g + 4]), "r"(lreg[8 * g + 5]), "r"(lreg[8 * g + 6]), "r"(lreg[8 * g + 7]) : "memory");
-          }
-          TR(7);
-          fence_proxy_async_smem();
-          named_bar_sync(1, 256);
-          TR(8);
-          if (e0) {
-            for (int b = 0; b < cols_pass / 64; ++b) tma_store_2d(&P.o_map[1], c0 + 64 * b, r0, smem_o + static_cast<uint32_t>(b) * 16384u);
-            tma_store_commit();
-          }
+          for (int i = 0; i < 4; ++i) op[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
         }
       }
-      }   // column passes
-      l1_run = fmaxf(l1_run, l1);
     }
-    if (P.staged && e0) tma_store_wait_all();
-    if (P.l1max) {
-      // real units; a row's L1 norm is bounded by (number of column segments it is split into) x the largest segment sum
-      l1_run *= (P.epi == GEPI_F32 ? 1.f : inv_out) * static_cast<float>(gridDim.y * 2);       // two column halves (warp groups) per slice
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) l1_run = fmaxf(l1_run, __shfl_xor_sync(0xffffffffu, l1_run, o));
-      if (lane == 0 && isfinite(l1_run)) atomicMax(P.l1max, __float_as_uint(l1_run));
-    }
-    if (saturated && P.status) atomicOr(P.status, 2);
   }
   tc_fence_before_sync();
   if (kPair) cluster_sync_all(); else __syncthreads();       // pair: neither CTA may exit (or free TMEM) while its peer can still address it
@@ -853,7 +691,7 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
   P.n_stages = stages > 4 ? 4 : stages;
   P.epi = a.epi; P.relu = a.relu; P.bias = a.bias; P.bias_ld = a.bias_ld; P.rows_per_ray = a.rows_per_ray > 0 ? a.rows_per_ray : 1;
   P.out_hi = a.out.hi; P.out_lo = a.out.lo; P.out_ll = a.out.ll; P.out_ld = a.out.ld; P.out_f32 = a.out_f32; P.out_f32_ld = a.out_f32_ld; P.accumulate = a.accumulate;
-  P.mask_hi = a.mask_hi; P.mask_ld = a.mask_ld; P.row_scale = a.row_scale; P.row_scale_ld = a.row_scale_ld; P.col_vec = a.col_vec;
+  P.mask_bits = a.mask_bits; P.bits_out = a.bits_out; P.bits_ld = a.bits_ld; P.row_scale = a.row_scale; P.row_scale_ld = a.row_scale_ld; P.col_vec = a.col_vec;
   P.sc_in = a.sc_in; P.sc_out = a.sc_out; P.l1max = a.l1max; P.status = a.status;
   if (a.epi == GEPI_PLANES && !a.out.hi) { set_error("tile_gemm: planes epilogue without an output"); return NRF_E_INVALID; }
   if (a.epi == GEPI_F32 && !a.out_f32) { set_error("tile_gemm: fp32 epilogue without an output"); return NRF_E_INVALID; }
@@ -902,7 +740,7 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
     static long long host[1200];
     cudaStreamSynchronize(stream);
     cudaMemcpy(host, dbg_trace, sizeof(host), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[tile_gemm trace] pair=%d staged=%d stages=%d mask=%d b_mn=%d\n", pair ? 1 : 0, P.staged, P.n_stages, a.mask_hi ? 1 : 0, P.b_mn);
+    fprintf(stderr, "[tile_gemm trace] pair=%d staged=%d stages=%d mask=%d b_mn=%d\n", pair ? 1 : 0, P.staged, P.n_stages, a.mask_bits ? 1 : 0, P.b_mn);
     long long t0 = host[1];
     for (int i = 0; i < 600 && host[2 * i + 1]; ++i) { fprintf(stderr, "%lld:%lld ", host[2 * i], host[2 * i + 1] - t0); if (host[2 * i] == 8 || (i + 1 < 600 && host[2 * (i + 1)] == 0)) fprintf(stderr, "\n"); }
     fprintf(stderr, "\n");

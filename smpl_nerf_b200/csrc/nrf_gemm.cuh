@@ -43,7 +43,8 @@ struct TileGemmParams {
   const float* bias; int32_t bias_ld; int32_t rows_per_ray;      // bias[(row / rows_per_ray) * bias_ld + col]  (bias_ld = 0: one vector)
   __half* out_hi; __half* out_lo; __half* out_ll; int32_t out_ld;
   float* out_f32; int32_t out_f32_ld; int32_t accumulate;
-  const __half* mask_hi; int32_t mask_ld;                         // keep out[row, col] only where mask_hi[row, col] > 0 (ReLU')
+  const uint32_t* mask_bits; uint32_t* bits_out; int32_t bits_ld;  // ReLU' bit masks, bits_ld words per row: keep out[row, col] only where bit col of
+                                                                   // mask_bits[row] is set (dX); bits_out[row] receives bit col <=> hi(out[row, col]) != 0 (forward)
   const float* row_scale; int32_t row_scale_ld; const float* col_vec;   // + row_scale[row * ld] * sc_out[0] * col_vec[col]
   // gradient scaling (all NULL in the forward): the A planes hold real * sc_in[0]; the output planes are written as
   // real * sc_out[0] (sc_x = {s, 1/s}, powers of two); GEPI_F32 writes REAL values.  l1max (float bits, atomicMax) receives
@@ -80,7 +81,7 @@ struct TileGemmArgs {
   int epi, relu;
   const float* bias; int bias_ld; int rows_per_ray;
   Planes out; float* out_f32; int out_f32_ld; int accumulate;
-  const __half* mask_hi; int mask_ld;
+  const uint32_t* mask_bits; uint32_t* bits_out; int bits_ld;
   const float* row_scale; int row_scale_ld; const float* col_vec;
   const float* sc_in; const float* sc_out; unsigned int* l1max;
   int32_t* status;

@@ -81,6 +81,7 @@ static inline int wslot(int p, int l) { return p * 20 + l; }
 struct PassWs {
   int64_t S; int n;
   Planes encx, encd, wpe, warph, act[kMaxLayers];
+  uint32_t* bits[kMaxLayers];      // ReLU' bit masks of the ReLU layers ([S, n_out / 32] words): what the backward reads instead of the hi plane
   float *a_f32, *h2_f32, *warph_f32, *raw, *dnorm, *warp_raw, *warped, *u, *rb[kMaxLayers], *rbw, *g_raw, *g_dnorm, *z;
   const float* pts;
 };
@@ -134,6 +135,7 @@ static void layout_ws(Bump& m, const TrainCfg& c, const TNet net[2], TrainWs* ws
     for (int l = 0; l < net[p].n; ++l) {
       const TLayer& L = net[p].L[l];
       w.act[l] = m.planes(w.S, L.n_out, lo);
+      w.bits[l] = L.relu ? m.take<uint32_t>(static_cast<size_t>(w.S) * (L.n_out / 32)) : nullptr;
       if (L.ray_src) w.rb[l] = m.take<float>(static_cast<size_t>(c.B) * L.n_out);
     }
     w.a_f32 = m.take<float>(static_cast<size_t>(w.S) * net[p].W);
@@ -333,6 +335,7 @@ static int forward_pass(TrainCtx& t, int p) {
     g.bias = bias; g.bias_ld = L.ray_src ? L.n_out : 0; g.rows_per_ray = w.n; g.out = w.act[l];
     if (L.role == ROLE_LINEAR) { g.out_f32 = w.a_f32; g.out_f32_ld = net.W; }
     if (L.role == ROLE_RGB) { g.out_f32 = w.h2_f32; g.out_f32_ld = net.W / 2; }
+    if (L.relu) { g.bits_out = w.bits[l]; g.bits_ld = L.n_out / 32; }
     g.status = t.io.status;
     TRY(launch_tile_gemm(g, t.n_sms, t.st));
   }
@@ -505,7 +508,7 @@ static int backward_pass(TrainCtx& t, int p, const Grads& G) {
       TileGemmArgs a{};
       a.a[0] = dy; a.b[0] = t.ws.w[p].act[l]; a.n_src = 1; a.b_mn = 1; a.N = L.in_act; a.passes = c.passes; a.epi = GEPI_PLANES;
       a.out = view(t.ws.dy[cur ^ 1], L.in_act, w.S);
-      if (Pv.relu) { a.mask_hi = w.act[l - 1].hi; a.mask_ld = w.act[l - 1].ld; }
+      if (Pv.relu) { a.mask_bits = w.bits[l - 1]; a.bits_ld = Pv.n_out / 32; }
       if (dir) { a.row_scale = w.g_raw + 3; a.row_scale_ld = 4; a.col_vec = t.par[p][2 * nl + 2]; }
       a.sc_in = sc; a.sc_out = SC(slot + 1); a.l1max = MX(slot + 1); a.status = t.io.status;
       TRY(launch_tile_gemm(a, t.n_sms, t.st));

@@ -25,7 +25,7 @@ data = [t[:B].to(dev) for t in scene.data_list(rays, 'smpl')]
 def step():
     out = pipe(data)
     loss = torch.mean((out[0] - data[-1]) ** 2) + torch.mean((out[1] - data[-1]) ** 2)
-    opt.zero_grad(set_to_none=False)
+    opt.zero_grad()
     loss.backward()
     opt.step()
 
