@@ -1,13 +1,15 @@
 #!/bin/bash
 # Assemble profiles/r2/ (tracked) from gpurun_out/ (scratch): run here, on the CPU box, after tools/gpu_round2.sh + tools/prof_train.sh.
-#   bash tools/collect_profiles_r2.sh <sweep dir, e.g. gpurun_out/r2a> <train capture dir, e.g. gpurun_out/r2b>
+#   bash tools/collect_profiles_r2.sh <sweep dir, e.g. gpurun_out/r2f> [<train capture dir if separate>]
 set -e
-SW=${1:-gpurun_out/r2a}; TR=${2:-gpurun_out/r2b}; OUT=profiles/r2
+SW=${1:-gpurun_out/r2f}; TR=${2:-$SW}; OUT=profiles/r2
 mkdir -p $OUT
 cp $SW/bench_*.json $SW/smi.txt $SW/nproc.txt $OUT/ 2>/dev/null || true
 cp $SW/launches_cfg2_parity.csv $OUT/launches_cfg2_parity.csv
 cp $SW/sanitizer_train.txt $OUT/ 2>/dev/null || true
 cp $SW/train_step_kernels.txt $OUT/ 2>/dev/null || true
+cp $SW/grad_errors_*.txt $OUT/ 2>/dev/null || true
+rm -f $OUT/ncu_full_prof_tile_gemm_*.txt
 for f in timeline_cfg2_parity.txt timeline_cfg2_fast.txt launches_train.csv; do [ -f $TR/$f ] && cp $TR/$f $OUT/$f; done
 digest() {   # <ncu-rep> <out txt> <title>
   ncu -i $1 --page raw --csv > /tmp/_raw.csv 2>/dev/null; ncu -i $1 --page source --csv > /tmp/_src.csv 2>/dev/null

@@ -25,13 +25,20 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --c
 echo "== ncu full: fused kernel"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:nrf_fused -s 3 -c 1 -f -o $OUT/prof_fused \
    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
-echo "== ncu launch list + full captures: training step"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'tile_gemm|dw_gemm|head_bwd|colsum|bias_grad|dw_reduce|heads_kernel|encode_planes|composite|smpl_points|rayfeat|ray_bias2|split_planes|fine_sampling' \
-   -s 1500 -c 460 --csv --log-file $OUT/launches_train.csv python tools/train_profile.py 2048 > $OUT/ncu_launches_train.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tile_gemm -s 600 -c 2 -f -o $OUT/prof_tile_gemm \
-   python tools/train_profile.py 2048 > $OUT/ncu_full_tile.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:dw_gemm -s 300 -c 2 -f -o $OUT/prof_dw_gemm \
+echo "== ncu launch list (durations + DRAM bytes) + full captures: training step"
+# tools/train_profile.py runs 8 steps; one step = 50 tile_gemm + 28 dw_gemm launches.  tile_gemm 315 = a fine-pass 256x256 forward layer
+# (393,216 samples), 342 = a fine-pass dX launch, dw_gemm 188 = a fine-pass 256x256 dW.
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+   -k regex:'tile_gemm|dw_gemm|head_bwd|colsum|bias_grad|dw_reduce|heads_kernel|encode_planes|composite|smpl_points|rayfeat|ray_bias|split_planes|fine_sampling|absmax|scale_from|ray_feats|points_from' \
+   -s 1000 -c 160 --csv --log-file $OUT/launches_train.csv python tools/train_profile.py 2048 > $OUT/ncu_launches_train.log 2>&1
+for skip in 315 342; do
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:tile_gemm -s $skip -c 1 -f -o $OUT/prof_tile_gemm_$skip \
+   python tools/train_profile.py 2048 > $OUT/ncu_full_tile_$skip.log 2>&1
+done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:dw_gemm -s 188 -c 1 -f -o $OUT/prof_dw_gemm \
    python tools/train_profile.py 2048 > $OUT/ncu_full_dw.log 2>&1
+echo "== gradient error tables"
+for k in nerf append smpl; do timeout 300 python tools/dbg_grad.py $k > $OUT/grad_errors_$k.txt 2>&1; done
 echo "== compute-sanitizer (memcheck) on the training tests"
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_train.py -x -q -k "gemm or forward_matches or fp64_autograd and nerf" > $OUT/sanitizer_train.txt 2>&1; echo "rc=$?" >> $OUT/sanitizer_train.txt
-ls -la $OUT
+ls -la $OUT; du -sh gpurun_out
