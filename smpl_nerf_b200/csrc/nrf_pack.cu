@@ -15,7 +15,7 @@ namespace nrf {
 
 // ------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
-thread_local long long g_train_launches = 0;
+std::atomic<long long> g_train_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;

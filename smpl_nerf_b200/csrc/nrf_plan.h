@@ -18,6 +18,7 @@
 // stages only half r of every stage and each M=256 x N instruction reads both halves.
 #pragma once
 #include <stdint.h>
+#include <atomic>
 #include <cuda_runtime.h>
 
 #include "../../include/nrf_b200.h"
@@ -89,7 +90,7 @@ int plan_warpnet(const NrfWarpNetDesc* d, NetPlan* plan);
 int launch_rows_differ(const float* feats, int64_t B, int A, int32_t* flag, cudaStream_t stream);   // nrf_ops.cu
 void set_error(const char* fmt, ...);
 // per-thread count of kernels launched by the training path (nrf_train_launch_count(): bench.py's gpu_launches accounting)
-extern thread_local long long g_train_launches;
+extern std::atomic<long long> g_train_launches;      // process-wide: the backward runs on autograd's worker thread
 int cuda_fail(int err, const char* what);
 
 // Number of aux features (<= 64) an encoder produces for a 3-vector, and the reference column of

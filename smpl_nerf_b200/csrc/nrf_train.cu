@@ -594,7 +594,7 @@ extern "C" int nrf_train_backward(const NrfPipelineDesc* pipe, const NrfRayNetDe
   return NRF_OK;
 }
 
-extern "C" long long nrf_train_launch_count(int reset) { const long long n = g_train_launches; if (reset) g_train_launches = 0; return n; }
+extern "C" long long nrf_train_launch_count(int reset) { return reset ? g_train_launches.exchange(0) : g_train_launches.load(); }
 
 // ------------------------------------------------------------------------------ per-ray pose bias of AppendSmplParamsPipeline (tcgen05)
 // out[b, e, n] = bias_e[n] + sum_k W_e[n, col0_e + k] * feats[b, k]     b < B, n < 256, k < A  (A = 69 or 1380)

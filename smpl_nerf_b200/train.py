@@ -38,9 +38,52 @@ def _ptr_table(tensors: List[torch.Tensor]):
     return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
+# One training workspace per device is kept between steps (a solver loop asks for the same ~1.2 MB per ray every step; handing it back
+# to PyTorch's caching allocator each time let any >1 MB allocation made between two steps -- e.g. the next batch's host->device copy --
+# split the cached block, and the following step then paid a multi-GB cudaMalloc).  A forward whose graph is still alive owns the cached
+# buffer; a second forward issued before that backward gets a private allocation.  The buffer is reused in stream order: issue the
+# steps of one device from one stream (what the reference's solvers do).
+_ws_cache: Dict[int, list] = {}      # device index -> [uint8 tensor, in use]
+
+
+def _ws_acquire(device, nbytes: int):
+    ent = _ws_cache.get(device.index)
+    if ent is not None and not ent[1] and ent[0].numel() >= nbytes:
+        ent[1] = True
+        return ent[0], True
+    t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    if ent is None or not ent[1]:
+        _ws_cache[device.index] = [t, True]
+        return t, True
+    return t, False
+
+
+def _ws_release(device, t) -> None:
+    ent = _ws_cache.get(device.index)
+    if ent is not None and ent[0] is t:
+        ent[1] = False
+
+
+def release_workspaces() -> None:
+    """Drop the cached training workspaces (they are otherwise kept until the process ends)."""
+    for k in [k for k, ent in _ws_cache.items() if not ent[1]]:
+        del _ws_cache[k]
+
+
 class _Call:
     """Everything one forward/backward pair shares (descs, io struct, tensors kept alive)."""
-    __slots__ = ('pipe', 'dc', 'df', 'dw', 'io', 'B', 'n_c', 'n_f', 'n_w', 'keep', 'workspace', 'device', 'smpl', 'run_fine', 'n_sms')
+    __slots__ = ('pipe', 'dc', 'df', 'dw', 'io', 'B', 'n_c', 'n_f', 'n_w', 'keep', 'rgb_bufs', 'workspace', 'ws_cached', 'device', 'smpl', 'run_fine', 'n_sms')
+
+    def drop_workspace(self) -> None:
+        if self.workspace is not None and self.ws_cached:
+            _ws_release(self.device, self.workspace)
+        self.workspace = None
+
+    def __del__(self):          # a graph that is never back-propagated (loss only evaluated) frees the cached buffer too
+        try:
+            self.drop_workspace()
+        except Exception:
+            pass
 
 
 class RenderTrain(torch.autograd.Function):
@@ -59,7 +102,7 @@ class RenderTrain(torch.autograd.Function):
                                                    C.byref(call.dw) if call.dw is not None else None, call.B)
             if ws_bytes == 0:
                 check(-1, 'nrf_train_workspace_bytes')
-            call.workspace = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=call.device)
+            call.workspace, call.ws_cached = _ws_acquire(call.device, ws_bytes + 256)
             off = (-call.workspace.data_ptr()) % 256
             rc = L.nrf_train_forward(C.byref(call.pipe), C.byref(call.dc), _ptr_table(pc), len(pc),
                                      C.byref(call.df) if call.df is not None else None, _ptr_table(pf) if pf else None, len(pf),
@@ -68,14 +111,18 @@ class RenderTrain(torch.autograd.Function):
             check(rc, 'nrf_train_forward')
         ctx.call = call
         ctx.save_for_backward(*params)
-        out = call.keep['out']
-        res = [out['rgb']] + ([out['rgb_fine']] if call.run_fine else [])
+        # the colour buffers become the graph-carrying outputs: the call must not keep them (tensor -> grad_fn -> ctx -> call would be a
+        # reference cycle through C++ that Python's collector cannot see; every step would leak its outputs and its workspace)
+        res, call.rgb_bufs = call.rgb_bufs, None
         return tuple(res)
 
     @staticmethod
     def backward(ctx, *gs):
         call: _Call = ctx.call
         L = _lib.lib()
+        if call.workspace is None:
+            raise RuntimeError('smpl_nerf_b200: backward through this pipeline call ran already (its saved activations are released after the '
+                               'first backward; retain_graph is not supported)')
         params = ctx.saved_tensors
         ps = [p.detach() for p in params]
         pc, pf, pw = ps[:call.n_c], ps[call.n_c:call.n_c + call.n_f], ps[call.n_c + call.n_f:]
@@ -96,7 +143,7 @@ class RenderTrain(torch.autograd.Function):
                                       g_rgb.data_ptr(), g_fine.data_ptr() if g_fine is not None else None,
                                       _ptr_table(gc), _ptr_table(gf) if gf else None, _ptr_table(gw) if gw else None, call.n_sms, stream)
             check(rc, 'nrf_train_backward')
-        call.workspace = None        # one backward per forward (like retain_graph=False)
+        call.drop_workspace()        # one backward per forward (like retain_graph=False)
         return (None,) + tuple(grads)
 
 
@@ -114,8 +161,10 @@ def render_train(kind: str, model_coarse, model_fine, model_warp, pipe: Pipeline
     call.n_f = len(params[1]) if run_fine else 0
     call.n_w = len(params[-1]) if kind == 'smpl' else 0
     call.smpl, call.run_fine, call.n_sms = kind == 'smpl', run_fine, int(n_sms)
-    call.keep = {'out': out, 'inputs': keep}
-    call.workspace = None
+    call.rgb_bufs = [out['rgb']] + ([out['rgb_fine']] if run_fine else [])
+    call.keep = {'out': {k: v for k, v in out.items() if k not in ('rgb', 'rgb_fine')}, 'inputs': keep,
+                 'rgb_storage': [t.detach() for t in call.rgb_bufs]}      # graph-less aliases: the io struct points into them
+    call.workspace, call.ws_cached = None, False
     flat = [p for ps in params for p in ps]
     res = RenderTrain.apply(call, *flat)
     out['rgb'] = res[0]

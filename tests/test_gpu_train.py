@@ -352,6 +352,67 @@ def test_eval_mode_and_no_grad_stay_on_the_fused_kernel():
         engine.render('nerf', gnets[0], gnets[1], None, args, gnets[3], gnets[4], None, gdata, trace_cap=16)
 
 
+def test_workspace_cache_and_two_live_graphs():
+    """The training workspace is cached per device between steps.  A second forward issued while the first graph is still alive
+    must not share it; a backward may run only once; a graph that is dropped without a backward hands the buffer back."""
+    from smpl_nerf_b200 import train as TR
+    nets = _build('nerf', 3, 4, (2,))
+    args = O.make_args(number_fine_samples=32)
+    d1 = _rays('nerf', 6, 6, 32, 2)
+    d2 = _rays('nerf', 6, 6, 32, 9)
+    gnets, g1 = H.to_cuda(nets, d1)
+    _, g2 = H.to_cuda(nets, d2)
+    for m in gnets[:2]:
+        m.train()
+    pipe = _pipe('nerf', gnets, args)
+    params = [p for m in gnets[:2] for p in m.parameters()]
+
+    def grads(data):
+        for p in params:
+            p.grad = None
+        _loss(pipe(data), data[-1]).backward()
+        return [p.grad.clone() for p in params]
+
+    ref1, ref2 = grads(g1), grads(g2)
+    dev = g1[0].device.index
+    grads(g1)
+    torch.cuda.synchronize()
+    m0 = torch.cuda.memory_allocated()
+    for _ in range(3):                                        # no per-step leak (outputs, workspace) once the graphs are gone
+        grads(g1)
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_allocated() <= m0
+    assert TR._ws_cache[dev][1] is False                      # released by the backward
+    cached = TR._ws_cache[dev][0]
+    # two graphs alive at once: the second forward gets a private buffer, both backward passes reproduce the separate runs
+    for p in params:
+        p.grad = None
+    o1 = pipe(g1)
+    assert TR._ws_cache[dev][1] is True and TR._ws_cache[dev][0] is cached
+    o2 = pipe(g2)
+    l1, l2 = _loss(o1, g1[-1]), _loss(o2, g2[-1])
+    l2.backward()
+    got2 = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    l1.backward()
+    got1 = [p.grad.clone() for p in params]
+    for a_, b_ in zip(got1 + got2, ref1 + ref2):
+        assert torch.allclose(a_, b_, rtol=1e-4, atol=1e-7 * float(b_.abs().max()) + 1e-12)      # (head gradients use float atomics)
+    assert TR._ws_cache[dev][1] is False
+    with pytest.raises(RuntimeError):
+        l1.backward()
+    # a graph that is never back-propagated frees the cached buffer when it dies
+    o3 = pipe(g1)
+    assert TR._ws_cache[dev][1] is True
+    del o3
+    import gc
+    gc.collect()
+    assert TR._ws_cache[dev][1] is False
+    TR.release_workspaces()
+    assert dev not in TR._ws_cache
+
+
 @pytest.mark.parametrize('kind', ['nerf', 'append', 'smpl'])
 def test_solver_loop_tracks_the_reference_loop(kind):
     """solver/nerf_solver.py:76-88 / solver/smpl_nerf_solver.py:66-83: 50 Adam steps on the drop-in pipeline (GPU) and on

@@ -30,7 +30,7 @@ echo "== ncu launch list (durations + DRAM bytes) + full captures: training step
 # (393,216 samples), 342 = a fine-pass dX launch, dw_gemm 188 = a fine-pass 256x256 dW.
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
    -k regex:'tile_gemm|dw_gemm|head_bwd|colsum|bias_grad|dw_reduce|heads_kernel|encode_planes|composite|smpl_points|rayfeat|ray_bias|split_planes|fine_sampling|absmax|scale_from|ray_feats|points_from' \
-   -s 1000 -c 160 --csv --log-file $OUT/launches_train.csv python tools/train_profile.py 2048 > $OUT/ncu_launches_train.log 2>&1
+   -s 900 -c 420 --csv --log-file $OUT/launches_train.csv python tools/train_profile.py 2048 > $OUT/ncu_launches_train.log 2>&1
 for skip in 315 342; do
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tile_gemm -s $skip -c 1 -f -o $OUT/prof_tile_gemm_$skip \
    python tools/train_profile.py 2048 > $OUT/ncu_full_tile_$skip.log 2>&1
