@@ -58,6 +58,7 @@ WORKLOADS = {
     'cfg5': dict(kind='smpl', side=512, n_coarse=64, n_fine=128, run_fine=1, n_layers=8, skips=[4], strong=True,
                  text='smpl_nerf_pipeline, 512x512 full-frame render, rays sharded over the GPUs (BASELINE configs[4])'),
 }
+TRAIN_TRAFFIC_GB = {'parity': 39.9}      # measured DRAM traffic of one --workload train step (ncu, profiles/r2/train_step_launch_summary.txt)
 N_VIEWS = 8          # rotating distinct input views so that consecutive steps never reuse inputs
 
 
@@ -92,6 +93,30 @@ def flops_per_ray(w, coarse, fine, warp):
     if warp is not None:
         total += mac(warp) * (nc + (na if w['run_fine'] else 0))
     return 2.0 * total
+
+
+def train_plane_bytes_per_ray(w, coarse, fine, warp, planes=2):
+    """Algorithmic HBM bytes of the layer-by-layer training step per ray: every nn.Linear with >= 64 outputs over S
+    samples streams its input and output as `planes` 16-bit planes three times -- forward (read X, write Y), dX (read dY, write dX) and dW
+    (read dY, read X): 3 x 2 B x planes x (K + N) per sample, K = per-sample inputs padded to 64-feature chunks (per-ray inputs are folded
+    into a bias).  The fp32 head copies, encodings and reductions are NOT counted (they are in the measured traffic)."""
+    pad = lambda k: (k + 63) // 64 * 64
+
+    def per_sample(net, per_ray_in=0):
+        tot = 0
+        for m in net.modules():
+            if isinstance(m, torch.nn.Linear) and m.out_features >= 64:
+                k = m.in_features - (per_ray_in if m.in_features > per_ray_in and per_ray_in and m is first[id(net)] else 0)
+                tot += pad(k) + m.out_features
+        return 3 * 2 * planes * tot
+
+    first = {id(n): next(m for m in n.modules() if isinstance(m, torch.nn.Linear)) for n in (coarse, fine, warp) if n is not None}
+    nc, na = w['n_coarse'], w['n_coarse'] + (w['n_fine'] if w['run_fine'] else 0)
+    total = per_sample(coarse) * nc + (per_sample(fine) * na if w['run_fine'] else 0)
+    if warp is not None:
+        pose = first[id(warp)].in_features - int(getattr(warp, 'positions_dim', first[id(warp)].in_features))      # encoded pose columns: constant per ray
+        total += per_sample(warp, pose) * (nc + (na if w['run_fine'] else 0))
+    return float(total)
 
 
 def make_views(w, rank, n_views, world=1):
@@ -462,6 +487,10 @@ def run_train(a, w, rank, world, local_rank):
     peak_tf = float(peaks.get('bf16_tflops' if burst else 'bf16_tflops_sustained', 1650.0 if burst else 1400.0))
     n_total = B * world
     achieved = 3.0 * fl_ray * B / (ms_median / 1e3) / 1e12
+    planes = 1 if a.precision == 'fast' else 2
+    bytes_ray = train_plane_bytes_per_ray(w, nets[0], nets[1], nets[2], planes)
+    hbm_peak = float(peaks.get('hbm_gbs', 6500.0))
+    hbm_achieved = bytes_ray * B / (ms_median / 1e3) / 1e9
     h2d = sum(x.numel() * x.element_size() for x in batches_host[0])
     line = {
         'metric': 'rays/sec', 'value': n_total / (ms_median / 1e3), 'unit': 'rays/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
@@ -475,11 +504,17 @@ def run_train(a, w, rank, world, local_rank):
         'clocks': clocks,
         'e2e': {'value': n_total * a.steps / (ms_e2e / 1e3), 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
         'gpu_launches': launches,
-        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None,
-                     'flop_per_ray': 3.0 * fl_ray, 'kernel': 'tile_gemm_kernel + dw_gemm_kernel (whole step timed)', 'kernel_ms': ms_median,
-                     'peak_source': ('MEASURED_PEAKS.json ' if peaks else 'fallback ') + ('burst' if burst else 'sustained'),
-                     'note': 'algorithmic FLOPs = 3 x (2 x MACs of the reference nn.Linear layers): forward + dX + dW; the whole optimisation '
-                             'step (encodings, heads, compositing, reductions, Adam) is inside the timed region'},
+        'roofline': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': hbm_achieved / hbm_peak,
+                     'traffic': TRAIN_TRAFFIC_GB.get(a.precision), 'bytes_per_ray': bytes_ray,
+                     'kernel': 'tile_gemm_kernel (forward, dX) + dw_gemm_kernel (dW); the WHOLE step is timed', 'kernel_ms': ms_median,
+                     'peak_source': ('MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6500 GB/s'),
+                     'note': 'the layer-by-layer path is HBM-bound (194 flop/B at K = N = 256, 3 passes: below the ridge): algorithmic bytes = '
+                             '3 x 2 B x planes x (K + N) per sample and nn.Linear (forward, dX, dW), fp32 head copies / encodings / reductions not '
+                             'counted; traffic = dram bytes of one step summed over an ncu launch list (GB, cold caches; '
+                             'profiles/r2/train_step_launch_summary.txt); encodings, heads, compositing, reductions and Adam are inside the timed region'},
+        'roofline_tensor': {'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'flop_per_ray': 3.0 * fl_ray,
+                            'peak_source': ('MEASURED_PEAKS.json ' if peaks else 'fallback ') + ('burst' if burst else 'sustained'),
+                            'note': 'algorithmic FLOPs = 3 x (2 x MACs of the reference nn.Linear layers): forward + dX + dW'},
     }
     if world == 1 and not a.no_cpu_baseline:
         rps, times = cpu_train_rays_per_s(w, state, 3, 256)

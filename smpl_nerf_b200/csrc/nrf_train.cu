@@ -429,7 +429,7 @@ static int dw_into(TrainCtx& t, const Planes& dy, const float* sc, int M, const 
 static int colsum_and_bias(TrainCtx& t, const Planes& dy, const float* sc, int F, int n, float* db) {
   ray_colsum_kernel<<<static_cast<unsigned>(t.c.B), F, 0, t.st>>>(dy.hi, dy.lo, dy.ld, F, n, t.ws.dysum);
   LAUNCH_CHECK("ray_colsum_kernel");
-  bias_grad_kernel<<<(F + 31) / 32, 256, 0, t.st>>>(t.ws.dysum, t.c.B, F, sc, db);
+  bias_grad_kernel<<<(F + 31) / 32, 1024, 0, t.st>>>(t.ws.dysum, t.c.B, F, sc, db);
   LAUNCH_CHECK("bias_grad_kernel");
   return NRF_OK;
 }
@@ -519,7 +519,7 @@ static int backward_pass(TrainCtx& t, int p, const Grads& G) {
   if (c.smpl) {
     const NrfRayNetDesc* d = t.nd[p];
     ++slot;
-    smpl_points_bwd_kernel<<<grid1(w.S, 128), 128, 0, t.st>>>(t.ws.g_encx, d->pos_freqs, d->pos_identity, t.ws.g_encd, d->dir_freqs, d->dir_identity,
+    smpl_points_bwd_kernel<<<grid1((w.S + 7) / 8 * 8 * 4, 128), 128, 0, t.st>>>(t.ws.g_encx, d->pos_freqs, d->pos_identity, t.ws.g_encd, d->dir_freqs, d->dir_identity,
                                                                w.warped, w.u, w.dnorm, p == 0 ? w.g_dnorm : nullptr, w.S, t.ws.g_warp, MX(slot));
     LAUNCH_CHECK("smpl_points_bwd_kernel");
     float* const* gw = G.g[2];

@@ -416,38 +416,49 @@ __global__ void ray_colsum_kernel(const __half* __restrict__ hi, const __half* _
     dysum[b * F + f] = acc;
   }
 }
-// db[f] += inv_scale * sum_b dysum[b, f]      (block = 32 features x 8 ray lanes)
-__global__ void bias_grad_kernel(const float* __restrict__ dysum, int64_t B, int F, const float* __restrict__ scale2, float* __restrict__ db) {
-  __shared__ float red[8][33];
+// db[f] += inv_scale * sum_b dysum[b, f]      (block = 32 features x 32 ray lanes, fixed summation order)
+__global__ void __launch_bounds__(1024) bias_grad_kernel(const float* __restrict__ dysum, int64_t B, int F, const float* __restrict__ scale2,
+                                                         float* __restrict__ db) {
+  __shared__ float red[32][33];
   const int fx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int f = blockIdx.x * 32 + fx;
-  float acc = 0.f;
-  if (f < F) for (int64_t b = ry; b < B; b += 8) acc += dysum[b * F + f];
-  red[ry][fx] = acc;
+  float a0 = 0.f, a1 = 0.f;
+  if (f < F) {
+    int64_t b = ry;
+    for (; b + 32 < B; b += 64) { a0 += dysum[b * F + f]; a1 += dysum[(b + 32) * F + f]; }
+    if (b < B) a0 += dysum[b * F + f];
+  }
+  red[ry][fx] = a0 + a1;
   __syncthreads();
   if (ry == 0 && f < F) {
     float t = 0.f;
-    for (int r = 0; r < 8; ++r) t += red[r][fx];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += red[r][fx];
     db[f] += t * __ldg(scale2 + 1);
   }
 }
-// dW[n, col0 + k] += inv_scale * sum_b dysum[b, n] feat[b, k]      (16 x 16 output tile per CTA, rays in steps of 16 via smem)
-__global__ void rayfeat_dw_kernel(const float* __restrict__ dysum, const float* __restrict__ feat, int64_t B, int n_out, int K,
-                                  const float* __restrict__ scale2, float* __restrict__ dW, int ld, int col0) {
-  __shared__ float ys[16][17], fs[16][17];
+// dW[n, col0 + k] += inv_scale * sum_b dysum[b, n] feat[b, k]      (16 x 16 output tile per CTA, rays in steps of 64 via smem)
+__global__ void __launch_bounds__(256) rayfeat_dw_kernel(const float* __restrict__ dysum, const float* __restrict__ feat, int64_t B, int n_out, int K,
+                                                         const float* __restrict__ scale2, float* __restrict__ dW, int ld, int col0) {
+  constexpr int R = 64;
+  __shared__ float ys[R][17], fs[R][17];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int k = blockIdx.x * 16 + tx, n = blockIdx.y * 16 + ty;
-  float acc = 0.f;
-  for (int64_t b0 = 0; b0 < B; b0 += 16) {
-    const int64_t b = b0 + ty;
-    ys[ty][tx] = (b < B && blockIdx.y * 16 + tx < n_out) ? dysum[b * n_out + blockIdx.y * 16 + tx] : 0.f;
-    fs[ty][tx] = (b < B && k < K) ? feat[b * K + k] : 0.f;
+  const int nl = blockIdx.y * 16 + tx;                      // the dysum column this thread loads
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int64_t b0 = 0; b0 < B; b0 += R) {
+#pragma unroll
+    for (int j = 0; j < R / 16; ++j) {
+      const int64_t b = b0 + ty + 16 * j;
+      ys[ty + 16 * j][tx] = (b < B && nl < n_out) ? dysum[b * n_out + nl] : 0.f;
+      fs[ty + 16 * j][tx] = (b < B && k < K) ? feat[b * K + k] : 0.f;
+    }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; ++r) acc = fmaf(ys[r][ty], fs[r][tx], acc);
+    for (int r = 0; r < R; r += 2) { acc0 = fmaf(ys[r][ty], fs[r][tx], acc0); acc1 = fmaf(ys[r + 1][ty], fs[r + 1][tx], acc1); }
     __syncthreads();
   }
-  if (k < K && n < n_out) dW[static_cast<size_t>(n) * ld + col0 + k] += acc * __ldg(scale2 + 1);
+  if (k < K && n < n_out) dW[static_cast<size_t>(n) * ld + col0 + k] += (acc0 + acc1) * __ldg(scale2 + 1);
 }
 // dst[m, col0 + c] += inv_scale * sum_split partial[split][m][c]        (m < M <= Mp rows of the partials, c < cols <= N)
 // and, in the blocks past the first `main_blocks`, db[m] += inv_scale * sum_split cs_partial[split][m] (the ones-column of dw_gemm).
@@ -526,43 +537,49 @@ __global__ void smpl_points_bwd_kernel(const float* __restrict__ g_encx, int xf,
                                        const float* __restrict__ warped, const float* __restrict__ u, const float* __restrict__ dnorm,
                                        const float* __restrict__ g_dnorm, int64_t S, float* __restrict__ g_warp,
                                        unsigned int* __restrict__ gmax_bits) {
-  const float sc = 1.f;
+  // 4 lanes per sample: lanes 0..2 own one component each (the sincos chains of the three components run side by side), lane 3 idles;
+  // the dot product gu . u is folded with two shuffles inside the group
   float gmax = 0.f;
-  for (int64_t s = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; s < S; s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    float gx[3], gu[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
+  const int64_t total = (S + 7) / 8 * 8 * 4;                // whole warps take part in the shuffles
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t s = idx >> 2;
+    const int j = static_cast<int>(idx & 3);
+    const bool ok = s < S && j < 3;
+    float gx = 0.f, gu = 0.f, uj = 0.f;
+    if (ok) {
       const float* g = g_encx + s * 64;
       const float x = warped[s * 3 + j];
-      float acc = xid ? g[j] : 0.f;
+      gx = xid ? g[j] : 0.f;
       const int base = xid ? 3 : 0;
       for (int k = 0; k < xf; ++k) {
         const float f = __int_as_float((127 + k) << 23);
         float sv, cv;
         sincos_pe(x * f, sv, cv);
-        acc = fmaf(f, fmaf(cv, g[base + 6 * k + j], -sv * g[base + 6 * k + 3 + j]), acc);
+        gx = fmaf(f, fmaf(cv, g[base + 6 * k + j], -sv * g[base + 6 * k + 3 + j]), gx);
       }
-      gx[j] = acc;
       const float* gd = g_encd + s * 64;
-      const float uu = u[s * 3 + j];
-      float accd = did ? gd[j] : 0.f;
+      uj = u[s * 3 + j];
+      gu = did ? gd[j] : 0.f;
       const int based = did ? 3 : 0;
       for (int k = 0; k < df; ++k) {
         const float f = __int_as_float((127 + k) << 23);
         float sv, cv;
-        sincos_pe(uu * f, sv, cv);
-        accd = fmaf(f, fmaf(cv, gd[based + 6 * k + j], -sv * gd[based + 6 * k + 3 + j]), accd);
+        sincos_pe(uj * f, sv, cv);
+        gu = fmaf(f, fmaf(cv, gd[based + 6 * k + j], -sv * gd[based + 6 * k + 3 + j]), gu);
       }
-      gu[j] = accd;
     }
-    const float u0 = u[s * 3], u1 = u[s * 3 + 1], u2 = u[s * 3 + 2];
-    const float dot = gu[0] * u0 + gu[1] * u1 + gu[2] * u2;
-    const float inv = 1.f / dnorm[s];
-    const float gd = g_dnorm ? g_dnorm[s] * sc : 0.f;
-    g_warp[s * 3 + 0] = gx[0] + (gu[0] - u0 * dot) * inv + gd * u0;
-    g_warp[s * 3 + 1] = gx[1] + (gu[1] - u1 * dot) * inv + gd * u1;
-    g_warp[s * 3 + 2] = gx[2] + (gu[2] - u2 * dot) * inv + gd * u2;
-    gmax = fmaxf(gmax, fmaxf(fabsf(g_warp[s * 3]), fmaxf(fabsf(g_warp[s * 3 + 1]), fabsf(g_warp[s * 3 + 2]))));
+    // dot = gu0 u0 + gu1 u1 + gu2 u2 in the order of the one-thread-per-sample formulation: (p0 + p1) + p2
+    const float pj = gu * uj;
+    const unsigned lane = threadIdx.x & 31u, l0 = lane & ~3u;
+    const float p0 = __shfl_sync(0xffffffffu, pj, l0), p1 = __shfl_sync(0xffffffffu, pj, l0 + 1), p2 = __shfl_sync(0xffffffffu, pj, l0 + 2);
+    const float dot = p0 + p1 + p2;
+    if (ok) {
+      const float inv = 1.f / dnorm[s];
+      const float gdn = g_dnorm ? g_dnorm[s] : 0.f;
+      const float out = gx + (gu - uj * dot) * inv + gdn * uj;
+      g_warp[s * 3 + j] = out;
+      gmax = fmaxf(gmax, fabsf(out));
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
