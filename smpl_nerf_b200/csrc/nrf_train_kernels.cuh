@@ -190,22 +190,34 @@ __global__ void ray_bias2_kernel(const float* __restrict__ W, int ld, int col0, 
 // out[s, c0 + c] = b[c] + sum_k W[c, k] x[s, k]     (sigma_out_layer / rgb_out_layer / WarpFieldNet.linear2)
 __global__ void heads_kernel(const float* __restrict__ x, int64_t S, int K, const float* __restrict__ W, const float* __restrict__ b, int nh,
                              float* __restrict__ out, int out_ld, int c0) {
-  extern __shared__ float ws[];     // [nh][K]
+  // 8 lanes per row, 4 rows per warp: 16-byte loads (128 contiguous bytes per row and instruction), 3 shuffle steps per accumulator
+  // (a warp per row with 4-byte loads spent its time in 15 shuffles per row: 4.1 TB/s)
+  extern __shared__ __align__(16) float ws[];     // [nh][K]
   for (int i = threadIdx.x; i < nh * K; i += blockDim.x) ws[i] = W[i];
   __syncthreads();
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (int64_t s = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); s < S; s += static_cast<int64_t>(gridDim.x) * wpb) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, sub = lane & 7, rw = lane >> 3;
+  const int64_t n4 = (S + 3) / 4;                 // groups of 4 rows
+  for (int64_t q = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); q < n4; q += static_cast<int64_t>(gridDim.x) * wpb) {
+    const int64_t s = q * 4 + rw;
+    const bool ok = s < S;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float v = x[s * K + k];
-      a0 = fmaf(v, ws[k], a0);
-      if (nh > 1) { a1 = fmaf(v, ws[K + k], a1); a2 = fmaf(v, ws[2 * K + k], a2); }
+    if (ok) {
+      for (int k = 4 * sub; k < K; k += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(x + s * K + k);
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + k);
+        a0 = fmaf(v.x, w0.x, a0); a0 = fmaf(v.y, w0.y, a0); a0 = fmaf(v.z, w0.z, a0); a0 = fmaf(v.w, w0.w, a0);
+        if (nh > 1) {
+          const float4 w1 = *reinterpret_cast<const float4*>(ws + K + k), w2 = *reinterpret_cast<const float4*>(ws + 2 * K + k);
+          a1 = fmaf(v.x, w1.x, a1); a1 = fmaf(v.y, w1.y, a1); a1 = fmaf(v.z, w1.z, a1); a1 = fmaf(v.w, w1.w, a1);
+          a2 = fmaf(v.x, w2.x, a2); a2 = fmaf(v.y, w2.y, a2); a2 = fmaf(v.z, w2.z, a2); a2 = fmaf(v.w, w2.w, a2);
+        }
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 4; o > 0; o >>= 1) {
       a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
     }
-    if (lane == 0) {
+    if (sub == 0 && ok) {
       out[s * out_ld + c0] = a0 + b[0];
       if (nh > 1) { out[s * out_ld + c0 + 1] = a1 + b[1]; out[s * out_ld + c0 + 2] = a2 + b[2]; }
     }
@@ -230,16 +242,23 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   if (nh > 1) { w1 = *reinterpret_cast<const float4*>(W + K + k4); w2 = *reinterpret_cast<const float4*>(W + 2 * K + k4); }
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
   float b0 = 0.f, b1 = 0.f, b2 = 0.f, l1_run = 0.f;
-  for (int it = 0; it * n_rg < rows_per_block; ++it) {      // uniform trip count: the warp shuffles below need every lane
-    const int64_t s = r0 + static_cast<int64_t>(it) * n_rg + rg;
-    const bool ok = s < r0 + rows_per_block && s < S;
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok) {
-      g0 = g[s * g_ld + c0];
-      if (nh > 1) { g1 = g[s * g_ld + c0 + 1]; g2 = g[s * g_ld + c0 + 2]; }
-      xv = *reinterpret_cast<const float4*>(x + s * K + k4);
+  struct Row { int64_t s; bool ok; float g0, g1, g2; float4 xv; };
+  auto fetch = [&](int it) {                                // all loads of a row: issued for TWO rows before either is consumed
+    Row r;
+    r.s = r0 + static_cast<int64_t>(it) * n_rg + rg;
+    r.ok = it * n_rg < rows_per_block && r.s < r0 + rows_per_block && r.s < S;
+    r.g0 = r.g1 = r.g2 = 0.f;
+    r.xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r.ok) {
+      r.g0 = g[r.s * g_ld + c0];
+      if (nh > 1) { r.g1 = g[r.s * g_ld + c0 + 1]; r.g2 = g[r.s * g_ld + c0 + 2]; }
+      r.xv = *reinterpret_cast<const float4*>(x + r.s * K + k4);
     }
+    return r;
+  };
+  auto consume = [&](const Row& r) {
+    const float g0 = r.g0, g1 = r.g1, g2 = r.g2;
+    const float4 xv = r.xv;
     b0 += g0; b1 += g1; b2 += g2;
     a0.x = fmaf(g0, xv.x, a0.x); a0.y = fmaf(g0, xv.y, a0.y); a0.z = fmaf(g0, xv.z, a0.z); a0.w = fmaf(g0, xv.w, a0.w);
     if (nh > 1) {
@@ -259,9 +278,9 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       __align__(8) __half l[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) split_store(d[i] * sc, &h[i], &l[i]);
-      if (ok) {
-        *reinterpret_cast<uint2*>(dy_hi + s * dy_ld + k4) = *reinterpret_cast<const uint2*>(h);
-        if (dy_lo) *reinterpret_cast<uint2*>(dy_lo + s * dy_ld + k4) = *reinterpret_cast<const uint2*>(l);
+      if (r.ok) {
+        *reinterpret_cast<uint2*>(dy_hi + r.s * dy_ld + k4) = *reinterpret_cast<const uint2*>(h);
+        if (dy_lo) *reinterpret_cast<uint2*>(dy_lo + r.s * dy_ld + k4) = *reinterpret_cast<const uint2*>(l);
       }
       if (l1max) {          // L1 norm of this warp's 128 columns of the row (real units); a warp never straddles two rows (K >= 128) ...
         float a = fabsf(d[0]) + fabsf(d[1]) + fabsf(d[2]) + fabsf(d[3]);
@@ -270,6 +289,11 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
         l1_run = fmaxf(l1_run, a);
       }
     }
+  };
+  for (int it = 0; it * n_rg < rows_per_block; it += 2) {   // uniform trip count: the warp shuffles need every lane
+    const Row ra = fetch(it), rb = fetch(it + 1);
+    consume(ra);
+    consume(rb);
   }
   if (l1max && isfinite(l1_run)) {
 #pragma unroll
