@@ -460,12 +460,23 @@ def run_train(a, w, rank, world, local_rank):
     launches = int(_lib.lib().nrf_train_launch_count(1))
     ms_total = e0.elapsed_time(e1)
     ms_steps = [x.elapsed_time(y) for x, y in ev]
+    for i in range(2):          # untimed: the end-to-end loop allocates its inputs per step (first use of those allocator bins is a cudaMalloc)
+        data = [t.to(dev, non_blocking=True) for t in batches_host[i % n_b]]
+        loss_host.copy_(step(data).detach().reshape(1), non_blocking=True)
+    barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
+    dbg = [] if os.environ.get('NRF_BENCH_DEBUG') else None      # developer: host time at which every e2e step was ISSUED
     for i in range(a.steps):
+        if dbg is not None:
+            dbg.append(time.perf_counter())
         data = [t.to(dev, non_blocking=True) for t in batches_host[i % n_b]]
         loss_host.copy_(step(data).detach().reshape(1), non_blocking=True)
     f1.record(stream)
+    if dbg is not None:
+        torch.cuda.synchronize(dev)
+        dbg.append(time.perf_counter())
+        print(f'[rank {rank}] e2e issue times (ms): ' + ' '.join(f'{1e3 * (y - x):.1f}' for x, y in zip(dbg, dbg[1:])), file=sys.stderr, flush=True)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if sampler else None
