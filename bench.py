@@ -295,6 +295,18 @@ def run_reference(a, w, rank, world):
 WARM_SECONDS = 1.0     # warm-up runs at least this long (brings the SM clock up from idle), regardless of --warmup
 
 
+def warm_done(i, t0, min_steps, world, dev):
+    """Warm-up ends when EVERY rank has run at least `min_steps` steps and WARM_SECONDS: the decision is all-reduced, because a step holds a
+    collective -- ranks that left a purely time-based loop after different step counts would deadlock in it (seen at 8 GPUs)."""
+    done = i >= max(min_steps, 1) and time.perf_counter() - t0 >= WARM_SECONDS
+    if world > 1:
+        import torch.distributed as dist
+        flag = torch.tensor([1 if done else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        done = bool(int(flag.item()))
+    return done
+
+
 def measure(a, w, pipe, rank, world, dev, clocks=True):
     """Time K steps of workload `w` through the pipeline API: device-resident loop (per-step CUDA events) and the end-to-end
     loop (pinned host inputs, H2D + D2H inside).  Returns max-over-ranks times."""
@@ -323,11 +335,11 @@ def measure(a, w, pipe, rank, world, dev, clocks=True):
 
     with torch.no_grad():
         t0, i = time.perf_counter(), 0
-        while i < a.warmup or time.perf_counter() - t0 < WARM_SECONDS:
-            step(views[i % n_views])
-            i += 1
-            if i % 8 == 0:
-                torch.cuda.synchronize(dev)
+        while not warm_done(i, t0, a.warmup, world, dev):     # every rank runs the SAME number of steps (there is a collective inside)
+            for _ in range(4):
+                step(views[i % n_views])
+                i += 1
+            torch.cuda.synchronize(dev)
         # ---------------- device-resident throughput: exactly K steps
         barrier()
         sampler = ClockSampler(dev.index) if (rank == 0 and clocks) else None
@@ -442,8 +454,9 @@ def run_train(a, w, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     t0, i = time.perf_counter(), 0
-    while i < a.warmup or time.perf_counter() - t0 < WARM_SECONDS:
-        step(batches[i % n_b]); i += 1
+    while not warm_done(i, t0, a.warmup, world, dev):         # every rank runs the SAME number of steps (there is an all-reduce inside)
+        for _ in range(4):
+            step(batches[i % n_b]); i += 1
         torch.cuda.synchronize(dev)
     barrier()
     sampler = ClockSampler(dev.index) if rank == 0 else None
