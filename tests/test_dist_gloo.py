@@ -82,3 +82,38 @@ def test_single_process_is_a_no_op():
     img = nd.render_frame_sharded(_fake_pipeline, data)
     assert torch.equal(img, _fake_pipeline(data)[1])
     assert abs(nd.psnr(torch.zeros(4, 3), torch.full((4, 3), 0.1)) - 20.0) < 1e-4
+
+
+def _warm_worker(rank: int, world: int, port: int, out_dir: str):
+    """bench.py's warm-up: ranks whose steps take different host time must still run the SAME number of steps (a step holds a
+    collective; a purely time-based loop deadlocked the 8-GPU run of round 2)."""
+    import sys
+    import time
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        bench.WARM_SECONDS = 0.3
+        dev = torch.device('cpu')
+        t0, i = time.perf_counter(), 0
+        while not bench.warm_done(i, t0, 3, world, dev):
+            for _ in range(4):
+                time.sleep(0.004 * (1 + 5 * rank))              # rank 1 is 6x slower per step
+                x = torch.ones(1)
+                dist.all_reduce(x)                               # the collective inside a step: a count mismatch would hang here
+                i += 1
+        counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([i], dtype=torch.int64))
+        assert all(int(c) == i for c in counts) and i >= 3
+        open(os.path.join(out_dir, f'warm{rank}'), 'w').write(str(i))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_bench_warm_up_runs_the_same_number_of_steps_on_every_rank(tmp_path):
+    port = _free_port()
+    mp.spawn(_warm_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f'warm{r}').exists() for r in range(2))
