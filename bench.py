@@ -356,15 +356,34 @@ def measure(a, w, pipe, rank, world, dev, clocks=True):
         ms_steps = [x.elapsed_time(y) for x, y in ev]
         # ---------------- end to end through the public API: host inputs, H2D + D2H inside the timed region
         host_img = torch.empty(n_total if world > 1 else rays, 3).pin_memory()
-        for i in range(3):
-            data = [t.to(dev, non_blocking=True) for t in views_host[i % n_views]]
-            host_img.copy_(step(data), non_blocking=True)
+        # the host->device copy of step i + 1 is issued on a copy stream while step i renders (what a serving loop does); every copy,
+        # including the exposed first one, starts after f0 and is waited for before f1
+        copy_stream = torch.cuda.Stream(dev)
+
+        def h2d(v):
+            with torch.cuda.stream(copy_stream):
+                d = [t.to(dev, non_blocking=True) for t in views_host[v % n_views]]
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            return d, ready
+
+        def e2e_loop(n, v0):
+            nxt = h2d(v0)
+            for i in range(n):
+                data, ready = nxt
+                if i + 1 < n:
+                    nxt = h2d(v0 + i + 1)
+                stream.wait_event(ready)
+                for t in data:
+                    t.record_stream(stream)
+                host_img.copy_(step(data), non_blocking=True)
+
+        e2e_loop(3, 0)
         barrier()
+        copy_stream.synchronize()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
-        for i in range(a.steps):
-            data = [t.to(dev, non_blocking=True) for t in views_host[(a.warmup + i) % n_views]]
-            host_img.copy_(step(data), non_blocking=True)
+        e2e_loop(a.steps, a.warmup)
         f1.record(stream)
         barrier()
         ms_e2e = f0.elapsed_time(f1)
@@ -628,7 +647,8 @@ def run_ours(a, w, rank, world, local_rank):
                    'timing': f'value = rays / MEDIAN step time (CUDA events around every step, max over ranks); the K steps '
                              f'back to back took {ms_total:.2f} ms (mean {ms_total / a.steps:.3f} ms/step, '
                              f'{n_total * a.steps / (ms_total / 1e3):.0f} rays/s); warm-up = max({a.warmup} steps, '
-                             f'{WARM_SECONDS} s of launches); called through the pipeline API (pipe(data))'},
+                             f'{WARM_SECONDS} s of launches); called through the pipeline API (pipe(data)); e2e: pinned host inputs, the H2D copy of '
+                             f'step i + 1 issued on a copy stream while step i renders, D2H of rgb_fine every step, all inside the timed region'},
         'clocks': clocks,
         'e2e': {'value': n_total * a.steps / (ms_e2e / 1e3), 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': a.steps * engine.launches_per_render(w['kind'], bool(w['run_fine'])),

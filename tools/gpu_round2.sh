@@ -16,6 +16,7 @@ echo "== train"; timeout 600 python bench.py --workload train --steps 10 --warmu
 timeout 300 python bench.py --workload train --steps 10 --warmup 3 --precision fast --no-cpu-baseline 2>&1 | tail -1 > $OUT/bench_train_fast.json
 echo "== reference arms"; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 2>&1 | tail -1 > $OUT/bench_reference_cpu.json
 timeout 300 python bench.py --impl reference --device cuda --steps 10 --warmup 2 2>&1 | tail -1 > $OUT/bench_reference_torch_cuda.json
+if [ -n "$BENCH_ONLY" ]; then ls -la $OUT; exit 0; fi      # BENCH_ONLY=1: just the bench lines (after a change that leaves the kernels alone)
 echo "== per-kernel time of a training step"; timeout 300 python tools/train_profile.py 2048 > $OUT/train_step_kernels.txt 2>&1
 echo "== trace timeline"; timeout 300 python tools/trace_timeline.py cfg2 > $OUT/timeline_cfg2_parity.txt 2>&1
 timeout 300 python tools/trace_timeline.py cfg2 fast > $OUT/timeline_cfg2_fast.txt 2>&1
