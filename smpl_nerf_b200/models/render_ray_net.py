@@ -2,8 +2,9 @@
 names (models/render_ray_net.py:6-40), so checkpoints (`model_coarse.pt`, `model_fine.pt`) load
 unchanged and the fused engine can read the hyper-parameters off the module.
 
-The network is evaluated inside the fused kernel (csrc/nrf_fused.cu) when a pipeline is called; a
-stand-alone ``forward`` on pre-encoded features is not part of the accelerated path."""
+The network is evaluated inside the fused kernel (csrc/nrf_fused.cu) when a pipeline is called; the
+stand-alone ``forward`` on pre-encoded features (models/render_ray_net.py:42-61) runs every layer as one
+tcgen05 GEMM launch of the library (smpl_nerf_b200/mlp.py): inference only, CUDA only."""
 import torch.nn as nn
 
 
@@ -33,8 +34,8 @@ class RenderRayNet(nn.Module):
         self.rgb_out_layer = nn.Linear(half, 3)
 
     def forward(self, x):
-        raise NotImplementedError('RenderRayNet is evaluated inside the fused pipeline kernel; call a '
-                                  'smpl_nerf_b200.models.*Pipeline (there is no PyTorch fallback)')
+        from ..mlp import render_ray_net_forward
+        return render_ray_net_forward(self, x)
 
     @property
     def is_cuda(self):

@@ -1,6 +1,7 @@
 """WarpFieldNet -- parameter container with the reference's names (models/warp_field_net.py:6-15):
 Linear(positions_dim + pose_dim -> width) -> ReLU -> Linear(width -> 3).  Evaluated inside the fused
-kernel by SmplNerfPipeline."""
+kernel by SmplNerfPipeline; the stand-alone ``forward`` (models/warp_field_net.py:17-21) runs the two layers
+as tcgen05 GEMM launches of the library (smpl_nerf_b200/mlp.py): inference only, CUDA only."""
 import torch.nn as nn
 
 
@@ -14,8 +15,8 @@ class WarpFieldNet(nn.Module):
         self.linear2 = nn.Linear(width, 3)
 
     def forward(self, x):
-        raise NotImplementedError('WarpFieldNet is evaluated inside the fused pipeline kernel; call '
-                                  'smpl_nerf_b200.models.SmplNerfPipeline (there is no PyTorch fallback)')
+        from ..mlp import warp_field_net_forward
+        return warp_field_net_forward(self, x)
 
     @property
     def is_cuda(self):

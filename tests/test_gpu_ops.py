@@ -257,3 +257,36 @@ def test_positional_encoding_backward(L, ident):
     (ops.PositionalEncoder(L, ident).encode(xg) * gout.to(DEV)).sum().backward()
     want = x64.grad
     assert float((xg.grad.cpu().double() - want).abs().max()) <= 2e-6 * float(want.abs().max())
+
+
+@pytest.mark.parametrize('kind,n_layers,skips,width', [('nerf', 8, (4,), 256), ('append', 4, (2,), 128), ('smpl', 6, (3,), 256)])
+def test_standalone_net_forward(kind, n_layers, skips, width):
+    """RenderRayNet.forward / WarpFieldNet.forward on pre-encoded features (models/render_ray_net.py:42-61,
+    models/warp_field_net.py:17-21): every nn.Linear is one tcgen05 GEMM launch; against the oracle's nets in fp64."""
+    from smpl_nerf_b200.models import RenderRayNet, WarpFieldNet
+    c, _, w, *_ = O.build_nets(kind, 3, 'default', n_layers=n_layers, skips=skips, width=width)
+    net = RenderRayNet(n_layers, width, c.positions_dim, c.direcions_dim, c.additional_input_dim, list(skips))
+    net.load_state_dict(c.state_dict())
+    net = net.to(DEV).eval()
+    torch.manual_seed(5)
+    x = torch.randn(3, 333, c.positions_dim + c.additional_input_dim + c.direcions_dim)          # ragged row count, leading dims kept
+    got = net(x.to(DEV))
+    with torch.no_grad():
+        want = c.double()(x.double())
+    assert got.shape == want.shape == (3, 333, 4)
+    assert float((got.double().cpu() - want).abs().max()) <= 2e-5 * (1 + float(want.abs().max()))
+    with torch.no_grad():                                       # training-mode nets are fine under no_grad ...
+        net.train()
+        assert torch.equal(net(x.to(DEV)), got)
+    with pytest.raises(NotImplementedError):                    # ... but the stand-alone forward does not build a graph
+        net(x.to(DEV))
+    with pytest.raises(RuntimeError):                           # and there is no CPU path
+        net.eval()(x)
+    if w is not None:
+        wn = WarpFieldNet(n_layers, width, w.positions_dim, w.direcions_dim)
+        wn.load_state_dict(w.state_dict())
+        wn = wn.to(DEV).eval()
+        xw = torch.randn(1000, w.positions_dim + w.direcions_dim)
+        gw = wn(xw.to(DEV))
+        assert gw.shape == (1000, 3)
+        assert float((gw.double().cpu() - w.double()(xw.double())).abs().max()) <= 2e-5

@@ -114,6 +114,11 @@ def test_ops_and_ray_generation_refuse_cpu_tensors():
         rays.generate_view(4, 4, scene.sphere_pose(0., 0.), device='cpu')
     with pytest.raises(ValueError):
         rays.generate_view(4, 4, np.eye(3), device='cuda:0')
+    from smpl_nerf_b200.models import RenderRayNet, WarpFieldNet          # the stand-alone net forward: CUDA tensors only
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        RenderRayNet(4, 128, 60, 24, 0, [2]).eval()(torch.zeros(5, 84))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        WarpFieldNet(8, 256, 60, 40).eval()(torch.zeros(5, 100))
 
 
 def test_render_argument_errors_are_reported_without_a_gpu(L):
