@@ -1,10 +1,10 @@
 // tcgen05 GEMM kernels of the training path -- see nrf_gemm.cuh for the three products they serve.
 //
-//   tile_gemm_kernel   C[S, N] = A[S, K] . op(B): the weight operand (K <= 320, one 128- or 64-column slice) stays
-//                      RESIDENT in shared memory, the CTA streams 128-row sample tiles through a TMA ring and double-
-//                      buffers the accumulator in TMEM, so the epilogue of tile i (bias / ReLU / ReLU' mask / hi-lo split ->
-//                      planes) overlaps the MMAs of tile i + 1.  Roofline: tensor (3 x 2 S K N flop in parity mode) --
-//                      the A stream is 4 K bytes per sample per slice, ~40 B/clk/SM at the MMA rate.
+//   tile_gemm_kernel   C[S, N] = A[S, K] . op(B): the weight operand (K <= 320) stays RESIDENT in shared memory, the CTA (or CTA
+//                      pair: cta_group::2, M = 256, N = 256) streams sample tiles through a TMA ring and double-buffers the
+//                      accumulator in TMEM, so the epilogue of tile i (bias / ReLU / ReLU' bit mask / hi-lo split -> planes through
+//                      per-warp staging blocks and TMA stores) overlaps the MMAs of tile i + 1.  Roofline: HBM -- a 256 x 256
+//                      layer in parity mode is 194 flop/B (measured 80-82 % of the copy bandwidth).
 //   dw_gemm_kernel     dW[128, N] += A[s, m]^T B[s, n] over this CTA's share of the samples (split-K), both operands
 //                      MN-major straight out of the row-major planes; partial sums to HBM, reduced by dw_reduce_kernel.
 //                      Roofline: HBM (each sample row of dY and X is read once per 128-wide M half: ~3 KB per sample per
@@ -672,7 +672,7 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
     b_bytes = 0;
   }
   // staged epilogue (fp16 planes out through shared memory + TMA stores) whenever the ring keeps >= 2 stages beside it
-  const uint32_t stage_out = 32768u;       // [128 x 64] fp16 block of the hi plane | the same of the lo plane
+  const uint32_t stage_out = 32768u;       // 8 epilogue warps x 4 KB private staging blocks ([32 x 32] hi | lo, or one [32 x 32] fp32 block)
   uint32_t out_bytes = 0;
   if (a.epi == GEPI_PLANES && a.passes != 6 && a.out.hi && !(reinterpret_cast<uintptr_t>(a.out.hi) & 15u) && !(a.out.ld & 7) &&
       (!a.out.lo || !(reinterpret_cast<uintptr_t>(a.out.lo) & 15u)) && b_bytes + 2 * a_stage + stage_out + 256 <= kGemmSmemLimit) {
