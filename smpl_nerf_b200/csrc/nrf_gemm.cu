@@ -73,6 +73,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
   const int rows_tile = kPair ? 256 : 128;
   const int64_t n_mt = (P.S + rows_tile - 1) / rows_tile;
   const int64_t mt0 = kPair ? (blockIdx.x >> 1) : blockIdx.x, mt_step = kPair ? (gridDim.x >> 1) : gridDim.x;
+  // tile order: all CTAs sweep the samples together, front to back or (P.reverse) back to front -- a kernel that starts where the previous one
+  // ended finds the last ~L2-sized part of that kernel's output (or input) still in L2 instead of re-reading it from HBM
+  auto tile_of = [&](int64_t m) { return P.reverse ? n_mt - 1 - m : m; };
 
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bars->b_full), 1);
@@ -118,13 +121,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
             mbar_wait(smem_u32(&bars->a_empty[stage]), phase ^ 1);
             if (rank == 0) mbar_arrive_expect_tx(smem_u32(&bars->a_full[stage]), mult * a_stage);
             const uint32_t dst = smem_a + stage * a_stage;
-            const int32_t r0 = static_cast<int32_t>(mt * rows_tile + rank * 128);
+            const int32_t r0 = static_cast<int32_t>(tile_of(mt) * rows_tile + rank * 128);
             for (uint32_t p = 0; p < planes; ++p) load(dst + p * kATile, &P.a_map[j][p], 64 * lc, r0, bar_of(&bars->a_full[stage]));
             // the activation planes stream from HBM (hundreds of MB per layer): pull this CTA's NEXT tile into L2 now, so the 2-3 deep
             // ring is refilled at L2 latency (two tiles ahead was measured worse: 290 MB of a 402 MB operand were evicted by the
             // output stream before use and read twice)
             const int64_t pf = mt + (getenv_pf_dist > 0 ? getenv_pf_dist : 1) * mt_step;
-            if (pf < n_mt) for (uint32_t p = 0; p < planes; ++p) tma_prefetch_2d(&P.a_map[j][p], 64 * lc, static_cast<int32_t>(pf * rows_tile + rank * 128));
+            if (pf < n_mt) for (uint32_t p = 0; p < planes; ++p) tma_prefetch_2d(&P.a_map[j][p], 64 * lc, static_cast<int32_t>(tile_of(pf) * rows_tile + rank * 128));
             if (P.b_stream) load_b(j, lc, dst + planes * kATile, bar_of(&bars->a_full[stage]));
             if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
           }
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
 #pragma unroll
     for (int i = 0; i < kCT; ++i) bias[i] = 0.f;
     auto aux_load = [&](int64_t mt_l, int u_l) {
-      const int64_t row_l = mt_l * rows_tile + rank * 128 + r_t;
+      const int64_t row_l = tile_of(mt_l) * rows_tile + rank * 128 + r_t;
       const bool ok = row_l < P.S;
       const int c0 = n0 + 64 * u_l + kCT * cg;
       if (P.bias) {
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
     for (int64_t mt = mt0; mt < n_mt; mt += mt_step, ++it) {
       const uint32_t buf = it & 1u;
       TR(0);
-      const int64_t row = mt * rows_tile + rank * 128 + r_t;
+      const int64_t row = tile_of(mt) * rows_tile + rank * 128 + r_t;
       const bool row_ok = row < P.S;
       const float rs = (P.row_scale && row_ok) ? P.row_scale[row * P.row_scale_ld] * s_out : 0.f;
       float l1 = 0.f;
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
           continue;
         }
         const uint32_t st_w = smem_o + static_cast<uint32_t>(warp - 2) * 4096u;           // this warp's staging block
-        const int32_t r0w = static_cast<int32_t>(mt * rows_tile + rank * 128 + 32 * q);    // first row of the warp's 32
+        const int32_t r0w = static_cast<int32_t>(tile_of(mt) * rows_tile + rank * 128 + 32 * q);    // first row of the warp's 32
         if (P.f32_staged) {                                // fp32 copy of the unit: [32 rows x 32 floats], 128-byte rows, SWIZZLE_128B
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_gemm_kernel(const __grid
     const int r_t = 32 * q + lane;
     uint32_t it = 0;
     for (int64_t mt = mt0; mt < n_mt; mt += mt_step) {
-      const int64_t row = mt * rows_tile + r_t;
+      const int64_t row = tile_of(mt) * rows_tile + r_t;
       const bool row_ok = row < P.S;
       const int col0 = n0 + half * cols_w;
       const float* bias_row = (P.bias && row_ok) ? P.bias + (P.bias_ld ? (row / P.rows_per_ray) * P.bias_ld : 0) + col0 : nullptr;
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         const uint32_t full = smem_u32(&bars->a_full[stage]);
         mbar_arrive_expect_tx(full, stage_bytes);
         const uint32_t base = smem_u32(smem) + stage * stage_bytes;
-        const int32_t s0 = static_cast<int32_t>(c * 64);
+        const int32_t s0 = static_cast<int32_t>((P.reverse ? n_chunks - 1 - c : c) * 64);
         for (uint32_t p = 0; p < planes; ++p) {
           const uint32_t da = base + p * a_bytes, db = base + planes * a_bytes + p * b_bytes;
           for (int g = 0; g < 2; ++g) tma_load_2d(da + g * 8192u, p ? &P.a_lo : &P.a_hi, m_tile + 64 * g, s0, full);
@@ -515,8 +518,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         const int64_t pf = c + 3 * static_cast<int64_t>(gridDim.y);       // three chunks ahead of the 2-deep ring: into L2
         if (pf < n_chunks)
           for (uint32_t p = 0; p < planes; ++p) {
-            for (int g = 0; g < 2; ++g) tma_prefetch_2d(p ? &P.a_lo : &P.a_hi, m_tile + 64 * g, static_cast<int32_t>(pf * 64));
-            for (int g = 0; g < P.N / 64; ++g) tma_prefetch_2d(p ? &P.b_lo : &P.b_hi, P.n0 + 64 * g, static_cast<int32_t>(pf * 64));
+            for (int g = 0; g < 2; ++g) tma_prefetch_2d(p ? &P.a_lo : &P.a_hi, m_tile + 64 * g, static_cast<int32_t>((P.reverse ? n_chunks - 1 - pf : pf) * 64));
+            for (int g = 0; g < P.N / 64; ++g) tma_prefetch_2d(p ? &P.b_lo : &P.b_hi, P.n0 + 64 * g, static_cast<int32_t>((P.reverse ? n_chunks - 1 - pf : pf) * 64));
           }
         if (++stage == static_cast<uint32_t>(P.n_stages)) { stage = 0; phase ^= 1; }
       }
@@ -692,7 +695,7 @@ int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream) {
   P.epi = a.epi; P.relu = a.relu; P.bias = a.bias; P.bias_ld = a.bias_ld; P.rows_per_ray = a.rows_per_ray > 0 ? a.rows_per_ray : 1;
   P.out_hi = a.out.hi; P.out_lo = a.out.lo; P.out_ll = a.out.ll; P.out_ld = a.out.ld; P.out_f32 = a.out_f32; P.out_f32_ld = a.out_f32_ld; P.accumulate = a.accumulate;
   P.mask_bits = a.mask_bits; P.bits_out = a.bits_out; P.bits_ld = a.bits_ld; P.row_scale = a.row_scale; P.row_scale_ld = a.row_scale_ld; P.col_vec = a.col_vec;
-  P.sc_in = a.sc_in; P.sc_out = a.sc_out; P.l1max = a.l1max; P.status = a.status;
+  P.sc_in = a.sc_in; P.sc_out = a.sc_out; P.l1max = a.l1max; P.status = a.status; P.reverse = a.reverse ? 1 : 0;
   if (a.epi == GEPI_PLANES && !a.out.hi) { set_error("tile_gemm: planes epilogue without an output"); return NRF_E_INVALID; }
   if (a.epi == GEPI_F32 && !a.out_f32) { set_error("tile_gemm: fp32 epilogue without an output"); return NRF_E_INVALID; }
   const int slices = a.N / P.n_tile;
@@ -756,7 +759,7 @@ int dw_gemm_max_split(int n_sms, int M) {
 }
 
 int launch_dw_gemm(const Planes& a, int m0, int M, const Planes& b, int n0, int N, int passes, float* partial, int max_split,
-                   int* n_split_out, int n_sms, cudaStream_t stream, float* colsum_partial) {
+                   int* n_split_out, int n_sms, cudaStream_t stream, float* colsum_partial, int reverse) {
   static thread_local DwGemmParams P;
   memset(&P, 0, sizeof(P));
   if (passes != 1 && passes != 3) { set_error("dw_gemm: passes must be 1 or 3"); return NRF_E_INVALID; }
@@ -771,7 +774,7 @@ int launch_dw_gemm(const Planes& a, int m0, int M, const Planes& b, int n0, int 
     if ((rc = encode_planes_map(&P.a_lo, a.lo, a.rows, a.cols, a.ld, 64, 64)) != NRF_OK) return rc;
     if ((rc = encode_planes_map(&P.b_lo, b.lo, b.rows, b.cols, b.ld, 64, 64)) != NRF_OK) return rc;
   }
-  P.m0 = m0; P.n0 = n0; P.N = N; P.passes = passes; P.S = a.rows; P.partial = partial; P.M_total = M; P.colsum_partial = colsum_partial;
+  P.m0 = m0; P.n0 = n0; P.N = N; P.passes = passes; P.S = a.rows; P.partial = partial; P.M_total = M; P.colsum_partial = colsum_partial; P.reverse = reverse ? 1 : 0;
   const uint32_t planes = passes == 3 ? 2u : 1u;
   const uint32_t stage_bytes = planes * (16384u + static_cast<uint32_t>(N) * 128u);
   const uint32_t ones_bytes = colsum_partial ? 8192u : 0u;

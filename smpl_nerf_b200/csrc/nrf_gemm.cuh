@@ -52,6 +52,7 @@ struct TileGemmParams {
   // norm, from which the host derives the next layer's scale (|dX| <= |dY row|_1 max|W|).
   const float* sc_in; const float* sc_out; unsigned int* l1max;
   int32_t* status;                                                 // bit 1: an output saturated the fp16 range
+  int32_t reverse;                                                 // 1: walk the sample tiles back to front (L2 reuse across consecutive kernels)
   int32_t pf_dist;                                                 // L2 prefetch distance in tiles (developer A/B: NRF_GEMM_PF; default 1)
   long long* trace;                                                // developer tap (NRF_GEMM_TRACE): CTA 0's epilogue timeline, SM clocks
 };
@@ -63,6 +64,7 @@ struct DwGemmParams {
   int64_t S;
   float* partial;                 // [n_split][M_total][N]
   int32_t M_total;
+  int32_t reverse;                // 1: walk the 64-sample chunks back to front (see TileGemmParams::reverse)
   float* colsum_partial;          // optional [n_split][M_total]: sum over this CTA's samples of (hi + lo)[s, m] -- the bias gradient --
                                   // from two extra N = 16 MMAs per K-step against a constant tile of ones (no extra pass over dY)
 };
@@ -85,12 +87,13 @@ struct TileGemmArgs {
   const float* row_scale; int row_scale_ld; const float* col_vec;
   const float* sc_in; const float* sc_out; unsigned int* l1max;
   int32_t* status;
+  int reverse;
 };
 int launch_tile_gemm(const TileGemmArgs& a, int n_sms, cudaStream_t stream);
 
 // dW[M, N] = sum_s A[s, m0 + m] * B[s, n0 + n]: partial sums per CTA into `partial` ([n_split][M][N] floats, n_split returned)
 int launch_dw_gemm(const Planes& a, int m0, int M, const Planes& b, int n0, int N, int passes, float* partial, int max_split,
-                   int* n_split_out, int n_sms, cudaStream_t stream, float* colsum_partial = nullptr);
+                   int* n_split_out, int n_sms, cudaStream_t stream, float* colsum_partial = nullptr, int reverse = 0);
 int dw_gemm_max_split(int n_sms, int M);
 
 }  // namespace nrf

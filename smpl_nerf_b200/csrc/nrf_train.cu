@@ -194,6 +194,11 @@ static int make_cfg(const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, co
   return NRF_OK;
 }
 
+static int sweep_alternates() {      // developer A/B: NRF_TRAIN_SWEEP=0 walks every GEMM front to back
+  static int v = -1;
+  if (v < 0) v = getenv("NRF_TRAIN_SWEEP") ? (atoi(getenv("NRF_TRAIN_SWEEP")) ? 1 : 0) : 1;
+  return v;
+}
 static int grid1(int64_t total, int block) {
   int64_t g = (total + block - 1) / block;
   return static_cast<int>(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g));
@@ -207,6 +212,7 @@ struct TrainCtx {
   const float* const* par[3];      // coarse, fine, warp parameter tables (host arrays of device pointers)
   NrfRenderIO io;
   int n_sms; cudaStream_t st;
+  int rev;                         // sweep direction of the next large GEMM: alternates, so that each starts where its predecessor ended (L2 reuse)
 };
 
 static int setup(TrainCtx& t, const NrfPipelineDesc* pipe, const NrfRayNetDesc* coarse, const float* const* pc, int n_pc,
@@ -293,6 +299,7 @@ static int encode(TrainCtx& t, const float* x, int64_t S, int freqs, int identit
 
 static int forward_pass(TrainCtx& t, int p) {
   const TrainCfg& c = t.c;
+  t.rev = 1;                       // the encodings were written front to back: the first GEMM starts at the end
   PassWs& w = t.ws.pass[p];
   const TNet& net = t.net[p];
   const NrfRayNetDesc* d = t.nd[p];
@@ -308,6 +315,7 @@ static int forward_pass(TrainCtx& t, int p) {
     g.a[0] = w.wpe; g.b[0] = t.ws.warp_w; g.n_src = 1; g.N = c.Ww; g.passes = c.passes; g.epi = GEPI_PLANES; g.relu = 1;
     g.bias = bias; g.bias_ld = Aw > 0 ? c.Ww : 0; g.rows_per_ray = w.n; g.out = w.warph; g.out_f32 = w.warph_f32; g.out_f32_ld = c.Ww;
     g.status = t.io.status;
+    g.reverse = t.rev & sweep_alternates(); t.rev ^= 1;
     TRY(launch_tile_gemm(g, t.n_sms, t.st));
     TRY(heads(t, w.warph_f32, w.S, c.Ww, t.par[2][2], t.par[2][3], 3, w.warp_raw, 3, 0));
     smpl_points_kernel<<<grid1(w.S, 256), 256, 0, t.st>>>(pts, w.warp_raw, t.io.ray_origin, w.S, w.n, w.warped, w.u, w.dnorm,
@@ -337,6 +345,7 @@ static int forward_pass(TrainCtx& t, int p) {
     if (L.role == ROLE_RGB) { g.out_f32 = w.h2_f32; g.out_f32_ld = net.W / 2; }
     if (L.relu) { g.bits_out = w.bits[l]; g.bits_ld = L.n_out / 32; }
     g.status = t.io.status;
+    g.reverse = t.rev & sweep_alternates(); t.rev ^= 1;
     TRY(launch_tile_gemm(g, t.n_sms, t.st));
   }
   const int nl = net.nl;
@@ -417,7 +426,8 @@ static int dw_into(TrainCtx& t, const Planes& dy, const float* sc, int M, const 
     if (cb <= 0) break;
     int split = 0;
     const bool with_db = db != nullptr && nb == 0;       // the bias gradient rides on the first block: (dY_hi + dY_lo)^T . ones
-    TRY(launch_dw_gemm(dy, 0, Mp, x, n0 + nb, Nb, t.c.passes, t.ws.partial, 148, &split, t.n_sms, t.st, with_db ? t.ws.cs_partial : nullptr));
+    TRY(launch_dw_gemm(dy, 0, Mp, x, n0 + nb, Nb, t.c.passes, t.ws.partial, 148, &split, t.n_sms, t.st, with_db ? t.ws.cs_partial : nullptr, t.rev & sweep_alternates()));
+    t.rev ^= 1;
     const int main_blocks = (M * cb + 63) / 64;      // + the bias gradient's blocks (same launch)
     dw_reduce_kernel<<<main_blocks + (with_db ? (M + 63) / 64 : 0), kDwReduceThreads, 0, t.st>>>(t.ws.partial, split, Mp, M, Nb, cb, sc, dst, ld, col0 + nb,
                                                                                                 main_blocks, with_db ? t.ws.cs_partial : nullptr, db);
@@ -459,6 +469,7 @@ static Planes view(const Planes& p, int cols, int64_t rows) { Planes v = p; v.co
 
 static int backward_pass(TrainCtx& t, int p, const Grads& G) {
   const TrainCfg& c = t.c;
+  t.rev = 1;                       // head_bwd_kernel wrote the first dY front to back
   PassWs& w = t.ws.pass[p];
   const TNet& net = t.net[p];
   const int nl = net.nl;
@@ -496,7 +507,8 @@ static int backward_pass(TrainCtx& t, int p, const Grads& G) {
       a.a[0] = dy; a.b[0] = t.ws.w[p].aux[l]; a.n_src = 1; a.b_mn = 1; a.N = 64; a.passes = c.passes; a.epi = GEPI_F32;
       a.out_f32 = L.aux == 1 ? t.ws.g_encx : t.ws.g_encd; a.out_f32_ld = 64; a.accumulate = (L.aux == 1 && encx_written) ? 1 : 0;
       a.sc_in = sc;
-      TRY(launch_tile_gemm(a, t.n_sms, t.st));
+      a.reverse = t.rev & sweep_alternates(); t.rev ^= 1;
+    TRY(launch_tile_gemm(a, t.n_sms, t.st));
       if (L.aux == 1) encx_written = true;
     }
     // dX -> the previous layer's dY (ReLU' of the previous layer fused; + the sigma head's rank-1 term below the dir layer)
@@ -511,7 +523,8 @@ static int backward_pass(TrainCtx& t, int p, const Grads& G) {
       if (Pv.relu) { a.mask_bits = w.bits[l - 1]; a.bits_ld = Pv.n_out / 32; }
       if (dir) { a.row_scale = w.g_raw + 3; a.row_scale_ld = 4; a.col_vec = t.par[p][2 * nl + 2]; }
       a.sc_in = sc; a.sc_out = SC(slot + 1); a.l1max = MX(slot + 1); a.status = t.io.status;
-      TRY(launch_tile_gemm(a, t.n_sms, t.st));
+      a.reverse = t.rev & sweep_alternates(); t.rev ^= 1;
+    TRY(launch_tile_gemm(a, t.n_sms, t.st));
       cur ^= 1;
       ++slot;
     }
