@@ -356,27 +356,33 @@ def measure(a, w, pipe, rank, world, dev, clocks=True):
         ms_steps = [x.elapsed_time(y) for x, y in ev]
         # ---------------- end to end through the public API: host inputs, H2D + D2H inside the timed region
         host_img = torch.empty(n_total if world > 1 else rays, 3).pin_memory()
-        # the host->device copy of step i + 1 is issued on a copy stream while step i renders (what a serving loop does); every copy,
-        # including the exposed first one, starts after f0 and is waited for before f1
+        # the host->device copy of step i + 1 is issued on a copy stream while step i renders (what a serving loop does), into two
+        # preallocated sets of device buffers (allocating the inputs per step on the side stream made the caching allocator cudaMalloc
+        # in the middle of short runs); every copy, including the exposed first one, starts after f0 and is waited for before f1
         copy_stream = torch.cuda.Stream(dev)
+        bufs = [[torch.empty_like(t, device=dev) for t in views_host[0]] for _ in range(2)]
+        consumed = [None, None]          # event: the render that read buffer set k has finished
 
-        def h2d(v):
+        def h2d(v, k):
             with torch.cuda.stream(copy_stream):
-                d = [t.to(dev, non_blocking=True) for t in views_host[v % n_views]]
+                if consumed[k] is not None:
+                    copy_stream.wait_event(consumed[k])
+                for dst, src in zip(bufs[k], views_host[v % n_views]):
+                    dst.copy_(src, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(copy_stream)
-            return d, ready
+            return bufs[k], ready
 
         def e2e_loop(n, v0):
-            nxt = h2d(v0)
+            nxt = h2d(v0, 0)
             for i in range(n):
                 data, ready = nxt
                 if i + 1 < n:
-                    nxt = h2d(v0 + i + 1)
+                    nxt = h2d(v0 + i + 1, (i + 1) % 2)
                 stream.wait_event(ready)
-                for t in data:
-                    t.record_stream(stream)
                 host_img.copy_(step(data), non_blocking=True)
+                consumed[i % 2] = torch.cuda.Event()
+                consumed[i % 2].record(stream)
 
         e2e_loop(3, 0)
         barrier()
