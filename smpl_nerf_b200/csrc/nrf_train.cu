@@ -445,8 +445,15 @@ static int colsum_and_bias(TrainCtx& t, const Planes& dy, const float* sc, int F
 }
 
 static int rayfeat_dw(TrainCtx& t, const float* sc, const float* feat, int n_out, int K, float* dW, int ld, int col0) {
-  rayfeat_dw_kernel<<<dim3((K + 15) / 16, (n_out + 15) / 16), 256, 0, t.st>>>(t.ws.dysum, feat, t.c.B, n_out, K, sc, dW, ld, col0);
+  // partial sums per ray slice into the dW scratch (n_out * K <= 512 * 1,408 floats per slice fits its 148 x 128 x 256), then the fixed-order reduce
+  const size_t cap = static_cast<size_t>(148) * 128 * 256, per = static_cast<size_t>(n_out) * K;
+  if (per > cap) { set_error("train: per-ray input block %d x %d too large", n_out, K); return NRF_E_INVALID; }
+  const int slices = static_cast<int>(cap / per < static_cast<size_t>(kRayFeatSlices) ? cap / per : kRayFeatSlices);
+  rayfeat_dw_kernel<<<dim3((K + 15) / 16, (n_out + 15) / 16, slices), 256, 0, t.st>>>(t.ws.dysum, feat, t.c.B, n_out, K, t.ws.partial);
   LAUNCH_CHECK("rayfeat_dw_kernel");
+  const int main_blocks = static_cast<int>((per + 63) / 64);
+  dw_reduce_kernel<<<main_blocks, kDwReduceThreads, 0, t.st>>>(t.ws.partial, slices, n_out, n_out, K, K, sc, dW, ld, col0, main_blocks, nullptr, nullptr);
+  LAUNCH_CHECK("dw_reduce_kernel");
   return NRF_OK;
 }
 

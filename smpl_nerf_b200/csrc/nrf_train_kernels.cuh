@@ -461,28 +461,33 @@ __global__ void __launch_bounds__(1024) bias_grad_kernel(const float* __restrict
     db[f] += t * __ldg(scale2 + 1);
   }
 }
-// dW[n, col0 + k] += inv_scale * sum_b dysum[b, n] feat[b, k]      (16 x 16 output tile per CTA, rays in steps of 64 via smem)
+// partial[z][n][k] = sum over the rays of slice z of dysum[b, n] feat[b, k]      (16 x 16 output tile per CTA, rays in steps of 64 via smem;
+// gridDim.z ray slices -- 48 CTAs walking all rays were latency bound -- summed in a fixed order by dw_reduce_kernel, which also divides
+// the gradient scale out and accumulates into dW[n, col0 + k])
+constexpr int kRayFeatSlices = 8;
 __global__ void __launch_bounds__(256) rayfeat_dw_kernel(const float* __restrict__ dysum, const float* __restrict__ feat, int64_t B, int n_out, int K,
-                                                         const float* __restrict__ scale2, float* __restrict__ dW, int ld, int col0) {
+                                                         float* __restrict__ partial) {
   constexpr int R = 64;
   __shared__ float ys[R][17], fs[R][17];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int k = blockIdx.x * 16 + tx, n = blockIdx.y * 16 + ty;
   const int nl = blockIdx.y * 16 + tx;                      // the dysum column this thread loads
+  const int64_t per = (B + gridDim.z - 1) / gridDim.z;
+  const int64_t b_lo = per * blockIdx.z, b_hi = b_lo + per < B ? b_lo + per : B;
   float acc0 = 0.f, acc1 = 0.f;
-  for (int64_t b0 = 0; b0 < B; b0 += R) {
+  for (int64_t b0 = b_lo; b0 < b_hi; b0 += R) {
 #pragma unroll
     for (int j = 0; j < R / 16; ++j) {
       const int64_t b = b0 + ty + 16 * j;
-      ys[ty + 16 * j][tx] = (b < B && nl < n_out) ? dysum[b * n_out + nl] : 0.f;
-      fs[ty + 16 * j][tx] = (b < B && k < K) ? feat[b * K + k] : 0.f;
+      ys[ty + 16 * j][tx] = (b < b_hi && nl < n_out) ? dysum[b * n_out + nl] : 0.f;
+      fs[ty + 16 * j][tx] = (b < b_hi && k < K) ? feat[b * K + k] : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < R; r += 2) { acc0 = fmaf(ys[r][ty], fs[r][tx], acc0); acc1 = fmaf(ys[r + 1][ty], fs[r + 1][tx], acc1); }
     __syncthreads();
   }
-  if (k < K && n < n_out) dW[static_cast<size_t>(n) * ld + col0 + k] += (acc0 + acc1) * __ldg(scale2 + 1);
+  if (k < K && n < n_out) partial[(static_cast<size_t>(blockIdx.z) * n_out + n) * K + k] = acc0 + acc1;
 }
 // dst[m, col0 + c] += inv_scale * sum_split partial[split][m][c]        (m < M <= Mp rows of the partials, c < cols <= N)
 // and, in the blocks past the first `main_blocks`, db[m] += inv_scale * sum_split cs_partial[split][m] (the ones-column of dw_gemm).
