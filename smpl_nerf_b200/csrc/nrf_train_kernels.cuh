@@ -229,7 +229,7 @@ __global__ void heads_kernel(const float* __restrict__ x, int64_t S, int K, cons
 //   dW[c, k] += sum_s g[s, c] x[s, k]      db[c] += sum_s g[s, c]      dY[s, k] = sum_c g[s, c] W[c, k]   (-> planes, masked by x > 0)
 // g is the upstream gradient in REAL units (fp32); the planes are written as real * sc_out[0].  l1max: see TileGemmParams (here the
 // row segment is a warp's 128 columns).
-__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ x, int64_t S, int K, const float* __restrict__ g, int g_ld, int c0, int nh,
+__global__ void __launch_bounds__(256, 3) head_bwd_kernel(const float* __restrict__ x, int64_t S, int K, const float* __restrict__ g, int g_ld, int c0, int nh,
                                                        const float* __restrict__ W, const float* __restrict__ sc_out, int relu_mask,
                                                        float* __restrict__ dW, float* __restrict__ db, __half* __restrict__ dy_hi,
                                                        __half* __restrict__ dy_lo, int dy_ld, int rows_per_block, unsigned int* __restrict__ l1max) {
@@ -290,10 +290,12 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       }
     }
   };
-  for (int it = 0; it * n_rg < rows_per_block; it += 2) {   // uniform trip count: the warp shuffles need every lane
-    const Row ra = fetch(it), rb = fetch(it + 1);
+  for (int it = 0; it * n_rg < rows_per_block; it += 4) {   // uniform trip count: the warp shuffles need every lane; 4 rows in flight
+    const Row ra = fetch(it), rb = fetch(it + 1), rc = fetch(it + 2), rd = fetch(it + 3);
     consume(ra);
     consume(rb);
+    consume(rc);
+    consume(rd);
   }
   if (l1max && isfinite(l1_run)) {
 #pragma unroll
