@@ -361,6 +361,35 @@ def test_eval_mode_and_no_grad_stay_on_the_fused_kernel():
         engine.render('nerf', gnets[0], gnets[1], None, args, gnets[3], gnets[4], None, gdata, trace_cap=16)
 
 
+def test_gradients_are_linear_in_the_batch_at_full_size():
+    """Size-independent property at the training workload's full size (2,048 rays, 64 + 128 samples, 8x256 nets + warp net, where the
+    CPU oracle would take minutes): the loss is a mean over rays, so the gradient of the whole batch equals the mean of the gradients
+    of its two halves (different tile counts, different per-layer gradient scales, different dW split counts)."""
+    nets = _build('smpl', 11)
+    args = O.make_args(number_fine_samples=128)
+    rays = scene.make_rays(64, 32, 64, seed=3, with_colours=True, arm_angle_deg=40.0)
+    data = scene.data_list(rays, 'smpl')
+    gnets, gdata = H.to_cuda(nets, data)
+    for m in gnets[:3]:
+        m.train()
+    pipe = _pipe('smpl', gnets, args)
+    params = [p for m in gnets[:3] for p in m.parameters()]
+    names = [f'{k}.{n}' for k, m in zip(('coarse', 'fine', 'warp'), gnets[:3]) for n, _ in m.named_parameters()]
+
+    def grads(sl):
+        for p in params:
+            p.grad = None
+        d = [t[sl] for t in gdata]
+        _loss(pipe(d), d[-1]).backward()
+        return [p.grad.double() for p in params]
+
+    full, a, b = grads(slice(0, 2048)), grads(slice(0, 1024)), grads(slice(1024, 2048))
+    for n, f, x, y in zip(names, full, a, b):
+        want = 0.5 * (x + y)
+        err = float((f - want).norm() / (want.norm() + 1e-30))
+        assert err <= 2e-4, f'{n}: |grad(batch) - mean(grad(halves))| / |.| = {err:.2e}'
+
+
 def test_workspace_cache_and_two_live_graphs():
     """The training workspace is cached per device between steps.  A second forward issued while the first graph is still alive
     must not share it; a backward may run only once; a graph that is dropped without a backward hands the buffer back."""
